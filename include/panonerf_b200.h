@@ -1,0 +1,189 @@
+/*
+ * panonerf_b200 — C ABI of the B200-native mip-NeRF volumetric-rendering hot path of Pano-NeRF.
+ *
+ * This is the drop-in boundary.  The reference has no FFI: its "operator API" for this path is
+ * the Python function surface of models/mip.py, models/{mip_nerf,pano_mip_nerf}.py and
+ * utils/surface_rendering.py.  Each entry point below replaces the arithmetic of the reference function cited
+ * beside it; the Python host (panonerf_b200/models/*.py) keeps the reference's names and signatures and calls
+ * these through ctypes (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer (sm_100a, current device) unless the comment says "host";
+ *   - tensors are contiguous row-major; `ld*` arguments are row strides in ELEMENTS;
+ *   - fp32 unless a `dtype` argument says otherwise (PNB_F32 / PNB_BF16);
+ *   - nothing here allocates device memory: outputs and workspaces are caller-owned;
+ *   - `stream` is a cudaStream_t passed as void*; kernels are launched asynchronously on it;
+ *   - return value: 0 on success, otherwise a cudaError_t value (or PNB_ERR_ARG) — pnb_last_error() gives text.
+ *   - there is NO CPU fallback anywhere behind this ABI.
+ */
+#ifndef PANONERF_B200_H_
+#define PANONERF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PNB_ABI_VERSION 1
+#define PNB_F32 0
+#define PNB_BF16 1
+#define PNB_ERR_ARG 10001
+
+/* epilogue flags of the GEMM entry points */
+#define PNB_EPI_BIAS 1       /* C += bias[n]                                                       */
+#define PNB_EPI_RELU 2       /* C = max(C, 0)                                                      */
+#define PNB_EPI_MASK 4       /* C = mask_src[m,n] > 0 ? C : 0   (ReLU backward / Jacobian chain)   */
+#define PNB_EPI_ACCUM 8      /* C += previous C (fp32 outputs only)                                */
+
+int pnb_abi_version(void);
+const char* pnb_last_error(void);
+/* number of kernels this library has launched since load (bench.py's `gpu_launches`). */
+long long pnb_launch_count(void);
+
+/* ---- K1  equirectangular ray generation: datasets/pano_datasets.py:152-216 -------------------------------
+ * rows [row0,row0+nrows) of an H x W panorama; c2w = 12 floats (3x4 row-major, HOST pointer).
+ * Outputs are [nrows*W, 3] / [nrows*W, 1] blocks of the 8 `Rays` fields (datasets/base_datasets.py:13-16). */
+int pnb_raygen_equirect(int H, int W, int row0, int nrows, const float* c2w_host, float near_v, float far_v,
+                        float* origins, float* directions, float* viewdirs, float* radii, float* lossmult,
+                        float* near_o, float* far_o, float* noise_var, void* stream);
+
+/* ---- K2  stratified sampling + conical-frustum Gaussians: models/mip.py:113-151, 154-194, 67-89, 36-58, 8-22
+ * ray r uses origins[r / o_div] and directions|radii|near|far[(d_mod ? r % d_mod : r)]
+ * (main rays: o_div=1,d_mod=0; env rays of sample_each_points: o_div=D,d_mod=D).
+ * s_lin = torch.linspace(0,1,N+1); t_rand (nullable) has row stride rand_ld (0 = one row shared by all rays). */
+int pnb_sample_cast(int R, int N, const float* origins, int o_div, const float* directions, const float* radii,
+                    const float* near_v, const float* far_v, int d_mod, const float* s_lin, const float* t_rand,
+                    int rand_ld, int disparity, float* t_out, float* means, float* covs, void* stream);
+/* cast_rays on given fence-posts t[R,N+1] (after resampling): models/mip.py:67-89 */
+int pnb_cast_rays(int R, int N, const float* t, const float* origins, int o_div, const float* directions,
+                  const float* radii, int d_mod, float* means, float* covs, void* stream);
+
+/* ---- integrated positional encoding: models/mip.py:394-428 + 355-361 ; pos_enc: models/mip.py:431-441 -----
+ * enc row = [sin(3L) | cos(3L)], L = max_deg-min_deg, written at enc + m*ld with element type `dtype`. */
+int pnb_ipe_fwd(int M, const float* means, const float* covs, int min_deg, int max_deg, void* enc, int ld,
+                int dtype, void* stream);
+/* d_means[m,c] = sum_f d_enc[m,f] * d enc_f / d mean_c   (vector-Jacobian product, used for normals and for
+ * the env-branch gradient into the surface point) */
+int pnb_ipe_vjp(int M, const float* means, const float* covs, int min_deg, int max_deg, const void* d_enc,
+                int ld, int dtype, float* d_means, void* stream);
+/* out[m,f] = sum_c (d enc_f / d mean_c) * v[m,c]   (Jacobian-vector product: the adjoint of pnb_ipe_vjp) */
+int pnb_ipe_jvp(int M, const float* means, const float* covs, int min_deg, int max_deg, const float* v,
+                void* out, int ld, int dtype, void* stream);
+int pnb_pos_enc(int R, const float* x, int deg, float* out, void* stream);
+
+/* ---- activations of compute_graph: models/pano_mip_nerf.py:264-278, models/mip_nerf.py:238-241 ------------
+ * raw_den is [M,C] (C=1 mipnerf, C=5 panonerf: sigma | albedo(3) | roughness).  sp1 (nullable) receives
+ * softplus'(raw_den[:,0]+bias) which the normals need. */
+int pnb_act_fwd(int M, int C, const float* raw_rgb, const float* raw_den, float density_bias, float rgb_padding,
+                float* rgb, float* density, float* albedo, void* stream);
+int pnb_act_bwd(int M, int C, const float* raw_rgb, const float* raw_den, float density_bias, float rgb_padding,
+                const float* d_rgb, const float* d_density, const float* d_albedo, float* d_raw_rgb,
+                float* d_raw_den, void* stream);
+/* normals_raw = -softplus'(raw0+bias) * v ; and its backward (models/pano_mip_nerf.py:299-302) */
+int pnb_density_grad_fwd(int M, int C, const float* raw_den, float density_bias, const float* v, float* n_raw,
+                         void* stream);
+int pnb_density_grad_bwd(int M, int C, const float* raw_den, float density_bias, const float* v,
+                         const float* d_n_raw, float* d_raw0, float* d_v, void* stream);
+
+/* ---- K6  alpha compositing: models/mip.py:444-483 ---------------------------------------------------------
+ * density is [R,N] (channel 0 already selected); dirs[(d_mod ? r % d_mod : r)]. */
+int pnb_composite_fwd(int R, int N, const float* rgb, const float* density, const float* t, const float* dirs,
+                      int d_mod, int white_bkgd, float* comp_rgb, float* distance, float* acc, float* weights,
+                      void* stream);
+int pnb_composite_bwd(int R, int N, const float* rgb, const float* density, const float* t, const float* dirs,
+                      int d_mod, int white_bkgd, const float* g_comp, const float* g_dist, const float* g_acc,
+                      const float* g_weights, float* d_rgb, float* d_density, void* stream);
+
+/* ---- K7  hierarchical resampling: models/mip.py:304-352 (blur-pool) + 240-301 (PDF/CDF/searchsorted/lerp) --
+ * u: [N+1] when u_ld==0 (deterministic linspace(0,1-eps,N+1)) or [R,N+1] (u_ld=N+1, randomized).
+ * inds (nullable) receives torch.searchsorted(cdf,u,right=True) as int64 — bit-exact contract.
+ * blur_pool=0 skips the blur-pool/padding step (plain sorted_piecewise_constant_pdf on the given weights). */
+int pnb_resample(int R, int N, const float* t, const float* weights, float padding, int blur_pool, const float* u,
+                 int u_ld, float* new_t, long long* inds, void* stream);
+
+/* ---- normals / orientation loss / albedo compositing: models/pano_mip_nerf.py:296-317 ---------------------- */
+int pnb_normals_fwd(int R, int N, const float* n_raw, const float* weights, const float* dirs,
+                    const float* albedos, float* normal, float* ort, float* albedo, void* stream);
+int pnb_normals_bwd(int R, int N, const float* n_raw, const float* weights, const float* dirs,
+                    const float* albedos, const float* g_normal, const float* g_ort, const float* g_albedo,
+                    float* d_n_raw, float* d_weights, float* d_albedos, void* stream);
+
+/* ---- surface point + Lambertian shading: models/pano_mip_nerf.py:321-324, utils/surface_rendering.py:104-165 */
+int pnb_surface_point_fwd(int R, const float* origins, const float* dirs, const float* dist, float* pts,
+                          void* stream);
+/* d_dist[r] = dirs[r] . sum_k d_means[r,k,:]   (k runs over the D*Ne env samples of ray r) */
+int pnb_surface_point_bwd(int R, int K, const float* dirs, const float* d_means, float* d_dist, void* stream);
+int pnb_shade_fwd(int R, int D, const float* env_rgb, const float* albedo, const float* normal,
+                  const float* light_dirs, const float* solid_angle, float* surface_rgb, float* shading,
+                  void* stream);
+int pnb_shade_bwd(int R, int D, const float* env_rgb, const float* albedo, const float* normal,
+                  const float* light_dirs, const float* solid_angle, const float* g_rgb, const float* g_shading,
+                  float* d_env, float* d_albedo, float* d_normal, void* stream);
+
+/* ---- tone mapping + losses: utils/surface_rendering.py:319-344, systems/panonerf_system.py:39-67 ---------- */
+int pnb_hdr_to_ldr(long long n, const float* x, int quantize_u8, float* out, void* stream);
+/* partial[r] = mask[r] * sum_c (ldr(pred[r,c]) - gt[r,c])^2 ; d_pred = scale * mask * 2 (ldr-gt) * ldr'  */
+int pnb_tonemap_se_fwd(int R, const float* pred, const float* gt_ldr, const float* mask, float* partial,
+                       void* stream);
+int pnb_tonemap_se_bwd(int R, const float* pred, const float* gt_ldr, const float* mask, const float* g_scale,
+                       float* d_pred, void* stream);
+/* partial[r] = sum_c (normalize(gt)[r,c] - normalize(alb)[r,c])^2 */
+int pnb_chroma_fwd(int R, const float* gt_ldr, const float* albedo, float* partial, void* stream);
+int pnb_chroma_bwd(int R, const float* gt_ldr, const float* albedo, const float* g_scale, float* d_albedo,
+                   void* stream);
+/* deterministic sum of n floats -> out[0] (two-pass, workspace ws >= 1024 floats) */
+int pnb_sum(long long n, const float* x, float scale, float* out, float* ws, void* stream);
+
+/* ---- K10  fused Adam on the flat parameter buffer: systems/base_system.py:81-87 ---------------------------
+ * g is multiplied by grad_scale first (1/world_size after the NCCL sum). step is 1-based. */
+int pnb_adam_step(long long n, float* p, const float* g, float* m, float* v, float lr, float beta1, float beta2,
+                  float eps, int step, float grad_scale, void* stream);
+
+/* ---- element-wise helpers of the MLP backward ------------------------------------------------------------- */
+/* out[m,n] = src[m,n] > 0 ? w[n]*g[m] : 0   (seed of the density-Jacobian chain; g nullable => 1) */
+int pnb_mask_scale(long long M, int N, const void* src, int ld_src, const float* w, const float* g, void* out,
+                   int ld_out, int dtype, void* stream);
+/* out = src>0 ? x : 0 */
+int pnb_mask_mul(long long M, int N, const void* x, int ldx, const void* src, int ld_src, void* out, int ld_out,
+                 int dtype, void* stream);
+/* out[n] (+)= sum_m x[m,n] (fp32 out, atomic accumulate into pre-zeroed/accumulating buffer) */
+int pnb_colsum(long long M, int N, const void* x, int ldx, int dtype, float* out, void* stream);
+/* dtype conversion with strides (fp32 <-> bf16) */
+int pnb_convert(long long M, int N, const void* src, int ld_src, int src_dtype, void* dst, int ld_dst,
+                int dst_dtype, void* stream);
+
+/* ---- K3/K4/K5  MLP GEMMs: models/pano_mip_nerf.py:78-114 (forward) and its hand-derived backward ----------
+ * fp32 SIMT path ("parity mode"): C[M,N] = op(A) * op(B) with
+ *   mode 0 (NT, forward)  : A[M,K] (lda) , B = W[N,K] (ldb)          -> C[M,N]
+ *   mode 1 (NN, dgrad)    : A[M,K] (lda) , B = W[K,N] (ldb)          -> C[M,N]
+ *   mode 2 (TN, wgrad)    : A[K,M] (lda) , B[K,N] (ldb), K = samples -> C[M,N]   (C is accumulated atomically)
+ * epilogue: PNB_EPI_* flags; bias[N]; row_bias [M/row_group, N] (nullable); mask_src [M,N] (ld_mask). */
+int pnb_gemm_f32(int mode, long long M, int N, long long K, const float* A, int lda, const float* B, int ldb,
+                 float* C, int ldc, const float* bias, const float* row_bias, int row_group, const float* mask_src,
+                 int ld_mask, int flags, void* stream);
+
+/* bf16 tensor-core path (tcgen05.mma, TMEM accumulators, TMA-fed):
+ * C[M,Nout] = A[M,K](bf16, lda) * W[Nout,K]^T (bf16, ldw) with fp32 accumulation; epilogue flags as above;
+ * C dtype = c_dtype (bf16 or fp32), bias fp32 [Nout], mask_src bf16 [M,Nout].  16 <= K <= 384 (K % 16 == 0).
+ * row_bias (nullable) is an fp32 [M/row_group, Nout] addend shared by each group of `row_group` consecutive rows
+ * (the per-ray view-direction term of the view layer, models/pano_mip_nerf.py:109-112).
+ * The same entry point serves forward (W) and dgrad (pre-transposed W^T). */
+int pnb_linear_tc(long long M, int Nout, int K, const void* A, int lda, const void* W, int ldw, void* C, int ldc,
+                  int c_dtype, const float* bias, const float* row_bias, int row_group, const void* mask_src,
+                  int ld_mask, int flags, void* stream);
+/* dW[Nw,Kw] (fp32, accumulated) += dZ[M,Nw]^T (bf16) * X[M,Kw] (bf16) ; reduction over the M samples.
+ * Nw in {128,256}; 16 <= Kw <= 256.  workspace: pnb_wgrad_tc_workspace(Nw,Kw) bytes (per-CTA partials, summed in a
+ * fixed order => deterministic). */
+long long pnb_wgrad_tc_workspace(int Nw, int Kw);
+int pnb_wgrad_tc(long long M, int Nw, int Kw, const void* dZ, int ldz, const void* X, int ldx, float* dW, int ldw,
+                 float* workspace, void* stream);
+/* out[g, n] = sum of the `group` consecutive rows of x belonging to group g (fp32 out [M/group, N]) */
+int pnb_group_sum(long long M, int N, int group, const void* x, int ldx, int dtype, float* out, void* stream);
+/* 1 when the tcgen05 path was compiled in and the device is sm_100 */
+int pnb_tc_available(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PANONERF_B200_H_ */

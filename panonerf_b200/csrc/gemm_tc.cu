@@ -1,0 +1,668 @@
+// K3/K4/K5: the MLP GEMMs on the 5th-generation tensor cores (sm_100a only).
+//
+//   pnb_linear_tc : C[M,Nout] = epi(A[M,K] * W[Nout,K]^T)   bf16 operands, fp32 accumulation in TMEM
+//   pnb_wgrad_tc  : dW[Nw,Kw] += dZ[M,Nw]^T * X[M,Kw]        reduction over the M samples
+//
+// Design (one persistent CTA per SM, warp-specialised, no CUTLASS):
+//   warp 0      TMA producer  : cp.async.bulk.tensor.2d tiles, 128B-swizzled, completing on mbarriers
+//   warp 1      MMA issuer    : one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N<=256, K=16)
+//                               straight from shared memory; accumulators live in TMEM (double-buffered)
+//   warps 2..5  epilogue      : tcgen05.ld 32x32b -> bias / ReLU / mask -> bf16|fp32 -> global
+// linear: the weight matrix is loaded ONCE per CTA and stays resident in shared memory (<=160 KB), only the
+// activation tiles (128 rows x 64 bf16) stream through a 3-4 stage ring, so HBM traffic is the algorithmic
+// minimum: read A once, write C once.  wgrad: both operands are "MN-major" (the reduction axis is the slow axis
+// in memory), which tcgen05 consumes directly through MN-major shared-memory descriptors - no transposes.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace pnb {
+namespace tc {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;  // bf16 elements = one 128-byte swizzle row
+constexpr int kATileBytes = kBlockM * kBlockK * 2;
+constexpr int kThreads = 192;
+constexpr int kMaxStages = 4;
+constexpr int kSmemLimit = 227 * 1024;
+
+// ---------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  const uint32_t addr = smem_u32(bar);
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem]; `accum` = 0 overwrites D.
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// arrive on `bar` once every tcgen05 op issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// 32 lanes x 32 consecutive fp32 columns: thread `lane` receives row (lane base + lane), columns [col, col+32)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout type [61,64) with SWIZZLE_128B = 2.
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= 1ull << 46;
+  d |= 2ull << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
+// a_major bit 15, b_major bit 16 (0 = K-major, 1 = MN-major), N>>3 [17,23), M>>4 [24,29).
+__host__ __device__ constexpr uint32_t instr_desc_bf16(int m, int n, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+struct Barriers {
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t w_full;
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint8_t* align_1024(uint8_t* p) {
+  return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~(uintptr_t)1023);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// linear: C = epi(A * W^T)
+// ---------------------------------------------------------------------------------------------------------------
+struct LinearParams {
+  long long M;
+  int Nout, K, num_kb, stages, tail_k16;
+  void* C;
+  int ldc, c_dtype;
+  const float* bias;
+  const float* row_bias;
+  int row_group;
+  const __nv_bfloat16* mask_src;
+  int ld_mask, flags;
+  long long num_m_tiles;
+};
+
+template <int BLOCK_N, typename OutT>
+__device__ __forceinline__ void store_row_chunk(const LinearParams& p, long long m, int n_base, float* v, int count) {
+  // v[0..count) are columns n_base.. of row m (already offset by the CTA's n0)
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    if (i >= count) break;
+    int n = n_base + i;
+    float x = v[i];
+    if (n < p.Nout) {
+      if (p.flags & PNB_EPI_BIAS) x += p.bias[n];
+      if (p.row_bias) x += p.row_bias[(m / p.row_group) * p.Nout + n];
+      if (p.flags & PNB_EPI_RELU) x = fmaxf(x, 0.f);
+    }
+    v[i] = x;
+  }
+  OutT* crow = reinterpret_cast<OutT*>(p.C) + m * p.ldc;
+  const bool full = n_base + count <= p.Nout;
+  if ((p.flags & PNB_EPI_MASK) != 0) {
+    const __nv_bfloat16* mrow = p.mask_src + m * p.ld_mask;
+    if (full && (p.ld_mask % 8 == 0) && (n_base % 8 == 0)) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        if (i >= count) break;
+        uint4 raw = *reinterpret_cast<const uint4*>(mrow + n_base + i);
+        const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&raw);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (!(__bfloat162float(h[j]) > 0.f)) v[i + j] = 0.f;
+      }
+    } else {
+      for (int i = 0; i < count; ++i)
+        if (n_base + i < p.Nout && !(__bfloat162float(mrow[n_base + i]) > 0.f)) v[i] = 0.f;
+    }
+  }
+  if (sizeof(OutT) == 2) {
+    if (full && (p.ldc % 8 == 0) && (n_base % 8 == 0)) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        if (i >= count) break;
+        __nv_bfloat162 h[4];
+        if (p.flags & PNB_EPI_ACCUM) {
+          uint4 prev = *reinterpret_cast<const uint4*>(reinterpret_cast<__nv_bfloat16*>(crow) + n_base + i);
+          const __nv_bfloat16* ph = reinterpret_cast<const __nv_bfloat16*>(&prev);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[i + j] += __bfloat162float(ph[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[i + 2 * j], v[i + 2 * j + 1]);
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(crow) + n_base + i) =
+            *reinterpret_cast<uint4*>(h);
+      }
+    } else {
+      for (int i = 0; i < count; ++i)
+        if (n_base + i < p.Nout) {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(crow) + n_base + i;
+          float x = v[i];
+          if (p.flags & PNB_EPI_ACCUM) x += __bfloat162float(*o);
+          *o = __float2bfloat16_rn(x);
+        }
+    }
+  } else {
+    float* frow = reinterpret_cast<float*>(crow);
+    if (full && (p.ldc % 4 == 0) && (n_base % 4 == 0)) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        if (i >= count) break;
+        float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        if (p.flags & PNB_EPI_ACCUM) {
+          float4 prev = *reinterpret_cast<float4*>(frow + n_base + i);
+          o.x += prev.x, o.y += prev.y, o.z += prev.z, o.w += prev.w;
+        }
+        *reinterpret_cast<float4*>(frow + n_base + i) = o;
+      }
+    } else {
+      for (int i = 0; i < count; ++i)
+        if (n_base + i < p.Nout) {
+          float o = v[i];
+          if (p.flags & PNB_EPI_ACCUM) o += frow[n_base + i];
+          frow[n_base + i] = o;
+        }
+    }
+  }
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kThreads, 1)
+linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, LinearParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_1024(smem_raw);
+  constexpr int kWTileBytes = BLOCK_N * kBlockK * 2;  // one k-block of the resident weight
+  uint8_t* smem_w = smem;
+  uint8_t* smem_a = smem + (size_t)p.num_kb * kWTileBytes;
+  Barriers* bars = reinterpret_cast<Barriers*>(smem_a + (size_t)p.stages * kATileBytes);
+  constexpr uint32_t kTmemCols = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;  // power of two for every BLOCK_N we use
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.y * BLOCK_N;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&bars->full[s], 1);
+      mbar_init(&bars->empty[s], 1);
+    }
+    mbar_init(&bars->w_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&bars->tmem_full[b], 1);
+      mbar_init(&bars->tmem_empty[b], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&bars->tmem_base, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(&bars->w_full, (uint32_t)(p.num_kb * kWTileBytes));
+      for (int kb = 0; kb < p.num_kb; ++kb)
+        tma_load_2d(smem_w + (size_t)kb * kWTileBytes, &tmW, &bars->w_full, kb * kBlockK, n0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&bars->empty[stage], phase ^ 1);
+          mbar_expect_tx(&bars->full[stage], kATileBytes);
+          tma_load_2d(smem_a + (size_t)stage * kATileBytes, &tmA, &bars->full[stage], kb * kBlockK,
+                      (int)(tile * kBlockM));
+          if (++stage == p.stages) stage = 0, phase ^= 1;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = instr_desc_bf16(kBlockM, BLOCK_N, 0, 0);
+      mbar_wait(&bars->w_full, 0);
+      tc_fence_after();
+      int stage = 0;
+      uint32_t phase = 0;
+      long long it = 0;
+      for (long long tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, ++it) {
+        const uint32_t buf = (uint32_t)(it & 1);
+        mbar_wait(&bars->tmem_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1));
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * BLOCK_N;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&bars->full[stage], phase);
+          tc_fence_after();
+          const int nk16 = (kb == p.num_kb - 1) ? p.tail_k16 : kBlockK / 16;
+          const uint32_t a_addr = smem_u32(smem_a + (size_t)stage * kATileBytes);
+          const uint32_t b_addr = smem_u32(smem_w + (size_t)kb * kWTileBytes);
+          for (int k = 0; k < nk16; ++k) {
+            // K-major, 128B swizzle: 8-row groups are 1024 B apart; a K=16 slice is 32 B further along the row
+            uint64_t ad = smem_desc_sw128(a_addr + k * 32, 16, 1024);
+            uint64_t bd = smem_desc_sw128(b_addr + k * 32, 16, 1024);
+            umma_f16(d_tmem, ad, bd, idesc, (uint32_t)((kb | k) != 0));
+          }
+          umma_commit(&bars->empty[stage]);
+          if (++stage == p.stages) stage = 0, phase ^= 1;
+        }
+        umma_commit(&bars->tmem_full[buf]);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;  // TMEM lane quadrant this warp may read
+    long long it = 0;
+    for (long long tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, ++it) {
+      const uint32_t buf = (uint32_t)(it & 1);
+      mbar_wait(&bars->tmem_full[buf], (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      const long long m = tile * kBlockM + q * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BLOCK_N;
+      constexpr int kChunk = BLOCK_N >= 32 ? 32 : 16;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += kChunk) {
+        float v[32];
+        if (kChunk == 32) tmem_ld32(taddr + c0, v); else tmem_ld16(taddr + c0, v);
+        if (m < p.M && n0 + c0 < p.Nout) {
+          if (p.c_dtype == PNB_BF16)
+            store_row_chunk<BLOCK_N, __nv_bfloat16>(p, m, n0 + c0, v, kChunk);
+          else
+            store_row_chunk<BLOCK_N, float>(p, m, n0 + c0, v, kChunk);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->tmem_empty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// wgrad: dW[Nw,Kw] += dZ^T X, both operands MN-major.  Each CTA reduces a contiguous slab of samples into TMEM
+// (Nw/128 accumulators of 128 x Kw fp32), then writes its partial to a workspace; a second kernel sums the
+// partials in a fixed order (deterministic) into the accumulating gradient buffer.
+// ---------------------------------------------------------------------------------------------------------------
+struct WgradParams {
+  long long M;
+  int Nw, Kw, n_halves, kw_chunks, stages;
+  long long rows_per_cta;
+  float* partial;  // [gridDim.x, Nw, Kw]
+};
+
+constexpr int kWgRows = 64;                          // samples per pipeline stage
+constexpr int kWgBoxBytes = kWgRows * kBlockK * 2;   // one 64x64 bf16 box = 8 KB
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmX, WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_1024(smem_raw);
+  const int z_chunks = p.n_halves * 2;  // 64-wide column chunks of dZ
+  const int stage_bytes = (z_chunks + p.kw_chunks) * kWgBoxBytes;
+  Barriers* bars = reinterpret_cast<Barriers*>(smem + (size_t)p.stages * stage_bytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row_begin = (long long)blockIdx.x * p.rows_per_cta;
+  long long row_end = row_begin + p.rows_per_cta;
+  if (row_end > p.M) row_end = p.M;
+  const int num_it = row_end > row_begin ? (int)((row_end - row_begin + kWgRows - 1) / kWgRows) : 0;
+  const int kw_pad = p.kw_chunks * 64;  // TMEM columns per accumulator
+  const uint32_t tmem_cols = 512;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmZ);
+    tma_prefetch_desc(&tmX);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&bars->full[s], 1);
+      mbar_init(&bars->empty[s], 1);
+    }
+    mbar_init(&bars->tmem_full[0], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&bars->tmem_base, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < num_it; ++it) {
+        mbar_wait(&bars->empty[stage], phase ^ 1);
+        mbar_expect_tx(&bars->full[stage], (uint32_t)stage_bytes);
+        uint8_t* base = smem + (size_t)stage * stage_bytes;
+        const int row = (int)(row_begin + (long long)it * kWgRows);
+        // slabs are multiples of 64 rows, so only the global tail is partial and TMA zero-fills it
+        for (int c = 0; c < z_chunks; ++c)
+          tma_load_2d(base + (size_t)c * kWgBoxBytes, &tmZ, &bars->full[stage], c * 64, row);
+        for (int c = 0; c < p.kw_chunks; ++c)
+          tma_load_2d(base + (size_t)(z_chunks + c) * kWgBoxBytes, &tmX, &bars->full[stage], c * 64, row);
+        if (++stage == p.stages) stage = 0, phase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = instr_desc_bf16(128, p.Kw, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < num_it; ++it) {
+        mbar_wait(&bars->full[stage], phase);
+        tc_fence_after();
+        const uint32_t base = smem_u32(smem + (size_t)stage * stage_bytes);
+        const uint32_t x_addr = base + z_chunks * kWgBoxBytes;
+#pragma unroll 1
+        for (int k = 0; k < kWgRows / 16; ++k) {
+          // MN-major, 128B swizzle: 64-element column chunks are one box (8 KB) apart (LBO), 8-sample groups are
+          // 1024 B apart (SBO); a K=16 slice (16 samples) starts 2048 B further.
+          uint64_t bd = smem_desc_sw128(x_addr + k * 2048, kWgBoxBytes, 1024);
+          for (int h = 0; h < p.n_halves; ++h) {
+            uint64_t ad = smem_desc_sw128(base + h * 2 * kWgBoxBytes + k * 2048, kWgBoxBytes, 1024);
+            umma_f16(tmem_base + h * kw_pad, ad, bd, idesc, (uint32_t)((it | k) != 0));
+          }
+        }
+        umma_commit(&bars->empty[stage]);
+        if (++stage == p.stages) stage = 0, phase ^= 1;
+      }
+      umma_commit(&bars->tmem_full[0]);
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    mbar_wait(&bars->tmem_full[0], 0);
+    tc_fence_after();
+    float* out = p.partial + (size_t)blockIdx.x * p.Nw * p.Kw;
+    for (int h = 0; h < p.n_halves; ++h) {
+      const int n = h * 128 + q * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + h * kw_pad;
+#pragma unroll 1
+      for (int c0 = 0; c0 < p.Kw; c0 += 32) {
+        float v[32];
+        tmem_ld32(taddr + c0, v);
+        if (num_it == 0) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        }
+        if (n < p.Nw) {
+          float* orow = out + (size_t)n * p.Kw + c0;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            if (c0 + i < p.Kw) *reinterpret_cast<float4*>(orow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+__global__ void wgrad_reduce_kernel(int parts, int Nw, int Kw, const float* __restrict__ partial,
+                                    float* __restrict__ dW, int ldw) {
+  const int total = Nw * Kw;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int c = 0; c < parts; ++c) s += partial[(size_t)c * total + i];
+    int n = i / Kw, k = i - n * Kw;
+    dW[(size_t)n * ldw + k] += s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map: `cols` contiguous elements per row, `rows` rows, row pitch `ld` elements, 128B swizzle.
+static bool make_map(CUtensorMap* out, const void* base, unsigned long long rows, unsigned long long cols,
+                     unsigned long long ld, unsigned box_cols, unsigned box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (enc == nullptr) {
+    set_error_msg("cuTensorMapEncodeTiled not available from the driver");
+    return false;
+  }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[160];
+    snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled failed (%d): rows=%llu cols=%llu ld=%llu box=%ux%u", (int)r, rows,
+             cols, ld, box_cols, box_rows);
+    set_error_msg(msg);
+    return false;
+  }
+  return true;
+}
+
+template <int BLOCK_N>
+static int launch_linear(const CUtensorMap& tmA, const CUtensorMap& tmW, const LinearParams& p, int grid_y,
+                         size_t smem_bytes, cudaStream_t st) {
+  auto kern = linear_tc_kernel<BLOCK_N>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  if (e != cudaSuccess) {
+    set_error("linear_tc(smem attr)", e);
+    return (int)e;
+  }
+  long long gx = p.num_m_tiles < kNumSMs / grid_y ? p.num_m_tiles : kNumSMs / grid_y;
+  if (gx < 1) gx = 1;
+  dim3 grid((unsigned)gx, (unsigned)grid_y, 1);
+  kern<<<grid, kThreads, smem_bytes, st>>>(tmA, tmW, p);
+  return finish("linear_tc");
+}
+
+}  // namespace tc
+}  // namespace pnb
+
+using namespace pnb;
+using namespace pnb::tc;
+
+extern "C" int pnb_tc_available(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 0;
+  return prop.major == 10 ? 1 : 0;
+}
+
+extern "C" int pnb_linear_tc(long long M, int Nout, int K, const void* A, int lda, const void* W, int ldw, void* C,
+                             int ldc, int c_dtype, const float* bias, const float* row_bias, int row_group,
+                             const void* mask_src, int ld_mask, int flags, void* stream) {
+  PNB_REQUIRE(M >= 0 && Nout >= 1 && Nout <= 512 && K >= 16 && K <= 384 && K % 16 == 0,
+              "linear_tc: need 1<=Nout<=512, 16<=K<=384, K%16==0");
+  PNB_REQUIRE(lda % 8 == 0 && ldw % 8 == 0 && ((uintptr_t)A % 16 == 0) && ((uintptr_t)W % 16 == 0),
+              "linear_tc: A/W rows must be 16-byte aligned (ld % 8 == 0)");
+  PNB_REQUIRE(!(flags & PNB_EPI_BIAS) || bias, "linear_tc: bias flag without bias");
+  PNB_REQUIRE(!(flags & PNB_EPI_MASK) || mask_src, "linear_tc: mask flag without mask source");
+  PNB_REQUIRE(row_bias == nullptr || row_group > 0, "linear_tc: row_bias needs row_group");
+  if (M == 0) return 0;
+  LinearParams p;
+  p.M = M, p.Nout = Nout, p.K = K;
+  p.num_kb = (K + kBlockK - 1) / kBlockK;
+  p.tail_k16 = (K - (p.num_kb - 1) * kBlockK) / 16;
+  p.C = C, p.ldc = ldc, p.c_dtype = c_dtype;
+  p.bias = bias, p.row_bias = row_bias, p.row_group = row_group;
+  p.mask_src = (const __nv_bfloat16*)mask_src, p.ld_mask = ld_mask, p.flags = flags;
+  p.num_m_tiles = (M + kBlockM - 1) / kBlockM;
+  // smallest tile width covering Nout whose resident weight leaves room for >= 3 activation stages
+  int bn = Nout <= 16 ? 16 : Nout <= 32 ? 32 : Nout <= 64 ? 64 : Nout <= 128 ? 128 : 256;
+  auto smem_need = [&](int bn_, int stages) {
+    return (size_t)p.num_kb * bn_ * kBlockK * 2 + (size_t)stages * kATileBytes + sizeof(Barriers) + 1024;
+  };
+  while (bn > 16 && smem_need(bn, 3) > (size_t)kSmemLimit) bn /= 2;
+  p.stages = smem_need(bn, 4) <= (size_t)kSmemLimit ? 4 : 3;
+  PNB_REQUIRE(smem_need(bn, p.stages) <= (size_t)kSmemLimit, "linear_tc: weight does not fit shared memory");
+  int grid_y = (Nout + bn - 1) / bn;
+  size_t smem_bytes = smem_need(bn, p.stages);
+  CUtensorMap tmA, tmW;
+  if (!make_map(&tmA, A, (unsigned long long)M, (unsigned long long)K, (unsigned long long)lda, kBlockK, kBlockM))
+    return PNB_ERR_ARG;
+  if (!make_map(&tmW, W, (unsigned long long)Nout, (unsigned long long)K, (unsigned long long)ldw, kBlockK, bn))
+    return PNB_ERR_ARG;
+  cudaStream_t st = as_stream(stream);
+  switch (bn) {
+    case 16: return launch_linear<16>(tmA, tmW, p, grid_y, smem_bytes, st);
+    case 32: return launch_linear<32>(tmA, tmW, p, grid_y, smem_bytes, st);
+    case 64: return launch_linear<64>(tmA, tmW, p, grid_y, smem_bytes, st);
+    case 128: return launch_linear<128>(tmA, tmW, p, grid_y, smem_bytes, st);
+    default: return launch_linear<256>(tmA, tmW, p, grid_y, smem_bytes, st);
+  }
+}
+
+extern "C" long long pnb_wgrad_tc_workspace(int Nw, int Kw) { return (long long)kNumSMs * Nw * Kw * 4; }
+
+extern "C" int pnb_wgrad_tc(long long M, int Nw, int Kw, const void* dZ, int ldz, const void* X, int ldx, float* dW,
+                            int ldw, float* workspace, void* stream) {
+  PNB_REQUIRE(M >= 0 && (Nw == 128 || Nw == 256) && Kw >= 16 && Kw <= 256 && Kw % 16 == 0,
+              "wgrad_tc: need Nw in {128,256}, 16<=Kw<=256, Kw%16==0");
+  PNB_REQUIRE(ldz % 8 == 0 && ldx % 8 == 0 && ((uintptr_t)dZ % 16 == 0) && ((uintptr_t)X % 16 == 0),
+              "wgrad_tc: operand rows must be 16-byte aligned");
+  PNB_REQUIRE(workspace != nullptr, "wgrad_tc: workspace required (pnb_wgrad_tc_workspace bytes)");
+  if (M == 0) return 0;
+  WgradParams p;
+  p.M = M, p.Nw = Nw, p.Kw = Kw;
+  p.n_halves = Nw / 128;
+  p.kw_chunks = (Kw + 63) / 64;
+  int stage_bytes = (p.n_halves * 2 + p.kw_chunks) * kWgBoxBytes;
+  p.stages = 4;
+  while (p.stages > 2 && (size_t)p.stages * stage_bytes + sizeof(Barriers) + 1024 > (size_t)kSmemLimit) --p.stages;
+  size_t smem_bytes = (size_t)p.stages * stage_bytes + sizeof(Barriers) + 1024;
+  PNB_REQUIRE(smem_bytes <= (size_t)kSmemLimit, "wgrad_tc: tile does not fit shared memory");
+  long long blocks64 = (M + kWgRows - 1) / kWgRows;
+  int grid = (int)(blocks64 < kNumSMs ? blocks64 : kNumSMs);
+  p.rows_per_cta = (blocks64 + grid - 1) / grid * kWgRows;
+  p.partial = workspace;
+  CUtensorMap tmZ, tmX;
+  if (!make_map(&tmZ, dZ, (unsigned long long)M, (unsigned long long)Nw, (unsigned long long)ldz, 64, kWgRows))
+    return PNB_ERR_ARG;
+  if (!make_map(&tmX, X, (unsigned long long)M, (unsigned long long)Kw, (unsigned long long)ldx, 64, kWgRows))
+    return PNB_ERR_ARG;
+  cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  if (e != cudaSuccess) {
+    set_error("wgrad_tc(smem attr)", e);
+    return (int)e;
+  }
+  cudaStream_t st = as_stream(stream);
+  wgrad_tc_kernel<<<grid, kThreads, smem_bytes, st>>>(tmZ, tmX, p);
+  int rc = finish("wgrad_tc");
+  if (rc) return rc;
+  int total = Nw * Kw;
+  wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(grid, Nw, Kw, workspace, dW, ldw);
+  return finish("wgrad_reduce");
+}

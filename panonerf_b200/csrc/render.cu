@@ -1,0 +1,253 @@
+// K6 alpha compositing (fwd/bwd) and K7 hierarchical resampling.  One warp owns one ray: the per-ray scans run
+// in registers with warp shuffles, per-ray samples are staged in shared memory, nothing per-sample round-trips
+// HBM.  HBM-bound: composite fwd moves 24 B/sample + 36 B/ray, bwd 40 B/sample + 32 B/ray, resample
+// 12 B/sample + 8 B/ray.
+#include "common.cuh"
+
+namespace pnb {
+
+constexpr int kWarpsPerBlock = 8;
+
+__device__ __forceinline__ float nan_to_num_f(float x) {
+  if (isnan(x)) return 0.f;
+  if (isinf(x)) return x > 0.f ? 3.402823466e+38f : -3.402823466e+38f;
+  return x;
+}
+
+// models/mip.py:458-478
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+composite_fwd_kernel(long long R, int N, const float* __restrict__ rgb, const float* __restrict__ density,
+                     const float* __restrict__ t, const float* __restrict__ dirs, int d_mod, int white_bkgd,
+                     float* __restrict__ comp_rgb, float* __restrict__ distance, float* __restrict__ acc_out,
+                     float* __restrict__ weights) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = blockIdx.x * (long long)kWarpsPerBlock + (threadIdx.x >> 5);
+  for (long long r = warp0; r < R; r += (long long)gridDim.x * kWarpsPerBlock) {
+    long long rd = d_mod ? r % d_mod : r;
+    float d0 = dirs[3 * rd], d1 = dirs[3 * rd + 1], d2 = dirs[3 * rd + 2];
+    float dnorm = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
+    const float* tr = t + r * (N + 1);
+    double carry = 0.0;
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f, a = 0.f, s = 0.f;
+    for (int base = 0; base < N; base += 32) {
+      int i = base + lane;
+      bool ok = i < N;
+      float t0 = ok ? tr[i] : 0.f, t1 = ok ? tr[i + 1] : 0.f;
+      float sd = ok ? density[r * N + i] * ((t1 - t0) * dnorm) : 0.f;
+      double incl = warp_scan_incl((double)sd, lane);
+      double prev = __shfl_up_sync(0xffffffffu, incl, 1);
+      double excl = carry + (lane == 0 ? 0.0 : prev);
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+      float w = (1.f - expf(-sd)) * expf(-(float)excl);
+      if (ok) {
+        weights[r * N + i] = w;
+        const float* c = rgb + 3 * (r * N + i);
+        c0 += w * c[0];
+        c1 += w * c[1];
+        c2 += w * c[2];
+        a += w;
+        s += w * (0.5f * (t0 + t1));
+      }
+    }
+    c0 = warp_sum(c0), c1 = warp_sum(c1), c2 = warp_sum(c2), a = warp_sum(a), s = warp_sum(s);
+    if (lane == 0) {
+      float dist = fminf(fmaxf(nan_to_num_f(s / a), tr[0]), tr[N]);
+      if (white_bkgd) {
+        float bg = 1.f - a;
+        c0 += bg, c1 += bg, c2 += bg;
+      }
+      comp_rgb[3 * r] = c0, comp_rgb[3 * r + 1] = c1, comp_rgb[3 * r + 2] = c2;
+      distance[r] = dist;
+      acc_out[r] = a;
+    }
+  }
+}
+
+// Hand-derived backward of the block above.  With sd_i = sigma_i*delta_i, T_i = exp(-sum_{j<i} sd_j),
+// w_i = (1-exp(-sd_i)) T_i and G_i = dL/dw_i:   dL/dsd_i = G_i (T_i - w_i) - sum_{j>i} G_j w_j.
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+composite_bwd_kernel(long long R, int N, const float* __restrict__ rgb, const float* __restrict__ density,
+                     const float* __restrict__ t, const float* __restrict__ dirs, int d_mod, int white_bkgd,
+                     const float* __restrict__ g_comp, const float* __restrict__ g_dist,
+                     const float* __restrict__ g_acc, const float* __restrict__ g_w, float* __restrict__ d_rgb,
+                     float* __restrict__ d_density) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  float* sT = smem + (size_t)wib * 3 * N;  // transmittance
+  float* sW = sT + N;                      // weights
+  float* sQ = sW + N;                      // G_i * w_i
+  const long long warp0 = blockIdx.x * (long long)kWarpsPerBlock + wib;
+  for (long long r = warp0; r < R; r += (long long)gridDim.x * kWarpsPerBlock) {
+    long long rd = d_mod ? r % d_mod : r;
+    float d0 = dirs[3 * rd], d1 = dirs[3 * rd + 1], d2 = dirs[3 * rd + 2];
+    float dnorm = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
+    const float* tr = t + r * (N + 1);
+    double carry = 0.0;
+    float a = 0.f, s = 0.f;
+    for (int base = 0; base < N; base += 32) {
+      int i = base + lane;
+      bool ok = i < N;
+      float t0 = ok ? tr[i] : 0.f, t1 = ok ? tr[i + 1] : 0.f;
+      float sd = ok ? density[r * N + i] * ((t1 - t0) * dnorm) : 0.f;
+      double incl = warp_scan_incl((double)sd, lane);
+      double prev = __shfl_up_sync(0xffffffffu, incl, 1);
+      double excl = carry + (lane == 0 ? 0.0 : prev);
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+      float T = expf(-(float)excl);
+      float w = (1.f - expf(-sd)) * T;
+      if (ok) {
+        sT[i] = T, sW[i] = w;
+        a += w;
+        s += w * (0.5f * (t0 + t1));
+      }
+    }
+    a = warp_sum(a), s = warp_sum(s);
+    float gc0 = g_comp ? g_comp[3 * r] : 0.f, gc1 = g_comp ? g_comp[3 * r + 1] : 0.f,
+          gc2 = g_comp ? g_comp[3 * r + 2] : 0.f;
+    float ga = (g_acc ? g_acc[r] : 0.f) - (white_bkgd ? (gc0 + gc1 + gc2) : 0.f);
+    float draw = s / a;
+    float dnum = nan_to_num_f(draw);
+    // torch.clamp passes the gradient on the closed interval, nan_to_num only for finite inputs
+    bool pass = isfinite(draw) && dnum >= tr[0] && dnum <= tr[N];
+    float gd = (g_dist && pass) ? g_dist[r] / a : 0.f;
+    __syncwarp();
+    for (int i = lane; i < N; i += 32) {
+      const float* c = rgb + 3 * (r * N + i);
+      float tm = 0.5f * (tr[i] + tr[i + 1]);
+      float G = gc0 * c[0] + gc1 * c[1] + gc2 * c[2] + ga + gd * (tm - draw) + (g_w ? g_w[r * N + i] : 0.f);
+      float w = sW[i];
+      sQ[i] = G * w;
+      sT[i] = G * (sT[i] - w);  // re-use: G_i (T_i - w_i)
+      float* o = d_rgb + 3 * (r * N + i);
+      o[0] = w * gc0, o[1] = w * gc1, o[2] = w * gc2;
+    }
+    __syncwarp();
+    // suffix-exclusive sum of Q, walking the chunks from the far end of the ray
+    float tail = 0.f;
+    for (int base = ((N - 1) / 32) * 32; base >= 0; base -= 32) {
+      int i = base + (31 - lane);  // lane 0 holds the farthest sample of the chunk
+      bool ok = i < N;
+      float q = ok ? sQ[i] : 0.f;
+      float incl = warp_scan_incl(q, lane);
+      float excl = tail + incl - q;
+      tail += __shfl_sync(0xffffffffu, incl, 31);
+      if (ok) d_density[r * N + i] = (sT[i] - excl) * ((tr[i + 1] - tr[i]) * dnorm);
+    }
+    __syncwarp();
+  }
+}
+
+// models/mip.py:324-329 (blur-pool) + 253-300 (pad, pdf, cdf, searchsorted(right=True), gather, lerp)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+resample_kernel(long long R, int N, const float* __restrict__ t, const float* __restrict__ weights, float padding,
+                int blur_pool, const float* __restrict__ u, int u_ld, float* __restrict__ new_t, long long* __restrict__ inds_out) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  float* sw = smem + (size_t)wib * (3 * N + 2);  // raw weights, then pdf
+  float* sc = sw + N;                            // cdf, N+1 entries
+  float* sb = sc + N + 1;                        // bins (t), N+1 entries
+  const long long warp0 = blockIdx.x * (long long)kWarpsPerBlock + wib;
+  for (long long r = warp0; r < R; r += (long long)gridDim.x * kWarpsPerBlock) {
+    for (int i = lane; i < N; i += 32) sw[i] = weights[r * N + i];
+    for (int i = lane; i <= N; i += 32) sb[i] = t[r * (N + 1) + i];
+    __syncwarp();
+    // blur-pool: wm[k] = max(w[max(k-1,0)], w[min(k,N-1)]), blur[i] = .5 (wm[i] + wm[i+1]) + padding.
+    // N <= 256 (checked by the launcher) so each lane owns at most 8 strided samples, kept in registers.
+    float local = 0.f;
+    float blur[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      int i = lane + 32 * k;
+      blur[k] = 0.f;
+      if (i < N) {
+        float wl = sw[i > 0 ? i - 1 : 0], wc = sw[i], wr = sw[i + 1 < N ? i + 1 : N - 1];
+        blur[k] = blur_pool ? 0.5f * (fmaxf(wl, wc) + fmaxf(wc, wr)) + padding : wc;
+        local += blur[k];
+      }
+    }
+    float wsum = warp_sum(local);
+    __syncwarp();  // every lane has read its neighbours: sw can be overwritten with the pdf
+    float pad = fmaxf(0.f, 1e-5f - wsum);  // mip.py:253-257
+    float add = pad / (float)N;
+    wsum += pad;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      int i = lane + 32 * k;
+      if (i < N) sw[i] = (blur[k] + add) / wsum;
+    }
+    __syncwarp();
+    // cdf[k] = min(1, float(sum_{j<k} double(pdf_j))) : torch's CPU cumsum accumulates in double
+    double carry = 0.0;
+    for (int base = 0; base < N; base += 32) {
+      int i = base + lane;
+      double p = i < N ? (double)sw[i] : 0.0;
+      double incl = warp_scan_incl(p, lane);
+      double prev = __shfl_up_sync(0xffffffffu, incl, 1);
+      double excl = carry + (lane == 0 ? 0.0 : prev);
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+      if (i < N) sc[i] = i == 0 ? 0.f : fminf(1.f, (float)excl);
+    }
+    if (lane == 0) sc[N] = 1.f;
+    __syncwarp();
+    for (int j = lane; j <= N; j += 32) {
+      float uj = u[(long long)u_ld * r + j];
+      int lo = 0, hi = N + 1;  // first index with cdf > u
+      while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (sc[mid] <= uj) lo = mid + 1; else hi = mid;
+      }
+      int below = lo - 1 > 0 ? lo - 1 : 0, above = lo < N ? lo : N;
+      float c0 = sc[below], c1 = sc[above];
+      float den = c1 - c0;
+      if (den < 1e-5f) den = 1.f;
+      float frac = (uj - c0) / den;
+      float b0 = sb[below], b1 = sb[above];
+      new_t[r * (N + 1) + j] = b0 + frac * (b1 - b0);
+      if (inds_out) inds_out[r * (N + 1) + j] = lo;
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace pnb
+
+using namespace pnb;
+
+extern "C" int pnb_composite_fwd(int R, int N, const float* rgb, const float* density, const float* t,
+                                 const float* dirs, int d_mod, int white_bkgd, float* comp_rgb, float* distance,
+                                 float* acc, float* weights, void* stream) {
+  PNB_REQUIRE(R >= 0 && N > 0 && d_mod >= 0, "composite_fwd: bad sizes");
+  if (R == 0) return 0;
+  int grid = grid_for((long long)R * 32, kWarpsPerBlock * 32, 8);
+  composite_fwd_kernel<<<grid, kWarpsPerBlock * 32, 0, as_stream(stream)>>>(R, N, rgb, density, t, dirs, d_mod,
+                                                                           white_bkgd, comp_rgb, distance, acc,
+                                                                           weights);
+  return finish("composite_fwd");
+}
+
+extern "C" int pnb_composite_bwd(int R, int N, const float* rgb, const float* density, const float* t,
+                                 const float* dirs, int d_mod, int white_bkgd, const float* g_comp,
+                                 const float* g_dist, const float* g_acc, const float* g_weights, float* d_rgb,
+                                 float* d_density, void* stream) {
+  PNB_REQUIRE(R >= 0 && N > 0 && d_mod >= 0, "composite_bwd: bad sizes");
+  if (R == 0) return 0;
+  size_t smem = (size_t)kWarpsPerBlock * 3 * N * sizeof(float);
+  PNB_REQUIRE(smem <= 200 * 1024, "composite_bwd: N too large for the per-warp shared-memory staging");
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(composite_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int grid = grid_for((long long)R * 32, kWarpsPerBlock * 32, 4);
+  composite_bwd_kernel<<<grid, kWarpsPerBlock * 32, smem, as_stream(stream)>>>(
+      R, N, rgb, density, t, dirs, d_mod, white_bkgd, g_comp, g_dist, g_acc, g_weights, d_rgb, d_density);
+  return finish("composite_bwd");
+}
+
+extern "C" int pnb_resample(int R, int N, const float* t, const float* weights, float padding, int blur_pool,
+                            const float* u, int u_ld, float* new_t, long long* inds, void* stream) {
+  PNB_REQUIRE(R >= 0 && N > 0 && N <= 256 && (u_ld == 0 || u_ld >= N + 1), "resample: need 0 < N <= 256");
+  if (R == 0) return 0;
+  size_t smem = (size_t)kWarpsPerBlock * (3 * N + 2) * sizeof(float);
+  int grid = grid_for((long long)R * 32, kWarpsPerBlock * 32, 4);
+  resample_kernel<<<grid, kWarpsPerBlock * 32, smem, as_stream(stream)>>>(R, N, t, weights, padding, blur_pool, u, u_ld,
+                                                                         new_t, inds);
+  return finish("resample");
+}

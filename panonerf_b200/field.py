@@ -1,0 +1,466 @@
+"""The radiance/density field: IPE -> 8x256 trunk (+skip) -> density / extra / view / colour heads
+(models/pano_mip_nerf.py:78-114 + 235-280), with the density-gradient normals (pano_mip_nerf.py:299-302) computed
+by an explicit Jacobian sweep instead of vmap(jacrev).  One autograd Function owns every activation buffer and
+implements the backward by hand (dgrad + wgrad per layer, plus the adjoint of the Jacobian sweep, i.e. the
+"double backward" the reference gets from functorch).
+
+Two GEMM back-ends share the orchestration:
+  * `tc`   bf16 operands on tcgen05 tensor cores (pnb_linear_tc / pnb_wgrad_tc), fp32 accumulation in TMEM;
+  * `f32`  fp32 FFMA (pnb_gemm_f32) - the parity mode that matches the fp32 reference to ~1e-6.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib
+from ._lib import EPI_ACCUM, EPI_BIAS, EPI_MASK, EPI_RELU, PNB_BF16, PNB_F32, check
+from . import ops
+from .ops import _p, _stream
+
+PARAM_ORDER_TRUNK = "layers.{}.0"
+
+
+def param_names(depth: int, depth_cond: int) -> List[str]:
+    """State-dict order of models/pano_mip_nerf.py:54-76."""
+    names = []
+    for i in range(depth):
+        names += [f"layers.{i}.0.weight", f"layers.{i}.0.bias"]
+    names += ["density_layer.weight", "density_layer.bias", "extra_layer.weight", "extra_layer.bias"]
+    for i in range(depth_cond):
+        names += [f"view_layers.{i}.0.weight", f"view_layers.{i}.0.bias"]
+    names += ["color_layer.weight", "color_layer.bias"]
+    return names
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# GEMM back-ends
+# ----------------------------------------------------------------------------------------------------------------
+def _ld(t: torch.Tensor) -> int:
+    assert t.dim() == 2 and t.stride(1) == 1, "matrix operands must be row-major views"
+    return t.stride(0)
+
+
+class _F32Backend:
+    """fp32 FFMA GEMMs. Weights are used in place (views of the fp32 parameters)."""
+    dtype = torch.float32
+    code = PNB_F32
+    name = "f32"
+
+    def __init__(self, params: Dict[str, torch.Tensor]):
+        self.params = params
+
+    def linear(self, a, w, out, bias=None, relu=False, mask=None, row_bias=None, group=0, accum=False):
+        flags = (EPI_BIAS if bias is not None else 0) | (EPI_RELU if relu else 0) | \
+                (EPI_MASK if mask is not None else 0) | (EPI_ACCUM if accum else 0)
+        m, k = a.shape
+        n = w.shape[0]
+        with torch.cuda.device(a.device):
+            check(_lib.lib().pnb_gemm_f32(0, m, n, k, _p(a), _ld(a), _p(w), _ld(w), _p(out), _ld(out), _p(bias),
+                                          _p(row_bias), group, _p(mask), _ld(mask) if mask is not None else 0, flags,
+                                          _stream()), "gemm_f32(NT)")
+
+    def dgrad(self, dz, w, out, mask=None, accum=False):
+        """out[M,K] = dz[M,N] @ w[N,K]"""
+        flags = (EPI_MASK if mask is not None else 0) | (EPI_ACCUM if accum else 0)
+        m, n = dz.shape
+        k = w.shape[1]
+        with torch.cuda.device(dz.device):
+            check(_lib.lib().pnb_gemm_f32(1, m, k, n, _p(dz), _ld(dz), _p(w), _ld(w), _p(out), _ld(out), None, None, 0,
+                                          _p(mask), _ld(mask) if mask is not None else 0, flags, _stream()),
+                  "gemm_f32(NN)")
+
+    dgrad_small = dgrad
+
+    def wgrad(self, dz, x, dw):
+        """dw[N,K] += dz[M,N]^T @ x[M,K]"""
+        m, n = dz.shape
+        k = x.shape[1]
+        with torch.cuda.device(dz.device):
+            check(_lib.lib().pnb_gemm_f32(2, n, k, m, _p(dz), _ld(dz), _p(x), _ld(x), _p(dw), _ld(dw), None, None, 0,
+                                          None, 0, 0, _stream()), "gemm_f32(TN)")
+
+    wgrad_small = wgrad
+
+    def w(self, name, c0=None, c1=None):
+        t = self.params[name]
+        return t if c0 is None else t[:, c0:c1]
+
+
+_pack_cache: Dict[int, dict] = {}
+_ws_cache: Dict[str, torch.Tensor] = {}
+_pack_epoch = [0]
+
+
+def invalidate_packs():
+    """Call after parameters were updated through raw pointers (the fused Adam kernel does not bump
+    torch's version counters)."""
+    _pack_epoch[0] += 1
+
+
+class _PackedWeight:
+    """bf16 copies of one fp32 weight (or a column slice of it): `fwd` [N,K] for A@W^T, `t` [K,N] for dZ@W.
+    Inner dimensions are zero-padded to a multiple of 64 so that every TMA row is 16-byte aligned."""
+
+    def __init__(self, w32: torch.Tensor):
+        n, k = w32.shape
+        self.shape = (n, k)
+        kp, np_ = (k + 63) // 64 * 64, (n + 63) // 64 * 64
+        self.fwd = torch.zeros(n, kp, device=w32.device, dtype=torch.bfloat16)
+        self.fwd[:, :k] = w32
+        self.t = torch.zeros(k, np_, device=w32.device, dtype=torch.bfloat16)
+        self.t[:, :n] = w32.t()
+
+
+class _TCBackend:
+    """bf16 tcgen05 GEMMs.  Weight packs are cached per parameter version (re-packed after each optimiser step)."""
+    dtype = torch.bfloat16
+    code = PNB_BF16
+    name = "tc"
+
+    def __init__(self, params: Dict[str, torch.Tensor]):
+        self.params = params
+        self._packs: Dict[tuple, _PackedWeight] = {}
+        w0, wv = params["layers.0.0.weight"], params["view_layers.0.0.weight"]
+        if w0.shape[0] != 256 or wv.shape[0] != 128:
+            raise NotImplementedError("the tcgen05 path is specialised for net_width=256 / net_width_condition=128 "
+                                      "(configs/*.yaml); use precision='fp32' for other widths")
+
+    def w(self, name, c0=None, c1=None):
+        key = (name, c0, c1)
+        if key not in self._packs:
+            p = self.params[name]
+            ck = (p.data_ptr(), p._version, _pack_epoch[0], c0, c1)
+            hit = _pack_cache.get(id(p), {}).get((c0, c1))
+            if hit is not None and hit[0] == ck:
+                self._packs[key] = hit[1]
+            else:
+                with torch.no_grad():
+                    pk = _PackedWeight(p.detach() if c0 is None else p.detach()[:, c0:c1])
+                _pack_cache.setdefault(id(p), {})[(c0, c1)] = (ck, pk)
+                self._packs[key] = pk
+        return self._packs[key]
+
+    @staticmethod
+    def _workspace(dev) -> torch.Tensor:
+        key = str(dev)
+        if key not in _ws_cache:
+            nbytes = int(_lib.lib().pnb_wgrad_tc_workspace(256, 256))
+            _ws_cache[key] = torch.empty(nbytes // 4, device=dev, dtype=torch.float32)
+        return _ws_cache[key]
+
+    def linear(self, a, w: _PackedWeight, out, bias=None, relu=False, mask=None, row_bias=None, group=0, accum=False):
+        flags = (EPI_BIAS if bias is not None else 0) | (EPI_RELU if relu else 0) | \
+                (EPI_MASK if mask is not None else 0) | (EPI_ACCUM if accum else 0)
+        m, k = a.shape
+        n = w.shape[0]
+        assert k == w.shape[1], (a.shape, w.shape)
+        k16 = (k + 15) // 16 * 16
+        with torch.cuda.device(a.device):
+            check(_lib.lib().pnb_linear_tc(m, n, k16, _p(a), _ld(a), _p(w.fwd), _ld(w.fwd), _p(out), _ld(out),
+                                           ops.dt_code(out.dtype), _p(bias), _p(row_bias), group, _p(mask),
+                                           _ld(mask) if mask is not None else 0, flags, _stream()), "linear_tc")
+
+    def dgrad(self, dz, w: _PackedWeight, out, mask=None, accum=False):
+        """out[M,K] = dz[M,N] @ W[N,K]  ==  linear with the pre-transposed pack W^T[K,N]"""
+        flags = (EPI_MASK if mask is not None else 0) | (EPI_ACCUM if accum else 0)
+        m, n = dz.shape
+        k = w.shape[1]
+        n16 = (n + 15) // 16 * 16
+        with torch.cuda.device(dz.device):
+            check(_lib.lib().pnb_linear_tc(m, k, n16, _p(dz), _ld(dz), _p(w.t), _ld(w.t), _p(out), _ld(out),
+                                           ops.dt_code(out.dtype), None, None, 0, _p(mask),
+                                           _ld(mask) if mask is not None else 0, flags, _stream()), "linear_tc(dgrad)")
+
+    def _pad64(self, x32: torch.Tensor) -> torch.Tensor:
+        """fp32 [M,C] head gradient -> bf16 [M,64] zero-padded (TMA rows must be 16-byte aligned)."""
+        m, c = x32.shape
+        buf = torch.zeros(m, 64, device=x32.device, dtype=torch.bfloat16)
+        with torch.cuda.device(x32.device):
+            check(_lib.lib().pnb_convert(m, c, _p(x32), _ld(x32), PNB_F32, _p(buf), 64, PNB_BF16, _stream()), "convert")
+        return buf
+
+    def dgrad_small(self, dz32, w: _PackedWeight, out, mask=None, accum=False):
+        pad = self._pad64(dz32)
+        self.dgrad(pad[:, :16], w, out, mask=mask, accum=accum)   # K=16 slice of the padded buffer (ld stays 64)
+        return pad
+
+    def wgrad(self, dz, x, dw):
+        m, n = dz.shape
+        k = x.shape[1]
+        with torch.cuda.device(dz.device):
+            check(_lib.lib().pnb_wgrad_tc(m, n, (k + 15) // 16 * 16, _p(dz), _ld(dz), _p(x), _ld(x), _p(dw), _ld(dw),
+                                          _p(self._workspace(dz.device)), _stream()), "wgrad_tc")
+
+    def wgrad_small(self, dz32, x, dw, pad=None):
+        """dw[C,K] += dz32[M,C]^T x[M,K] with C < 16: run the transposed product x^T dz (x plays the 128/256-wide
+        operand) into a scratch [K,64] and add its first C columns, transposed."""
+        pad = self._pad64(dz32) if pad is None else pad
+        c, k = dw.shape
+        tmp = torch.zeros(k, 64, device=x.device, dtype=torch.float32)
+        self.wgrad(x, pad, tmp)
+        dw.add_(tmp[:, :c].t())
+
+
+def make_backend(precision: str, params: Dict[str, torch.Tensor]):
+    if precision == "fp32":
+        return _F32Backend(params)
+    if precision == "bf16":
+        return _TCBackend(params)
+    raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+
+
+def _mask_scale(src, w_row, out):
+    m, n = src.shape
+    with torch.cuda.device(src.device):
+        check(_lib.lib().pnb_mask_scale(m, n, _p(src), _ld(src), _p(w_row), None, _p(out), _ld(out),
+                                        ops.dt_code(out.dtype), _stream()), "mask_scale")
+
+
+def _colsum(x, out):
+    m, n = x.shape
+    with torch.cuda.device(x.device):
+        check(_lib.lib().pnb_colsum(m, n, _p(x), _ld(x), ops.dt_code(x.dtype), _p(out), _stream()), "colsum")
+
+
+def _group_sum(x, group):
+    m, n = x.shape
+    out = torch.empty(m // group, n, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        check(_lib.lib().pnb_group_sum(m, n, group, _p(x), _ld(x), ops.dt_code(x.dtype), _p(out), _stream()), "group_sum")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# the autograd Function
+# ----------------------------------------------------------------------------------------------------------------
+class _Field(torch.autograd.Function):
+    """(means, covs, venc, *params) -> (raw_rgb [M,3], raw_den [M,C], n_raw [M,3] | None)."""
+
+    @staticmethod
+    def forward(ctx, means, covs, venc, cfg, *params):
+        names = cfg["names"]
+        P = dict(zip(names, params))
+        be = make_backend(cfg["precision"], P)
+        depth, skip = cfg["depth"], cfg["skip"]
+        width, xyz = cfg["width"], cfg["xyz_dim"]
+        S = cfg["samples_per_ray"]
+        M = means.numel() // 3
+        dev = means.device
+        dt = be.dtype
+        means2, covs2 = means.reshape(M, 3), covs.reshape(M, 3)
+        f32 = torch.float32
+
+        # cat = [h_skip | enc] (the input of the layer after the skip connection); enc lives only there
+        cat = torch.empty(M, width + xyz, device=dev, dtype=dt)
+        enc = cat[:, width:]
+        ops.ipe_into(means2, covs2, cfg["min_deg"], cfg["max_deg"], enc)
+        hs = []
+        x = enc
+        for i in range(depth):
+            to_cat = (i % skip == 0 and i > 0)
+            out = cat[:, :width] if to_cat else torch.empty(M, width, device=dev, dtype=dt)
+            be.linear(x, be.w(f"layers.{i}.0.weight"), out, bias=P[f"layers.{i}.0.bias"], relu=True)
+            hs.append(out)
+            x = cat if to_cat else out
+        trunk_out = x
+        C = P["density_layer.weight"].shape[0]
+        raw_den = torch.empty(M, C, device=dev, dtype=f32)
+        be.linear(trunk_out, be.w("density_layer.weight"), raw_den, bias=P["density_layer.bias"])
+        bott = torch.empty(M, width, device=dev, dtype=dt)
+        be.linear(trunk_out, be.w("extra_layer.weight"), bott, bias=P["extra_layer.bias"])
+        # view layer: the 27 view-direction inputs are constant along a ray -> per-ray addend (fp32, tiny)
+        wv = P["view_layers.0.0.weight"]
+        wc_ = wv.shape[0]
+        vb = torch.empty(venc.shape[0], wc_, device=dev, dtype=f32)
+        _F32Backend(P).linear(venc, wv[:, width:], vb, bias=P["view_layers.0.0.bias"])
+        hv = torch.empty(M, wc_, device=dev, dtype=dt)
+        be.linear(bott, be.w("view_layers.0.0.weight", 0, width), hv, relu=True, row_bias=vb, group=S)
+        raw_rgb = torch.empty(M, P["color_layer.weight"].shape[0], device=dev, dtype=f32)
+        be.linear(hv, be.w("color_layer.weight"), raw_rgb, bias=P["color_layer.bias"])
+
+        n_raw = None
+        jac = None
+        if cfg["with_normals"]:
+            # Jacobian sweep: a_i = relu'(h_i) * (a_{i+1} W_{i+1}), seeded with the sigma row of the density head
+            a = [None] * depth
+            a[depth - 1] = torch.empty(M, width, device=dev, dtype=dt)
+            _mask_scale(hs[depth - 1], P["density_layer.weight"][0].contiguous(), a[depth - 1])
+            g_enc = torch.empty(M, xyz, device=dev, dtype=f32)
+            skip_layers = [i for i in range(1, depth) if (i - 1) % skip == 0 and i > 1]
+            first = True
+            for i in range(depth - 1, 0, -1):
+                a[i - 1] = torch.empty(M, width, device=dev, dtype=dt)
+                if i in skip_layers:
+                    be.dgrad(a[i], be.w(f"layers.{i}.0.weight", 0, width), a[i - 1], mask=hs[i - 1])
+                    be.dgrad(a[i], be.w(f"layers.{i}.0.weight", width, width + xyz), g_enc, accum=not first)
+                    first = False
+                else:
+                    be.dgrad(a[i], be.w(f"layers.{i}.0.weight"), a[i - 1], mask=hs[i - 1])
+            be.dgrad(a[0], be.w("layers.0.0.weight"), g_enc, accum=not first)
+            v = ops.ipe_vjp(means2, covs2, cfg["min_deg"], cfg["max_deg"], g_enc)
+            del g_enc
+            n_raw = torch.empty(M, 3, device=dev, dtype=f32)
+            with torch.cuda.device(dev):
+                check(_lib.lib().pnb_density_grad_fwd(M, C, _p(raw_den), float(cfg["density_bias"]), _p(v), _p(n_raw),
+                                                      _stream()), "density_grad_fwd")
+            jac = (a, v)
+
+        ctx.cfg = cfg
+        ctx.n_params = len(params)
+        ctx.need_means = means.requires_grad
+        ctx.means_shape = means.shape
+        # raw buffers are kept on ctx (not save_for_backward): they are private to this Function and never
+        # modified in place afterwards
+        ctx.bufs = dict(means=means2, covs=covs2, venc=venc, cat=cat, hs=hs, bott=bott, hv=hv, vb_rows=venc.shape[0],
+                        raw_den=raw_den, jac=jac)
+        ctx.params = params
+        if n_raw is None:
+            return raw_rgb, raw_den, None
+        return raw_rgb, raw_den, n_raw
+
+    @staticmethod
+    def backward(ctx, d_raw_rgb, d_raw_den, d_n_raw):
+        cfg, B = ctx.cfg, ctx.bufs
+        names = cfg["names"]
+        P = dict(zip(names, ctx.params))
+        be = make_backend(cfg["precision"], P)
+        f32be = _F32Backend(P)
+        depth, skip, width, xyz = cfg["depth"], cfg["skip"], cfg["width"], cfg["xyz_dim"]
+        S = cfg["samples_per_ray"]
+        cat, hs, bott, hv, raw_den = B["cat"], B["hs"], B["bott"], B["hv"], B["raw_den"]
+        means, covs, venc = B["means"], B["covs"], B["venc"]
+        M = means.shape[0]
+        dev, dt, f32 = means.device, be.dtype, torch.float32
+        C = raw_den.shape[1]
+        enc = cat[:, width:]
+        skip_layers = [i for i in range(1, depth) if (i - 1) % skip == 0 and i > 1]
+
+        # one flat, zero-initialised gradient buffer; per-parameter views are what autograd receives
+        sizes = [p.numel() for p in ctx.params]
+        flat = torch.zeros(sum(sizes), device=dev, dtype=f32)
+        G, off = {}, 0
+        for nme, p, sz in zip(names, ctx.params, sizes):
+            G[nme] = flat[off:off + sz].view_as(p)
+            off += sz
+
+        d_raw_den = torch.zeros(M, C, device=dev, dtype=f32) if d_raw_den is None else d_raw_den.contiguous().clone()
+        d_raw_rgb = torch.zeros(M, 3, device=dev, dtype=f32) if d_raw_rgb is None else d_raw_rgb.contiguous()
+
+        # ---- adjoint of the Jacobian sweep (second-order terms of the normals) -------------------------------
+        if B["jac"] is not None and d_n_raw is not None:
+            a, v = B["jac"]
+            d_n_raw = d_n_raw.contiguous()
+            d_raw0 = torch.empty(M, device=dev, dtype=f32)
+            d_v = torch.empty(M, 3, device=dev, dtype=f32)
+            with torch.cuda.device(dev):
+                check(_lib.lib().pnb_density_grad_bwd(M, C, _p(raw_den), float(cfg["density_bias"]), _p(v), _p(d_n_raw),
+                                                      _p(d_raw0), _p(d_v), _stream()), "density_grad_bwd")
+            d_raw_den[:, 0] += d_raw0
+            # u = d L / d g_enc = J_ipe d_v ; forward-mode sweep q_i = relu'(h_i) * (q_{i-1} W_i^T)
+            ucat = torch.empty(M, width + xyz, device=dev, dtype=dt)
+            u = ucat[:, width:]
+            ops.ipe_jvp_into(means, covs, cfg["min_deg"], cfg["max_deg"], d_v, u)
+            q_prev = u
+            for i in range(depth):
+                wname = f"layers.{i}.0.weight"
+                # dW_i += a_i^T q_{i-1}
+                if i in skip_layers:
+                    be.wgrad(a[i], ucat[:, :width], G[wname][:, :width])
+                    be.wgrad(a[i], u, G[wname][:, width:])
+                else:
+                    be.wgrad(a[i], q_prev, G[wname])
+                to_cat = (i % skip == 0 and i > 0)
+                q = ucat[:, :width] if to_cat else torch.empty(M, width, device=dev, dtype=dt)
+                be.linear(q_prev, be.w(wname), q, mask=hs[i])
+                a[i] = None
+                q_prev = ucat if to_cat else q
+            # d wd[0,:] += colsum(q_last)   (a_last = relu'(h_last) * wd[0])
+            last = q_prev if q_prev.shape[1] == width else q_prev[:, :width]
+            _colsum(last, G["density_layer.weight"][0])
+            del ucat, q_prev
+
+        # ---- heads ------------------------------------------------------------------------------------------
+        trunk_out = cat if ((depth - 1) % skip == 0 and depth - 1 > 0) else hs[depth - 1]
+        # colour head
+        _colsum(d_raw_rgb, G["color_layer.bias"])
+        dzv = torch.empty(M, hv.shape[1], device=dev, dtype=dt)
+        pad = be.dgrad_small(d_raw_rgb, be.w("color_layer.weight"), dzv, mask=hv)
+        if isinstance(be, _TCBackend):
+            be.wgrad_small(d_raw_rgb, hv, G["color_layer.weight"], pad=pad)
+        else:
+            be.wgrad(d_raw_rgb, hv, G["color_layer.weight"])
+        del pad
+        # view layer: bottleneck part on the GEMM path, per-ray view-direction part in fp32
+        be.wgrad(dzv, bott, G["view_layers.0.0.weight"][:, :width])
+        dvb = _group_sum(dzv, S)
+        _colsum(dvb, G["view_layers.0.0.bias"])
+        f32be.wgrad(dvb, venc, G["view_layers.0.0.weight"][:, width:])
+        d_bott = torch.empty(M, width, device=dev, dtype=dt)
+        be.dgrad(dzv, be.w("view_layers.0.0.weight", 0, width), d_bott)
+        del dzv
+        # extra + density heads -> d trunk_out (masked by the last ReLU)
+        _colsum(d_bott, G["extra_layer.bias"])
+        be.wgrad(d_bott, trunk_out if trunk_out.shape[1] == width else trunk_out, G["extra_layer.weight"])
+        _colsum(d_raw_den, G["density_layer.bias"])
+        dz = torch.empty(M, width, device=dev, dtype=dt)
+        h_last = hs[depth - 1]
+        be.dgrad(d_bott, be.w("extra_layer.weight"), dz)
+        pad = be.dgrad_small(d_raw_den, be.w("density_layer.weight"), dz, mask=h_last, accum=True)
+        if isinstance(be, _TCBackend):
+            be.wgrad_small(d_raw_den, h_last, G["density_layer.weight"], pad=pad)
+        else:
+            be.wgrad(d_raw_den, h_last, G["density_layer.weight"])
+        del pad, d_bott
+
+        # ---- trunk -------------------------------------------------------------------------------------------
+        need_enc = ctx.need_means
+        d_enc = torch.zeros(M, xyz, device=dev, dtype=f32) if need_enc else None
+        for i in range(depth - 1, -1, -1):
+            wname, bname = f"layers.{i}.0.weight", f"layers.{i}.0.bias"
+            _colsum(dz, G[bname])
+            if i == 0:
+                be.wgrad(dz, enc, G[wname])
+                if need_enc:
+                    be.dgrad(dz, be.w(wname), d_enc, accum=True)
+                break
+            x_prev = hs[i - 1]
+            if i in skip_layers:
+                be.wgrad(dz, cat[:, :width], G[wname][:, :width])
+                be.wgrad(dz, enc, G[wname][:, width:])
+                if need_enc:
+                    be.dgrad(dz, be.w(wname, width, width + xyz), d_enc, accum=True)
+                nxt = torch.empty(M, width, device=dev, dtype=dt)
+                be.dgrad(dz, be.w(wname, 0, width), nxt, mask=x_prev)
+            else:
+                be.wgrad(dz, x_prev, G[wname])
+                nxt = torch.empty(M, width, device=dev, dtype=dt)
+                be.dgrad(dz, be.w(wname), nxt, mask=x_prev)
+            dz = nxt
+        d_means = None
+        if need_enc:
+            d_means = ops.ipe_vjp(means, covs, cfg["min_deg"], cfg["max_deg"], d_enc).view(ctx.means_shape)
+        ctx.bufs = None
+        return (d_means, None, None, None) + tuple(G[n] for n in names)
+
+
+def radiance_field(means, covs, venc, params: Dict[str, torch.Tensor], *, precision: str, samples_per_ray: int,
+                   min_deg: int, max_deg: int, density_bias: float, skip: int, with_normals: bool):
+    """Evaluate the MLP on [R,S,3] Gaussians. Returns raw_rgb [R,S,3], raw_den [R,S,C], n_raw [R,S,3] | None."""
+    names = list(params.keys())
+    depth = len([n for n in names if n.startswith("layers.") and n.endswith(".weight")])
+    w0 = params["layers.0.0.weight"]
+    cfg = dict(names=names, precision=precision, depth=depth, skip=skip, width=w0.shape[0], xyz_dim=w0.shape[1],
+               samples_per_ray=samples_per_ray, min_deg=min_deg, max_deg=max_deg, density_bias=density_bias,
+               with_normals=with_normals)
+    if w0.shape[1] != 6 * (max_deg - min_deg):
+        raise RuntimeError("IPE width does not match the first layer")
+    R = means.shape[0]
+    raw_rgb, raw_den, n_raw = _Field.apply(means, covs, venc, cfg, *[params[n] for n in names])
+    raw_rgb = raw_rgb.view(R, samples_per_ray, -1)
+    raw_den = raw_den.view(R, samples_per_ray, -1)
+    if n_raw is not None:
+        n_raw = n_raw.view(R, samples_per_ray, 3)
+    return raw_rgb, raw_den, n_raw

@@ -1,0 +1,454 @@
+"""Host-side operators: thin, checked wrappers over the C ABI plus the autograd Functions (explicit forward and
+hand-written backward) the models are assembled from.  PyTorch is used here for device memory, streams and the
+autograd tape only; every arithmetic step is a kernel of libpanonerf_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import PNB_BF16, PNB_F32, check
+
+_VP = ctypes.c_void_p
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else _VP(t.data_ptr())
+
+
+def _stream():
+    return _VP(torch.cuda.current_stream().cuda_stream)
+
+
+def _req(t: torch.Tensor, name: str, dtype=torch.float32):
+    """Inputs must already live on the GPU in the layout the kernels read (no silent CPU fallback, no copies)."""
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"panonerf_b200: `{name}` must be a CUDA tensor (there is no CPU path)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"panonerf_b200: `{name}` must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"panonerf_b200: `{name}` must be contiguous")
+    return t
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    """Normalise user-facing ray tensors (fp16 env rays, fp64 radii, expanded views) to contiguous fp32."""
+    if not t.is_cuda:
+        raise RuntimeError("panonerf_b200: tensors must be CUDA tensors (there is no CPU path)")
+    return t.detach().to(torch.float32).contiguous() if (t.dtype != torch.float32 or not t.is_contiguous()) else t
+
+
+def dt_code(dtype) -> int:
+    return PNB_BF16 if dtype == torch.bfloat16 else PNB_F32
+
+
+def launch_count() -> int:
+    return int(_lib.lib().pnb_launch_count())
+
+
+# --------------------------------------------------------------------------------------------------------------
+# rays / sampling / encodings (no autograd needed: inputs are data)
+# --------------------------------------------------------------------------------------------------------------
+_lin_cache = {}
+
+
+def linspace01(n: int, device) -> torch.Tensor:
+    """torch.linspace(0, 1, n) on `device`, computed by torch once so that its rounding matches the reference."""
+    key = ("lin", n, str(device))
+    if key not in _lin_cache:
+        _lin_cache[key] = torch.linspace(0.0, 1.0, n, device=device)
+    return _lin_cache[key]
+
+
+def linspace_u(n: int, device) -> torch.Tensor:
+    """torch.linspace(0, 1 - eps, n) of models/mip.py:279."""
+    key = ("u", n, str(device))
+    if key not in _lin_cache:
+        _lin_cache[key] = torch.linspace(0.0, 1.0 - torch.finfo(torch.float32).eps, n, device=device)
+    return _lin_cache[key]
+
+
+def raygen_equirect(h: int, w: int, c2w, near: float, far: float, device, row0: int = 0, nrows: Optional[int] = None):
+    nrows = h - row0 if nrows is None else nrows
+    n = nrows * w
+    import numpy as np
+    c = np.ascontiguousarray(np.asarray(c2w, dtype=np.float32)[:3, :4])
+    c44 = np.zeros((3, 4), dtype=np.float32)
+    c44[:] = c
+    mk = lambda k: torch.empty(n, k, device=device, dtype=torch.float32)
+    o, d, v = mk(3), mk(3), mk(3)
+    rad, lm, nr, fr, nv = mk(1), mk(1), mk(1), mk(1), mk(1)
+    with torch.cuda.device(o.device):
+        check(_lib.lib().pnb_raygen_equirect(h, w, row0, nrows, c44.ctypes.data_as(_VP), float(near), float(far),
+                                             _p(o), _p(d), _p(v), _p(rad), _p(lm), _p(nr), _p(fr), _p(nv),
+                                             _stream()), "raygen_equirect")
+    return o, d, v, rad, lm, nr, fr, nv
+
+
+def sample_cast(origins, directions, radii, near, far, n: int, t_rand=None, disparity=False, o_div=1, d_mod=0,
+                n_rays=None, rand_shared=False):
+    r = origins.shape[0] * o_div if n_rays is None else n_rays
+    dev = origins.device
+    t = torch.empty(r, n + 1, device=dev, dtype=torch.float32)
+    means = torch.empty(r, n, 3, device=dev, dtype=torch.float32)
+    covs = torch.empty(r, n, 3, device=dev, dtype=torch.float32)
+    if t_rand is not None:
+        _req(t_rand, "t_rand")
+    with torch.cuda.device(dev):
+        check(_lib.lib().pnb_sample_cast(r, n, _p(_req(origins, "origins")), o_div, _p(_req(directions, "directions")),
+                                         _p(_req(radii, "radii")), _p(_req(near, "near")), _p(_req(far, "far")), d_mod,
+                                         _p(linspace01(n + 1, dev)), _p(t_rand),
+                                         0 if (t_rand is None or rand_shared) else n + 1, int(bool(disparity)),
+                                         _p(t), _p(means), _p(covs), _stream()), "sample_cast")
+    return t, means, covs
+
+
+def cast_rays_t(t, origins, directions, radii, o_div=1, d_mod=0):
+    r, n = t.shape[0], t.shape[1] - 1
+    means = torch.empty(r, n, 3, device=t.device, dtype=torch.float32)
+    covs = torch.empty(r, n, 3, device=t.device, dtype=torch.float32)
+    with torch.cuda.device(t.device):
+        check(_lib.lib().pnb_cast_rays(r, n, _p(_req(t, "t")), _p(_req(origins, "origins")), o_div,
+                                       _p(_req(directions, "directions")), _p(_req(radii, "radii")), d_mod, _p(means),
+                                       _p(covs), _stream()), "cast_rays")
+    return means, covs
+
+
+def ipe_into(means, covs, min_deg, max_deg, out: torch.Tensor):
+    """IPE written into `out` ([M, 6L] view, any row stride, fp32 or bf16)."""
+    m = means.numel() // 3
+    with torch.cuda.device(means.device):
+        check(_lib.lib().pnb_ipe_fwd(m, _p(_req(means, "means")), _p(_req(covs, "covs")), min_deg, max_deg,
+                                     _p(out), out.stride(0), dt_code(out.dtype), _stream()), "ipe_fwd")
+    return out
+
+
+def ipe_vjp(means, covs, min_deg, max_deg, d_enc: torch.Tensor):
+    m = means.numel() // 3
+    out = torch.empty(m, 3, device=means.device, dtype=torch.float32)
+    with torch.cuda.device(means.device):
+        check(_lib.lib().pnb_ipe_vjp(m, _p(means), _p(covs), min_deg, max_deg, _p(d_enc), d_enc.stride(0),
+                                     dt_code(d_enc.dtype), _p(out), _stream()), "ipe_vjp")
+    return out
+
+
+def ipe_jvp_into(means, covs, min_deg, max_deg, v, out: torch.Tensor):
+    m = means.numel() // 3
+    with torch.cuda.device(means.device):
+        check(_lib.lib().pnb_ipe_jvp(m, _p(means), _p(covs), min_deg, max_deg, _p(_req(v, "v")), _p(out),
+                                     out.stride(0), dt_code(out.dtype), _stream()), "ipe_jvp")
+    return out
+
+
+def pos_enc(x, deg: int):
+    x = _req(x, "x")
+    out = torch.empty(x.shape[0], 3 + 6 * deg, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        check(_lib.lib().pnb_pos_enc(x.shape[0], _p(x), deg, _p(out), _stream()), "pos_enc")
+    return out
+
+
+def resample(t, weights, padding: float, u=None, return_inds=False, blur_pool=True):
+    """models/mip.py:304-352 (stop_grad branch): new fence-posts [R,N+1] (+ searchsorted indices for tests)."""
+    r, n = weights.shape
+    dev = t.device
+    if u is None:
+        u, u_ld = linspace_u(n + 1, dev), 0
+    else:
+        u, u_ld = _req(u, "u"), n + 1
+    new_t = torch.empty(r, n + 1, device=dev, dtype=torch.float32)
+    inds = torch.empty(r, n + 1, device=dev, dtype=torch.int64) if return_inds else None
+    with torch.cuda.device(dev):
+        check(_lib.lib().pnb_resample(r, n, _p(_req(t, "t")), _p(_req(weights, "weights")), float(padding), int(blur_pool), _p(u),
+                                      u_ld,
+                                      _p(new_t), _p(inds), _stream()), "resample")
+    return (new_t, inds) if return_inds else new_t
+
+
+def hdr_to_ldr(x, quantize=False):
+    x = _req(x, "x")
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(_lib.lib().pnb_hdr_to_ldr(x.numel(), _p(x), int(quantize), _p(out), _stream()), "hdr_to_ldr")
+    return out
+
+
+def dsum(x, scale=1.0):
+    """Deterministic sum of an fp32 tensor -> 0-dim tensor."""
+    x = _req(x, "x")
+    out = torch.empty(1, device=x.device, dtype=torch.float32)
+    ws = torch.empty(1024, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        check(_lib.lib().pnb_sum(x.numel(), _p(x), float(scale), _p(out), _p(ws), _stream()), "sum")
+    return out[0]
+
+
+def adam_step(p, g, m, v, lr, step, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
+    with torch.cuda.device(p.device):
+        check(_lib.lib().pnb_adam_step(p.numel(), _p(_req(p, "p")), _p(_req(g, "g")), _p(_req(m, "m")), _p(_req(v, "v")),
+                                       float(lr), beta1, beta2, eps, int(step), float(grad_scale), _stream()), "adam")
+
+
+# --------------------------------------------------------------------------------------------------------------
+# autograd Functions (explicit forward / backward kernels)
+# --------------------------------------------------------------------------------------------------------------
+class _Act(torch.autograd.Function):
+    """rgb/density/albedo activations of compute_graph (models/pano_mip_nerf.py:264-278)."""
+
+    @staticmethod
+    def forward(ctx, raw_rgb, raw_den, density_bias, rgb_padding, want_albedo):
+        m, c = raw_den.shape
+        dev = raw_den.device
+        rgb = torch.empty(m, 3, device=dev, dtype=torch.float32)
+        den = torch.empty(m, device=dev, dtype=torch.float32)
+        alb = torch.empty(m, 3, device=dev, dtype=torch.float32) if want_albedo else None
+        with torch.cuda.device(dev):
+            check(_lib.lib().pnb_act_fwd(m, c, _p(_req(raw_rgb, "raw_rgb")), _p(_req(raw_den, "raw_den")),
+                                         float(density_bias), float(rgb_padding), _p(rgb), _p(den), _p(alb),
+                                         _stream()), "act_fwd")
+        ctx.save_for_backward(raw_rgb, raw_den)
+        ctx.cfg = (float(density_bias), float(rgb_padding))
+        if want_albedo:
+            return rgb, den, alb
+        return rgb, den, None
+
+    @staticmethod
+    def backward(ctx, d_rgb, d_den, d_alb):
+        raw_rgb, raw_den = ctx.saved_tensors
+        m, c = raw_den.shape
+        d_raw_rgb = torch.empty_like(raw_rgb)
+        d_raw_den = torch.empty_like(raw_den)
+        cg = lambda g: None if g is None else g.contiguous()
+        d_rgb, d_den, d_alb = cg(d_rgb), cg(d_den), cg(d_alb)
+        with torch.cuda.device(raw_den.device):
+            check(_lib.lib().pnb_act_bwd(m, c, _p(raw_rgb), _p(raw_den), ctx.cfg[0], ctx.cfg[1], _p(d_rgb), _p(d_den),
+                                         _p(d_alb), _p(d_raw_rgb), _p(d_raw_den), _stream()), "act_bwd")
+        return d_raw_rgb, d_raw_den, None, None, None
+
+
+def activations(raw_rgb, raw_den, density_bias, rgb_padding, want_albedo):
+    return _Act.apply(raw_rgb, raw_den, density_bias, rgb_padding, want_albedo)
+
+
+class _Composite(torch.autograd.Function):
+    """volumetric_rendering (models/mip.py:444-483)."""
+
+    @staticmethod
+    def forward(ctx, rgb, density, t, dirs, d_mod, white_bkgd):
+        r, n = density.shape
+        dev = rgb.device
+        comp = torch.empty(r, 3, device=dev, dtype=torch.float32)
+        dist = torch.empty(r, device=dev, dtype=torch.float32)
+        acc = torch.empty(r, device=dev, dtype=torch.float32)
+        w = torch.empty(r, n, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            check(_lib.lib().pnb_composite_fwd(r, n, _p(_req(rgb, "rgb")), _p(_req(density, "density")), _p(_req(t, "t")),
+                                               _p(_req(dirs, "dirs")), d_mod, int(white_bkgd), _p(comp), _p(dist),
+                                               _p(acc), _p(w), _stream()), "composite_fwd")
+        ctx.save_for_backward(rgb, density, t, dirs)
+        ctx.cfg = (d_mod, int(white_bkgd))
+        return comp, dist, acc, w
+
+    @staticmethod
+    def backward(ctx, g_comp, g_dist, g_acc, g_w):
+        rgb, density, t, dirs = ctx.saved_tensors
+        r, n = density.shape
+        d_rgb = torch.empty_like(rgb)
+        d_den = torch.empty_like(density)
+        cg = lambda g: None if g is None else g.contiguous()
+        g_comp, g_dist, g_acc, g_w = cg(g_comp), cg(g_dist), cg(g_acc), cg(g_w)
+        with torch.cuda.device(rgb.device):
+            check(_lib.lib().pnb_composite_bwd(r, n, _p(rgb), _p(density), _p(t), _p(dirs), ctx.cfg[0], ctx.cfg[1],
+                                               _p(g_comp), _p(g_dist), _p(g_acc), _p(g_w), _p(d_rgb), _p(d_den),
+                                               _stream()), "composite_bwd")
+        return d_rgb, d_den, None, None, None, None
+
+
+def composite(rgb, density, t, dirs, white_bkgd, d_mod=0):
+    """rgb [R,N,3], density [R,N], t [R,N+1], dirs [R,3] (or [D,3] with d_mod=D) -> comp, distance, acc, weights."""
+    return _Composite.apply(rgb, density, t, dirs, d_mod, white_bkgd)
+
+
+class _Normals(torch.autograd.Function):
+    """Weighted, normalised density-gradient normals + orientation loss + albedo compositing
+    (models/pano_mip_nerf.py:296-317, models/mip_nerf.py:258-277)."""
+
+    @staticmethod
+    def forward(ctx, n_raw, weights, dirs, albedos):
+        r, n = weights.shape
+        dev = weights.device
+        normal = torch.empty(r, 3, device=dev, dtype=torch.float32)
+        ort = torch.empty(r, device=dev, dtype=torch.float32)
+        alb = torch.empty(r, 3, device=dev, dtype=torch.float32) if albedos is not None else None
+        with torch.cuda.device(dev):
+            check(_lib.lib().pnb_normals_fwd(r, n, _p(_req(n_raw, "n_raw")), _p(_req(weights, "weights")),
+                                             _p(_req(dirs, "dirs")), _p(albedos), _p(normal), _p(ort), _p(alb),
+                                             _stream()), "normals_fwd")
+        ctx.save_for_backward(n_raw, weights, dirs, albedos)
+        return normal, ort, alb
+
+    @staticmethod
+    def backward(ctx, g_normal, g_ort, g_alb):
+        n_raw, weights, dirs, albedos = ctx.saved_tensors
+        r, n = weights.shape
+        d_n = torch.empty_like(n_raw)
+        d_w = torch.empty_like(weights)
+        d_a = torch.empty_like(albedos) if albedos is not None else None
+        cg = lambda g: None if g is None else g.contiguous()
+        g_normal, g_ort, g_alb = cg(g_normal), cg(g_ort), cg(g_alb)
+        with torch.cuda.device(weights.device):
+            check(_lib.lib().pnb_normals_bwd(r, n, _p(n_raw), _p(weights), _p(dirs), _p(albedos), _p(g_normal),
+                                             _p(g_ort), _p(g_alb), _p(d_n), _p(d_w), _p(d_a), _stream()), "normals_bwd")
+        return d_n, d_w, None, d_a
+
+
+def normals_aggregate(n_raw, weights, dirs, albedos=None):
+    return _Normals.apply(n_raw, weights, dirs, albedos)
+
+
+class _EnvCast(torch.autograd.Function):
+    """Surface point o + d*distance (models/pano_mip_nerf.py:321-324) and the env-ray Gaussians of
+    sample_each_points (models/mip.py:154-194).  Differentiable w.r.t. `distance` (detach_dist=False upstream)."""
+
+    @staticmethod
+    def forward(ctx, origins, dirs, distance, env_dirs, env_radii, env_near, env_far, n_env, t_rand):
+        r, d = origins.shape[0], env_dirs.shape[0]
+        dev = origins.device
+        pts = torch.empty(r, 3, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            check(_lib.lib().pnb_surface_point_fwd(r, _p(_req(origins, "origins")), _p(_req(dirs, "dirs")),
+                                                   _p(_req(distance, "distance")), _p(pts), _stream()), "surface_point")
+        t, means, covs = sample_cast(pts, env_dirs, env_radii, env_near, env_far, n_env, t_rand=t_rand, o_div=d,
+                                     d_mod=d, n_rays=r * d, rand_shared=True)
+        ctx.save_for_backward(dirs)
+        ctx.k = d * n_env
+        ctx.mark_non_differentiable(t, covs)
+        return t, means, covs
+
+    @staticmethod
+    def backward(ctx, g_t, g_means, g_covs):
+        (dirs,) = ctx.saved_tensors
+        r = dirs.shape[0]
+        d_dist = torch.empty(r, device=dirs.device, dtype=torch.float32)
+        g_means = g_means.contiguous()
+        with torch.cuda.device(dirs.device):
+            check(_lib.lib().pnb_surface_point_bwd(r, ctx.k, _p(dirs), _p(g_means), _p(d_dist), _stream()),
+                  "surface_point_bwd")
+        return None, None, d_dist, None, None, None, None, None, None
+
+
+def env_cast(origins, dirs, distance, env_dirs, env_radii, env_near, env_far, n_env, t_rand=None):
+    return _EnvCast.apply(origins, dirs, distance, env_dirs, env_radii, env_near, env_far, n_env, t_rand)
+
+
+class _Shade(torch.autograd.Function):
+    """Lambertian surface rendering (utils/surface_rendering.py:104-165, roughness=None branch)."""
+
+    @staticmethod
+    def forward(ctx, env_rgb, albedo, normal, light_dirs, solid_angle):
+        r, d = env_rgb.shape[0], env_rgb.shape[1]
+        dev = env_rgb.device
+        rgb = torch.empty(r, 3, device=dev, dtype=torch.float32)
+        shading = torch.empty(r, 3, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            check(_lib.lib().pnb_shade_fwd(r, d, _p(_req(env_rgb, "env_rgb")), _p(_req(albedo, "albedo")),
+                                           _p(_req(normal, "normal")), _p(_req(light_dirs, "light_dirs")),
+                                           _p(_req(solid_angle, "solid_angle")), _p(rgb), _p(shading), _stream()),
+                  "shade_fwd")
+        ctx.save_for_backward(env_rgb, albedo, normal, light_dirs, solid_angle)
+        return rgb, shading
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_shading):
+        env_rgb, albedo, normal, light_dirs, solid_angle = ctx.saved_tensors
+        r, d = env_rgb.shape[0], env_rgb.shape[1]
+        d_env, d_alb, d_nrm = torch.empty_like(env_rgb), torch.empty_like(albedo), torch.empty_like(normal)
+        cg = lambda g: None if g is None else g.contiguous()
+        g_rgb, g_shading = cg(g_rgb), cg(g_shading)
+        with torch.cuda.device(env_rgb.device):
+            check(_lib.lib().pnb_shade_bwd(r, d, _p(env_rgb), _p(albedo), _p(normal), _p(light_dirs), _p(solid_angle),
+                                           _p(g_rgb), _p(g_shading), _p(d_env), _p(d_alb), _p(d_nrm), _stream()),
+                  "shade_bwd")
+        return d_env, d_alb, d_nrm, None, None
+
+
+def shade(env_rgb, albedo, normal, light_dirs, solid_angle):
+    return _Shade.apply(env_rgb, albedo, normal, light_dirs, solid_angle)
+
+
+class _TonemapMSE(torch.autograd.Function):
+    """sum(mask * (hdr_to_ldr(pred) - gt)^2) / sum(mask)   (systems/panonerf_system.py:44-50)."""
+
+    @staticmethod
+    def forward(ctx, pred, gt_ldr, mask, inv_mask_sum):
+        r = pred.shape[0]
+        partial = torch.empty(r, device=pred.device, dtype=torch.float32)
+        with torch.cuda.device(pred.device):
+            check(_lib.lib().pnb_tonemap_se_fwd(r, _p(_req(pred, "pred")), _p(_req(gt_ldr, "gt")), _p(_req(mask, "mask")),
+                                                _p(partial), _stream()), "tonemap_se_fwd")
+        ctx.save_for_backward(pred, gt_ldr, mask)
+        ctx.inv = inv_mask_sum
+        return dsum(partial, inv_mask_sum)
+
+    @staticmethod
+    def backward(ctx, g):
+        pred, gt_ldr, mask = ctx.saved_tensors
+        d_pred = torch.empty_like(pred)
+        gs = (g * ctx.inv).reshape(1).contiguous()
+        with torch.cuda.device(pred.device):
+            check(_lib.lib().pnb_tonemap_se_bwd(pred.shape[0], _p(pred), _p(gt_ldr), _p(mask), _p(gs), _p(d_pred),
+                                                _stream()), "tonemap_se_bwd")
+        return d_pred, None, None, None
+
+
+def tonemap_mse(pred, gt_ldr, mask, inv_mask_sum: float):
+    return _TonemapMSE.apply(pred, gt_ldr, mask, inv_mask_sum)
+
+
+class _Chroma(torch.autograd.Function):
+    """mean((normalize(gt) - normalize(albedo))^2)   (systems/panonerf_system.py:58-63)."""
+
+    @staticmethod
+    def forward(ctx, gt_ldr, albedo):
+        r = albedo.shape[0]
+        partial = torch.empty(r, device=albedo.device, dtype=torch.float32)
+        with torch.cuda.device(albedo.device):
+            check(_lib.lib().pnb_chroma_fwd(r, _p(_req(gt_ldr, "gt")), _p(_req(albedo, "albedo")), _p(partial),
+                                            _stream()), "chroma_fwd")
+        ctx.save_for_backward(gt_ldr, albedo)
+        return dsum(partial, 1.0 / (3 * r))
+
+    @staticmethod
+    def backward(ctx, g):
+        gt_ldr, albedo = ctx.saved_tensors
+        r = albedo.shape[0]
+        d_alb = torch.empty_like(albedo)
+        gs = (g / (3 * r)).reshape(1).contiguous()
+        with torch.cuda.device(albedo.device):
+            check(_lib.lib().pnb_chroma_bwd(r, _p(gt_ldr), _p(albedo), _p(gs), _p(d_alb), _stream()), "chroma_bwd")
+        return None, d_alb
+
+
+def chroma_loss(gt_ldr, albedo):
+    return _Chroma.apply(gt_ldr, albedo)
+
+
+class _Mean(torch.autograd.Function):
+    """Deterministic mean of a per-ray vector (ort_loss `.mean()`, models/pano_mip_nerf.py:311)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.n = x.numel()
+        ctx.dev = x.device
+        return dsum(x.contiguous(), 1.0 / x.numel())
+
+    @staticmethod
+    def backward(ctx, g):
+        return (g / ctx.n).expand(ctx.n)
+
+
+def dmean(x):
+    return _Mean.apply(x)

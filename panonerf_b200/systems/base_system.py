@@ -1,0 +1,143 @@
+"""Host-side mirror of systems/base_system.py without the Lightning dependency: model construction from the flat
+`hparams` dict (same keys as configs/*.yaml after configs/config.py flattening), the optimiser (fused Adam on one
+flat parameter buffer + MipLRDecay) and the data-parallel gradient all-reduce."""
+import math
+
+import torch
+import torch.distributed as dist
+
+from .. import field, ops
+from ..datasets.base_datasets import Rays
+
+
+def mip_lr_decay(step, lr_init, lr_final, max_steps, lr_delay_steps=0, lr_delay_mult=1.0):
+    """utils/lr_schedule.py:51-60."""
+    if lr_delay_steps > 0:
+        delay_rate = lr_delay_mult + (1 - lr_delay_mult) * math.sin(
+            0.5 * math.pi * min(max(step / lr_delay_steps, 0.0), 1.0))
+    else:
+        delay_rate = 1.0
+    t = min(max(step / max_steps, 0.0), 1.0)
+    return delay_rate * math.exp(math.log(lr_init) * (1 - t) + math.log(lr_final) * t)
+
+
+class FlatAdam:
+    """torch.optim.Adam (defaults) semantics on ONE contiguous fp32 buffer: parameters and their gradients are
+    re-homed as views of flat buffers so that the data-parallel all-reduce is a single NCCL call on 2.45 MB and the
+    update is a single kernel (pnb_adam_step) instead of 24 (systems/base_system.py:81-87 + train.py:92 DDP)."""
+
+    def __init__(self, params, lr_fn):
+        self.params = [p for p in params if p.requires_grad]
+        dev = self.params[0].device
+        n = sum(p.numel() for p in self.params)
+        self.flat_p = torch.empty(n, device=dev, dtype=torch.float32)
+        self.flat_g = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.m = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.v = torch.zeros(n, device=dev, dtype=torch.float32)
+        off = 0
+        with torch.no_grad():
+            for p in self.params:
+                k = p.numel()
+                self.flat_p[off:off + k].copy_(p.reshape(-1))
+                p.data = self.flat_p[off:off + k].view_as(p)
+                p.grad = self.flat_g[off:off + k].view_as(p)
+                off += k
+        self.lr_fn = lr_fn
+        self.step_count = 0
+        field.invalidate_packs()
+
+    def zero_grad(self):
+        self.flat_g.zero_()
+
+    def all_reduce_grads(self):
+        """Sum over ranks (mean taken inside the Adam kernel via grad_scale = 1/world)."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)
+            return 1.0 / dist.get_world_size()
+        return 1.0
+
+    def step(self):
+        scale = self.all_reduce_grads()
+        self.step_count += 1
+        lr = self.lr_fn(self.step_count - 1)
+        ops.adam_step(self.flat_p, self.flat_g, self.m, self.v, lr, self.step_count, grad_scale=scale)
+        field.invalidate_packs()
+        return lr
+
+
+class BaseSystem(torch.nn.Module):
+    """systems/base_system.py:9-55 (model construction) + :81-87 (optimiser)."""
+
+    def __init__(self, hparams):
+        super().__init__()
+        self.hparams = dict(hparams)
+        hp = self.hparams
+        self.train_randomized = hp["train.randomized"]
+        self.val_randomized = hp["val.randomized"]
+        self.white_bkgd = hp["train.white_bkgd"]
+        self.val_chunk_size = hp["val.chunk_size"]
+        self.batch_size = hp["train.batch_size"]
+        self.global_step = 0
+        if hp["nerf.mlp_name"] == "mipnerf":
+            from ..models.mip_nerf import MipNeRF as NeRFModel
+            num_density_channels = 1
+        elif hp["nerf.mlp_name"] == "panonerf":
+            from ..models.pano_mip_nerf import PanoMipNeRF as NeRFModel
+            num_density_channels = 5
+        else:
+            raise ValueError(hp["nerf.mlp_name"])
+        self.mip_nerf = NeRFModel(
+            num_samples=hp["nerf.num_samples"], num_levels=hp["nerf.num_levels"],
+            resample_padding=hp["nerf.resample_padding"], stop_resample_grad=hp["nerf.stop_resample_grad"],
+            use_viewdirs=hp["nerf.use_viewdirs"], disparity=hp["nerf.disparity"], ray_shape=hp["nerf.ray_shape"],
+            min_deg_point=hp["nerf.min_deg_point"], max_deg_point=hp["nerf.max_deg_point"],
+            deg_view=hp["nerf.deg_view"], density_activation=hp["nerf.density_activation"],
+            density_noise=hp["nerf.density_noise"], density_bias=hp["nerf.density_bias"],
+            rgb_activation=hp["nerf.rgb_activation"], alb_activation=hp["nerf.alb_activation"],
+            rgb_padding=hp["nerf.rgb_padding"], disable_integration=hp["nerf.disable_integration"],
+            append_identity=hp["nerf.append_identity"], mlp_net_depth=hp["nerf.mlp.net_depth"],
+            mlp_net_width=hp["nerf.mlp.net_width"], mlp_net_depth_condition=hp["nerf.mlp.net_depth_condition"],
+            mlp_net_width_condition=hp["nerf.mlp.net_width_condition"], mlp_skip_index=hp["nerf.mlp.skip_index"],
+            mlp_num_rgb_channels=hp["nerf.mlp.num_rgb_channels"], mlp_num_density_channels=num_density_channels,
+            mlp_net_activation=hp["nerf.mlp.net_activation"], mlp_name=hp["nerf.mlp_name"],
+            num_env_samples=hp["nerf.num_env_samples"], precision=hp.get("precision"))
+        self.env_rays = None
+
+    def configure_optimizers(self):
+        hp = self.hparams
+        lr_fn = lambda s: mip_lr_decay(s, hp["optimizer.lr_init"], hp["optimizer.lr_final"], hp["optimizer.max_steps"],
+                                       hp["optimizer.lr_delay_steps"], hp["optimizer.lr_delay_mult"])
+        return FlatAdam(self.mip_nerf.mlp.parameters(), lr_fn)
+
+    # ---- losses shared by both systems ---------------------------------------------------------------------------
+    @staticmethod
+    def _gt_ldr(rgbs):
+        return ops.hdr_to_ldr(ops._f32c(rgbs[..., :3]), quantize=True)     # systems/*_system.py:17 / :24
+
+    @staticmethod
+    def _masked_mse(pred_hdr, gt_ldr, mask, inv_mask_sum):
+        return ops.tonemap_mse(pred_hdr, gt_ldr, mask, inv_mask_sum)
+
+
+def default_hparams(mlp_name="panonerf", **over):
+    """configs/{mipnerf,panonerf}.yaml flattened the way configs/config.py:14-32 does (values after literal_eval)."""
+    hp = {
+        "seed": 4, "train.batch_size": 512, "train.batch_type": "all_images", "train.randomized": True,
+        "train.white_bkgd": False, "train.surface": mlp_name == "panonerf", "train.surface_start_step": 0,
+        "val.randomized": False, "val.white_bkgd": False, "val.chunk_size": 512,
+        "nerf.mlp_name": mlp_name, "nerf.num_env_samples": 10, "nerf.num_ray_samples": 10, "nerf.num_samples": 64,
+        "nerf.num_levels": 2, "nerf.resample_padding": 0.01, "nerf.stop_resample_grad": True,
+        "nerf.use_viewdirs": True, "nerf.disparity": False, "nerf.ray_shape": "cone", "nerf.min_deg_point": 0,
+        "nerf.max_deg_point": 16, "nerf.deg_view": 4, "nerf.density_activation": "softplus",
+        "nerf.density_noise": 0.0, "nerf.density_bias": -1.0, "nerf.rgb_activation": "softplus",
+        "nerf.alb_activation": "sigmoid", "nerf.rgb_padding": 0, "nerf.disable_integration": False,
+        "nerf.append_identity": "Ture", "nerf.mlp.num_density_channels": 5, "nerf.mlp.net_depth": 8,
+        "nerf.mlp.net_width": 256, "nerf.mlp.net_depth_condition": 1, "nerf.mlp.net_width_condition": 128,
+        "nerf.mlp.net_activation": "relu", "nerf.mlp.skip_index": 4, "nerf.mlp.num_rgb_channels": 3,
+        "optimizer.lr_init": 2e-4, "optimizer.lr_final": 2e-5, "optimizer.lr_delay_steps": 120,
+        "optimizer.lr_delay_mult": 0.01, "optimizer.max_steps": 44000,
+        "loss.coarse_loss_mult": 0.1, "loss.surface_loss": 1, "loss.ort_loss": 0.1 if mlp_name == "panonerf" else 0,
+        "loss.chrom_loss": 0.1, "range": (0, 10),
+    }
+    hp.update(over)
+    return hp

@@ -1,0 +1,108 @@
+"""CPU: the oracle restatement reproduces every golden vector the unmodified reference produced
+(tests/golden/make_golden.py).  This is what pins the oracle on machines without /root/reference."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from util import O, T, assert_close, golden_rays, golden_state_dict
+
+
+def test_raygen_and_env(golden_ops):
+    g = golden_ops
+    h, w = [int(v) for v in g["raygen_hw"]]
+    rays = O.equirect_rays(h, w, g["raygen_c2w"], 0.0, 10.0)
+    for k in O.Rays._fields:
+        tol = 1e-6 if k == "radii" else 0.0      # NumPy>=2 computed the golden radius in fp64
+        assert torch.allclose(getattr(rays, k), T(g[f"raygen_{k}"]), rtol=tol, atol=0), k
+    env = O.fibonacci_env_rays(10, float(g["env_radius"]))
+    for k in O.Rays._fields:
+        assert torch.equal(getattr(env, k).float(), T(g[f"env_{k}"])), k
+
+
+def test_sampling_and_cast(golden_ops):
+    g = golden_ops
+    h, w = [int(v) for v in g["raygen_hw"]]
+    rays = O.equirect_rays(h, w, g["raygen_c2w"], 0.0, 10.0)
+    r = O.Rays(*[T(g[f"raygen_{k}"])[:24] for k in O.Rays._fields])
+    t, (m, c) = O.sample_along_rays(r.origins, r.directions, r.radii, 16, r.near, r.far, False)
+    assert torch.equal(t, T(g["sample_t"])) and torch.equal(m, T(g["sample_mean"])) and torch.equal(c, T(g["sample_cov"]))
+    t, (m, c) = O.sample_along_rays(r.origins, r.directions, r.radii, 16, r.near, r.far, True, t_rand=T(g["sample_t_rand"]))
+    assert torch.equal(t, T(g["sample_t_r"])) and torch.equal(m, T(g["sample_mean_r"])) and torch.equal(c, T(g["sample_cov_r"]))
+
+
+def test_encodings(golden_ops):
+    g = golden_ops
+    assert torch.equal(O.ipe(T(g["ipe_mean"]), T(g["ipe_cov"]), 0, 16), T(g["ipe_out"]))
+    assert torch.equal(O.pos_enc(T(g["raygen_viewdirs"])[:24], 0, 4), T(g["posenc_out"]))
+
+
+def test_composite_with_grads(golden_ops):
+    g = golden_ops
+    rgb, den = T(g["vr_rgb"]).requires_grad_(), T(g["vr_density"]).requires_grad_()
+    comp, dist, acc, w = O.composite(rgb, den, T(g["vr_t"]), T(g["vr_dirs"]), True)
+    for a, k in ((comp, "vr_comp"), (dist, "vr_dist"), (acc, "vr_acc"), (w, "vr_weights")):
+        assert torch.equal(a, T(g[k])), k
+    ((comp * T(g["vr_g_comp"])).sum() + (dist * T(g["vr_g_dist"])).sum() + (acc * T(g["vr_g_acc"])).sum() +
+     (w * T(g["vr_g_w"])).sum()).backward()
+    assert torch.allclose(rgb.grad, T(g["vr_d_rgb"]), rtol=1e-6, atol=1e-9)
+    # the empty ray (acc == 0) gets NaN density gradients upstream (0/0 in the distance term): keep that visible
+    assert torch.allclose(den.grad, T(g["vr_d_density"]), rtol=1e-5, atol=1e-8, equal_nan=True)
+    assert torch.isnan(T(g["vr_d_density"])[3]).all()
+
+
+def test_resample_bit_exact(golden_ops):
+    g = golden_ops
+    r = O.Rays(*[T(g[f"raygen_{k}"])[:24] for k in O.Rays._fields])
+    new_t, (m, c) = O.resample_along_rays(r.origins, r.directions, r.radii, T(g["rs_t"]), T(g["rs_w"]), False, 0.01)
+    assert torch.equal(new_t, T(g["rs_new_t"])) and torch.equal(m, T(g["rs_mean"])) and torch.equal(c, T(g["rs_cov"]))
+    wb = O.blur_weights(T(g["rs_w"]), 0.01)
+    _, inds, cdf = O.pdf_sample(T(g["rs_t"]), wb, 17, False, return_aux=True)
+    assert torch.equal(inds, T(g["rs_inds"])) and torch.equal(cdf, T(g["rs_cdf"]))
+    out = O.pdf_sample(T(g["rs_t"]), wb, 17, True, u=T(g["rs_u_r"]))
+    assert torch.equal(out, T(g["rs_new_t_r"]))
+
+
+def test_surface_and_tonemap(golden_ops):
+    g = golden_ops
+    rgb, dif, shd = O.lambert_shade(T(g["sr_env"]), T(g["sr_albedo"]), T(g["sr_normal"]), T(g["sr_l"]),
+                                    T(g["env_lossmult"]))
+    assert torch.allclose(rgb, T(g["sr_rgb"]), rtol=1e-6) and torch.allclose(shd, T(g["sr_shading"]), rtol=1e-6)
+    assert torch.equal(O.hdr_to_ldr(T(g["tm_in"])), T(g["tm_out"]))
+    assert torch.equal(O.hdr_to_ldr(T(g["tm_in"]), quantize=True), T(g["tm_out_u8"]))
+
+
+@pytest.mark.parametrize("name,pano", [("mipnerf_w64.npz", False), ("panonerf_w64.npz", True),
+                                       ("mipnerf_w256.npz", False), ("panonerf_w256.npz", True)])
+def test_models_forward_loss_grads(name, pano):
+    g = load_golden(name)
+    sd = {k: v.clone().requires_grad_() for k, v in golden_state_dict(g).items()}
+    rays, env = golden_rays(g)
+    env = O.Rays(*[x.float() for x in env])
+    cfg = dict(num_samples=int(g["n"]))
+    if pano:
+        out, _ = O.panonerf_forward(sd, rays, env, cfg, train=True)
+        names = ["comp_rgb", "distance", "ort_loss", "normal", "albedo", "roughness", "surface_rgb", "diffuse", "shading"]
+        loss = O.panonerf_loss(out, rays, T(g["gt"]))
+    else:
+        out, _ = O.mipnerf_forward(sd, rays, cfg, use_ort_loss=True, train=True)
+        names = ["comp_rgb", "distance", "ort_loss", "normal"]
+        loss = O.mipnerf_loss(out, rays, T(g["gt"]), ort_mult=0.1)
+    for lvl in range(2):
+        for nm, v in zip(names, out[lvl]):
+            key = f"out/{lvl}/{nm}"
+            if key in g:
+                # density-gradient normals are ill-conditioned in fp32 (2^15-scaled IPE derivatives): upstream's own
+                # vmap(jacrev) and autograd.grad disagree at ~1e-5, everything downstream of them inherits that
+                loose = nm in ("normal", "shading", "surface_rgb", "diffuse", "ort_loss")
+                assert torch.allclose(v, T(g[key]), rtol=2e-5, atol=5e-5 if loose else 2e-6), key
+            else:
+                assert v is None or nm == "normal", key
+    assert abs(float(loss) - float(g["loss"])) < 1e-6
+    loss.backward()
+    for k, p in sd.items():
+        gn = float(p.grad.norm())
+        assert abs(gn - float(g["gnorm/" + k])) <= 2e-4 * max(float(g["gnorm/" + k]), 1e-6), k
+        if "grad/" + k in g:
+            ref = T(g["grad/" + k])
+            assert torch.allclose(p.grad, ref, rtol=1e-3, atol=2e-5 * float(ref.abs().max())), k
