@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""Benchmark of the Pano-NeRF hot path on B200 (contract: see the task statement / DESIGN.md §Measurement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload train|render] [--impl ours|reference]
+
+N=1 workload = BASELINE.json configs[1]: the configs/panonerf.yaml training step (mip-NeRF + HDR irradiance +
+surface-rendering branch, ort + chroma losses) on 8192 synthetic equirectangular rays, 64 coarse + 64 fine samples,
+10 env directions x 10 env samples, bf16 tensor-core MLP, forward + backward + gradient all-reduce + Adam.
+Under torchrun every rank trains on its own 8192 rays (weak scaling) and the flat 2.45 MB gradient is all-reduced
+with NCCL.  `--workload render` times the communication-free full-panorama render (configs[2]) instead.
+
+One JSON line is printed by rank 0.  `--impl reference` times the reference algorithm on the host CPU cores
+(oracle/ port of the pure-PyTorch reference; the upstream tree itself is not present on the GPU box).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RAYS_PER_GPU = 8192
+N_SAMPLES = 64
+GRID_HW = (256, 512)
+MLP_FLOP_PER_SAMPLE = 1222656.0          # SURVEY.md §8d, 5 density channels
+JAC_FLOP_PER_SAMPLE = 1016320.0          # one trunk input-gradient pass
+
+
+def camera():
+    c2w = np.eye(4, dtype=np.float32)
+    c2w[:3, 3] = [0.1, 0.2, 0.3]
+    return c2w
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def result(self):
+        self.stop_flag = True
+        self.join(timeout=1.0)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# synthetic inputs
+# ----------------------------------------------------------------------------------------------------------------
+def host_batch(rank, n_rays):
+    """Host-side (pinned) ray batch + HDR ground truth, built from the oracle's equirect generator once."""
+    from oracle import panonerf_oracle as O            # input synthesis only; never on the measured path
+    h, w = GRID_HW
+    rays = O.equirect_rays(h, w, camera(), 0.0, 10.0)
+    g = torch.Generator().manual_seed(rank)
+    perm = torch.randperm(h * w, generator=g)[:n_rays]
+    packed = torch.cat([getattr(rays, k)[perm] for k in O.Rays._fields], dim=1).contiguous()   # [n, 14]
+    gt = torch.rand(n_rays, 3, generator=g) * 2
+    return packed.pin_memory(), gt.pin_memory()
+
+
+def unpack_rays(packed):
+    from panonerf_b200.datasets.base_datasets import Rays
+    widths = (3, 3, 3, 1, 1, 1, 1, 1)
+    out, o = [], 0
+    for wd in widths:
+        out.append(packed[:, o:o + wd].contiguous())
+        o += wd
+    return Rays(*out)
+
+
+def make_system(device, precision="bf16", seed=4):
+    from oracle import panonerf_oracle as O            # deterministic weight factory (checksummed in the tests)
+    from panonerf_b200.systems.base_system import default_hparams
+    from panonerf_b200.systems.panonerf_system import PanoNeRFSystem
+    from panonerf_b200.datasets.pano_datasets import generate_lit_rays, pixel_radius
+    hp = default_hparams("panonerf", precision=precision)
+    hp["train.randomized"] = True
+    system = PanoNeRFSystem(hp).to(device)
+    system.mip_nerf.mlp.load_state_dict(O.synth_state_dict(seed=seed, width=256, c_density=5))
+    radius = pixel_radius(GRID_HW[0], GRID_HW[1], camera(), device)
+    system.env_rays = generate_lit_rays(radius, num=10, device=device)
+    return system
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from panonerf_b200 import field, ops
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(4 + rank)
+    system = make_system(dev)
+    opt = system.configure_optimizers()
+    packed_h, gt_h = host_batch(rank, RAYS_PER_GPU)
+    packed_d, gt_d = packed_h.to(dev), gt_h.to(dev)
+    rays_d = unpack_rays(packed_d)
+
+    def step_resident():
+        opt.zero_grad()
+        loss = system.training_step((rays_d, gt_d))
+        loss.backward()
+        opt.step()
+        return loss
+
+    def step_e2e():
+        p = packed_h.to(dev, non_blocking=True)
+        g = gt_h.to(dev, non_blocking=True)
+        opt.zero_grad()
+        loss = system.training_step((unpack_rays(p), g))
+        loss.backward()
+        opt.step()
+        return float(loss)                       # device -> host read of the step's result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, profile=False):
+        barrier()
+        sampler = ClockSampler(local)
+        sampler.start()
+        l0 = ops.launch_count()
+        if profile:
+            field.PROFILE = {}
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        prof = field.PROFILE
+        field.PROFILE = None
+        clocks = sampler.result()
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), ops.launch_count() - l0, clocks, prof, out
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    ms, launches, clocks, prof, last = timed(step_resident, args.steps, profile=True)
+    for _ in range(2):
+        step_e2e()
+    ms_e2e, _, _, _, _ = timed(step_e2e, args.steps)
+
+    total_rays = RAYS_PER_GPU * world * args.steps
+    value = total_rays / (ms / 1e3)
+    e2e = total_rays / (ms_e2e / 1e3)
+    pk = peaks()
+    roof = roofline_from_profile(prof, args.steps, pk)
+    line = {
+        "metric": "train_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "configs/panonerf.yaml training step: 8192 rays/GPU, 64+64 samples, 10 env dirs x 10 "
+                               "env samples, surface+ort+chroma losses, fwd+bwd+allreduce+Adam",
+                   "rays_per_gpu": RAYS_PER_GPU, "num_samples": N_SAMPLES, "parallelism": f"ray-dp{world}",
+                   "l2": "activations per step are several GB (>> 126 MB L2): every step streams from HBM",
+                   "randomized": True},
+        "clocks": clocks,
+        "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": int(packed_h.numel() * 4 + gt_h.numel() * 4),
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": roof,
+        "final_loss": float(last),
+        "step_tflops": step_flops() * world / (ms / args.steps / 1e3) / 1e12,
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args.cpu_rays)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def step_flops():
+    """Algorithmic MLP FLOPs of one 8192-ray Pano training step: 3x forward for every MLP
+    evaluation (fwd + dgrad + wgrad) plus the normals Jacobian pass and its adjoint (3x one trunk pass)."""
+    main = 2 * N_SAMPLES
+    env = 10 * 10
+    return RAYS_PER_GPU * (3 * (main + env) * MLP_FLOP_PER_SAMPLE + 3 * N_SAMPLES * JAC_FLOP_PER_SAMPLE)
+
+
+def roofline_from_profile(prof, steps, pk):
+    """Dominant kernel = the tcgen05 linear kernel (all trunk/head/dgrad/Jacobian GEMMs).  `achieved` is its
+    ALGORITHMIC HBM bytes (read A once + write C once (+ mask read)) over its CUDA-event time
+    summed over the timed region; it is HBM-bound as an un-fused layer (128 FLOP/B < ridge ~211 FLOP/B)."""
+    if not prof:
+        return None
+    out = {}
+    for name, rec in prof.items():
+        ms = sum(a.elapsed_time(b) for a, b in rec["events"])
+        out[name] = dict(ms=ms, bytes=rec["bytes"], flops=rec["flops"], launches=len(rec["events"]))
+    top = max(out, key=lambda k: out[k]["ms"])
+    r = out[top]
+    gbs = r["bytes"] / (r["ms"] / 1e3) / 1e9
+    tfs = r["flops"] / (r["ms"] / 1e3) / 1e12
+    return {"kernel": top, "bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
+            "traffic": None, "peak_source": pk["src"] + " (sustained copy bandwidth)",
+            "launches_per_step": r["launches"] / steps, "avg_launch_ms": r["ms"] / r["launches"],
+            "kernel_ms_per_step": r["ms"] / steps, "tensor_tflops": tfs, "tensor_frac_of_sustained": tfs / pk["tf_sust"],
+            "all_kernels_ms_per_step": {k: v["ms"] / steps for k, v in out.items()}}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU arm (oracle port of the reference algorithm)
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_train_step(n_rays, threads):
+    from oracle import panonerf_oracle as O
+    torch.set_num_threads(threads)
+    h, w = GRID_HW
+    rays = O.equirect_rays(h, w, camera(), 0.0, 10.0)
+    g = torch.Generator().manual_seed(0)
+    perm = torch.randperm(h * w, generator=g)[:n_rays]
+    rays = O.Rays(*[getattr(rays, k)[perm].contiguous() for k in O.Rays._fields])
+    gt = torch.rand(n_rays, 3, generator=g) * 2
+    env = O.fibonacci_env_rays(10, float(rays.radii[0, 0]))
+    env = O.Rays(*[x.float() for x in env])
+    sd = {k: v.clone().requires_grad_() for k, v in O.synth_state_dict(seed=4, width=256, c_density=5).items()}
+    cfg = dict(num_samples=N_SAMPLES)
+    params = list(sd.values())
+    opt = torch.optim.Adam(params, lr=2e-4)
+
+    def step():
+        opt.zero_grad()
+        torch.manual_seed(0)
+        out, _ = O.panonerf_forward(sd, rays, env, cfg, randomized=True, train=True)
+        loss = O.panonerf_loss(out, rays, gt)
+        loss.backward()
+        opt.step()
+        return float(loss)
+    return step
+
+
+def cpu_baseline(n_rays):
+    threads = os.cpu_count() or 1
+    step = cpu_train_step(n_rays, threads)
+    step()
+    t0 = time.perf_counter()
+    step()
+    dt = time.perf_counter() - t0
+    return {"value": n_rays / dt, "unit": "rays/s", "cores": threads, "kind": "port",
+            "sample": f"one fwd+bwd+Adam step of the same panonerf workload on {n_rays} rays (of 8192), fp32, "
+                      f"torch CPU ops of the oracle port, {dt:.1f} s"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_rays = args.cpu_rays
+    step = cpu_train_step(n_rays, threads)
+    for _ in range(min(args.warmup, 1)):
+        step()
+    steps = min(args.steps, 3)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    v = n_rays * steps / dt
+    print(json.dumps({
+        "impl": "reference", "metric": "train_rays_per_s", "value": v, "unit": "rays/s",
+        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": min(args.warmup, 1),
+        "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs/panonerf.yaml training step (same as the GPU arm), bounded CPU sample",
+                   "rays_per_step": n_rays, "num_samples": N_SAMPLES},
+        "cpu_baseline": {"value": v, "unit": "rays/s", "cores": threads, "kind": "port",
+                         "sample": f"{steps} steps x {n_rays} rays, oracle port of the reference (upstream tree is "
+                                   f"not present on the GPU box), {threads} torch threads"},
+        "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-rays", type=int, default=512)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

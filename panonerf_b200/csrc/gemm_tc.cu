@@ -173,24 +173,56 @@ struct LinearParams {
 
 template <int BLOCK_N, typename OutT>
 __device__ __forceinline__ void store_row_chunk(const LinearParams& p, long long m, int n_base, float* v, int count) {
-  // v[0..count) are columns n_base.. of row m (already offset by the CTA's n0)
+  // v[0..count) are columns n_base.. of row m.  Epilogue order (same as gemm_simt.cu):
+  //   + bias, + row_bias, + previous C (ACCUM), ReLU, mask, store.
+  OutT* crow = reinterpret_cast<OutT*>(p.C) + m * p.ldc;
+  const bool full = n_base + count <= p.Nout;
+  const bool vec_c = full && (p.ldc % 8 == 0) && (n_base % 8 == 0) &&
+                     ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
 #pragma unroll
   for (int i = 0; i < 32; ++i) {
     if (i >= count) break;
     int n = n_base + i;
-    float x = v[i];
     if (n < p.Nout) {
-      if (p.flags & PNB_EPI_BIAS) x += p.bias[n];
-      if (p.row_bias) x += p.row_bias[(m / p.row_group) * p.Nout + n];
-      if (p.flags & PNB_EPI_RELU) x = fmaxf(x, 0.f);
+      if (p.flags & PNB_EPI_BIAS) v[i] += p.bias[n];
+      if (p.row_bias) v[i] += p.row_bias[(m / p.row_group) * p.Nout + n];
     }
-    v[i] = x;
   }
-  OutT* crow = reinterpret_cast<OutT*>(p.C) + m * p.ldc;
-  const bool full = n_base + count <= p.Nout;
+  if (p.flags & PNB_EPI_ACCUM) {
+    if (sizeof(OutT) == 2 && vec_c) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        if (i >= count) break;
+        uint4 prev = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(crow) + n_base + i);
+        const __nv_bfloat16* ph = reinterpret_cast<const __nv_bfloat16*>(&prev);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i + j] += __bfloat162float(ph[j]);
+      }
+    } else if (sizeof(OutT) == 4 && vec_c) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        if (i >= count) break;
+        float4 prev = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(crow) + n_base + i);
+        v[i] += prev.x, v[i + 1] += prev.y, v[i + 2] += prev.z, v[i + 3] += prev.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if (i >= count) break;
+        if (n_base + i < p.Nout) v[i] += to_f32<OutT>(crow[n_base + i]);
+      }
+    }
+  }
+  if (p.flags & PNB_EPI_RELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      if (i >= count) break;
+      v[i] = fmaxf(v[i], 0.f);
+    }
+  }
   if ((p.flags & PNB_EPI_MASK) != 0) {
     const __nv_bfloat16* mrow = p.mask_src + m * p.ld_mask;
-    if (full && (p.ld_mask % 8 == 0) && (n_base % 8 == 0)) {
+    if (full && (p.ld_mask % 8 == 0) && (n_base % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.mask_src) & 15) == 0)) {
 #pragma unroll
       for (int i = 0; i < 32; i += 8) {
         if (i >= count) break;
@@ -201,56 +233,45 @@ __device__ __forceinline__ void store_row_chunk(const LinearParams& p, long long
           if (!(__bfloat162float(h[j]) > 0.f)) v[i + j] = 0.f;
       }
     } else {
-      for (int i = 0; i < count; ++i)
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if (i >= count) break;
         if (n_base + i < p.Nout && !(__bfloat162float(mrow[n_base + i]) > 0.f)) v[i] = 0.f;
+      }
     }
   }
   if (sizeof(OutT) == 2) {
-    if (full && (p.ldc % 8 == 0) && (n_base % 8 == 0)) {
+    __nv_bfloat16* brow = reinterpret_cast<__nv_bfloat16*>(crow);
+    if (vec_c) {
 #pragma unroll
       for (int i = 0; i < 32; i += 8) {
         if (i >= count) break;
         __nv_bfloat162 h[4];
-        if (p.flags & PNB_EPI_ACCUM) {
-          uint4 prev = *reinterpret_cast<const uint4*>(reinterpret_cast<__nv_bfloat16*>(crow) + n_base + i);
-          const __nv_bfloat16* ph = reinterpret_cast<const __nv_bfloat16*>(&prev);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[i + j] += __bfloat162float(ph[j]);
-        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[i + 2 * j], v[i + 2 * j + 1]);
-        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(crow) + n_base + i) =
-            *reinterpret_cast<uint4*>(h);
+        *reinterpret_cast<uint4*>(brow + n_base + i) = *reinterpret_cast<uint4*>(h);
       }
     } else {
-      for (int i = 0; i < count; ++i)
-        if (n_base + i < p.Nout) {
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(crow) + n_base + i;
-          float x = v[i];
-          if (p.flags & PNB_EPI_ACCUM) x += __bfloat162float(*o);
-          *o = __float2bfloat16_rn(x);
-        }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if (i >= count) break;
+        if (n_base + i < p.Nout) brow[n_base + i] = __float2bfloat16_rn(v[i]);
+      }
     }
   } else {
     float* frow = reinterpret_cast<float*>(crow);
-    if (full && (p.ldc % 4 == 0) && (n_base % 4 == 0)) {
+    if (vec_c) {  // ldc % 8 == 0 implies 16-byte aligned float4 rows
 #pragma unroll
       for (int i = 0; i < 32; i += 4) {
         if (i >= count) break;
-        float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-        if (p.flags & PNB_EPI_ACCUM) {
-          float4 prev = *reinterpret_cast<float4*>(frow + n_base + i);
-          o.x += prev.x, o.y += prev.y, o.z += prev.z, o.w += prev.w;
-        }
-        *reinterpret_cast<float4*>(frow + n_base + i) = o;
+        *reinterpret_cast<float4*>(frow + n_base + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
       }
     } else {
-      for (int i = 0; i < count; ++i)
-        if (n_base + i < p.Nout) {
-          float o = v[i];
-          if (p.flags & PNB_EPI_ACCUM) o += frow[n_base + i];
-          frow[n_base + i] = o;
-        }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if (i >= count) break;
+        if (n_base + i < p.Nout) frow[n_base + i] = v[i];
+      }
     }
   }
 }

@@ -89,6 +89,31 @@ class _F32Backend:
         return t if c0 is None else t[:, c0:c1]
 
 
+# bench.py sets PROFILE = {} around its timed region: every tensor-core GEMM launch is then bracketed by CUDA events
+# on the launching stream and its algorithmic bytes / FLOPs are tallied per kernel (roofline evidence).
+PROFILE = None
+
+
+class _prof:
+    def __init__(self, name, nbytes, flops):
+        self.on = PROFILE is not None
+        if self.on:
+            self.rec = PROFILE.setdefault(name, dict(events=[], bytes=0, flops=0))
+            self.rec["bytes"] += nbytes
+            self.rec["flops"] += flops
+
+    def __enter__(self):
+        if self.on:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *a):
+        if self.on:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            self.rec["events"].append((self.e0, e1))
+
+
 _pack_cache: Dict[int, dict] = {}
 _ws_cache: Dict[str, torch.Tensor] = {}
 _pack_epoch = [0]
@@ -158,7 +183,8 @@ class _TCBackend:
         n = w.shape[0]
         assert k == w.shape[1], (a.shape, w.shape)
         k16 = (k + 15) // 16 * 16
-        with torch.cuda.device(a.device):
+        nbytes = m * k * 2 + m * n * out.element_size() * (2 if accum else 1) + (m * n * 2 if mask is not None else 0)
+        with torch.cuda.device(a.device), _prof("linear_tc", nbytes, 2 * m * n * k):
             check(_lib.lib().pnb_linear_tc(m, n, k16, _p(a), _ld(a), _p(w.fwd), _ld(w.fwd), _p(out), _ld(out),
                                            ops.dt_code(out.dtype), _p(bias), _p(row_bias), group, _p(mask),
                                            _ld(mask) if mask is not None else 0, flags, _stream()), "linear_tc")
@@ -169,7 +195,8 @@ class _TCBackend:
         m, n = dz.shape
         k = w.shape[1]
         n16 = (n + 15) // 16 * 16
-        with torch.cuda.device(dz.device):
+        nbytes = m * n * 2 + m * k * out.element_size() * (2 if accum else 1) + (m * k * 2 if mask is not None else 0)
+        with torch.cuda.device(dz.device), _prof("linear_tc", nbytes, 2 * m * n * k):
             check(_lib.lib().pnb_linear_tc(m, k, n16, _p(dz), _ld(dz), _p(w.t), _ld(w.t), _p(out), _ld(out),
                                            ops.dt_code(out.dtype), None, None, 0, _p(mask),
                                            _ld(mask) if mask is not None else 0, flags, _stream()), "linear_tc(dgrad)")
@@ -190,7 +217,7 @@ class _TCBackend:
     def wgrad(self, dz, x, dw):
         m, n = dz.shape
         k = x.shape[1]
-        with torch.cuda.device(dz.device):
+        with torch.cuda.device(dz.device), _prof("wgrad_tc", m * (n + k) * 2, 2 * m * n * k):
             check(_lib.lib().pnb_wgrad_tc(m, n, (k + 15) // 16 * 16, _p(dz), _ld(dz), _p(x), _ld(x), _p(dw), _ld(dw),
                                           _p(self._workspace(dz.device)), _stream()), "wgrad_tc")
 

@@ -1,0 +1,351 @@
+"""GPU parity: every non-GEMM kernel of the C ABI against the golden vectors of the reference and against the
+oracle on seeded inputs.  fp32 tolerance 1e-5 relative (scale-aware) unless noted; indices bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from util import O, T, assert_close, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _rays(g, n=24):
+    return O.Rays(*[T(g[f"raygen_{k}"])[:n].to(DEV) for k in O.Rays._fields])
+
+
+def test_raygen_matches_reference(golden_ops):
+    from panonerf_b200.datasets.pano_datasets import generate_rays, generate_lit_rays, pixel_radius
+    g = golden_ops
+    h, w = [int(v) for v in g["raygen_hw"]]
+    rays = generate_rays(h, w, g["raygen_c2w"], 0.0, 10.0, DEV)
+    for k in O.Rays._fields:
+        assert_close(getattr(rays, k).cpu(), T(g[f"raygen_{k}"]), 2e-6, k)
+    # row-block generation (ray sharding) is bit-identical to the full image
+    part = generate_rays(h, w, g["raygen_c2w"], 0.0, 10.0, DEV, row0=3, nrows=2)
+    for k in O.Rays._fields:
+        assert torch.equal(getattr(part, k), getattr(rays, k)[3 * w:5 * w]), k
+    rad = pixel_radius(h, w, g["raygen_c2w"], DEV)
+    assert abs(rad - float(g["env_radius"])) < 2e-6 * rad
+    env = generate_lit_rays(float(g["env_radius"]), num=10, device=DEV)
+    for k in O.Rays._fields:
+        assert torch.equal(getattr(env, k).float().cpu(), T(g[f"env_{k}"])), k
+
+
+def test_raygen_large_panorama_properties():
+    from panonerf_b200.datasets.pano_datasets import generate_rays
+    c2w = np.eye(4, dtype=np.float32)
+    c2w[:3, 3] = [0.1, 0.2, 0.3]
+    h, w = 512, 1024
+    rays = generate_rays(h, w, c2w, 0.0, 10.0, DEV)
+    ref = O.equirect_rays(h, w, c2w, 0.0, 10.0)
+    assert_close(rays.directions.cpu(), ref.directions, 1e-5, "directions", floor=1.0)
+    assert_close(rays.viewdirs.cpu(), ref.viewdirs, 1e-5, "viewdirs", floor=1.0)
+    # the per-column radius is a difference of nearly equal fp32 vectors: 1 ulp of a direction is 2e-5 of it
+    assert_close(rays.radii.cpu(), ref.radii, 1e-4, "radii")
+    assert torch.allclose(rays.viewdirs.norm(dim=-1), torch.ones(h * w, device=DEV), atol=1e-6)
+
+
+def test_sample_cast(golden_ops):
+    from panonerf_b200.models import mip
+    g = golden_ops
+    r = _rays(g)
+    t, (m, c) = mip.sample_along_rays(r.origins, r.directions, r.radii, 16, r.near, r.far, False, False, "cone")
+    assert torch.equal(t.cpu(), T(g["sample_t"]))
+    assert_close(m.cpu(), T(g["sample_mean"]), 1e-6, "mean")
+    assert_close(c.cpu(), T(g["sample_cov"]), 1e-5, "cov")
+    t, (m, c) = mip.sample_along_rays(r.origins, r.directions, r.radii, 16, r.near, r.far, True, False, "cone",
+                                      t_rand=T(g["sample_t_rand"]).to(DEV))
+    assert_close(t.cpu(), T(g["sample_t_r"]), 1e-6, "t_rand")
+    assert_close(m.cpu(), T(g["sample_mean_r"]), 1e-6, "mean_r")
+    assert_close(c.cpu(), T(g["sample_cov_r"]), 1e-5, "cov_r")
+    with pytest.raises(NotImplementedError):
+        mip.sample_along_rays(r.origins, r.directions, r.radii, 16, r.near, r.far, False, False, "cylinder")
+    with pytest.raises(AssertionError):
+        mip.cast_rays(t, r.origins, r.directions, r.radii, "sphere")
+
+
+def test_randomized_stream_equals_reference(golden_ops):
+    """With the same seed the model-side draw consumes torch's CUDA generator exactly like upstream would."""
+    from panonerf_b200.models import mip
+    r = _rays(golden_ops)
+    torch.manual_seed(3)
+    t1, _ = mip.sample_along_rays(r.origins, r.directions, r.radii, 16, r.near, r.far, True, False, "cone")
+    torch.manual_seed(3)
+    t_rand = torch.rand(24, 17, device=DEV)
+    cpu = lambda x: x.cpu()
+    t2, _ = O.sample_along_rays(cpu(r.origins), cpu(r.directions), cpu(r.radii), 16, cpu(r.near), cpu(r.far), True,
+                                t_rand=t_rand.cpu())
+    assert_close(t1.cpu(), t2, 1e-6, "t")
+
+
+def test_disparity_sampling(golden_ops):
+    from panonerf_b200.models import mip
+    r = _rays(golden_ops)
+    near = torch.full_like(r.near, 0.5)
+    t, (m, c) = mip.sample_along_rays(r.origins, r.directions, r.radii, 32, near, r.far, False, True, "cone")
+    cpu = lambda x: x.cpu()
+    t2, (m2, c2) = O.sample_along_rays(cpu(r.origins), cpu(r.directions), cpu(r.radii), 32, cpu(near), cpu(r.far),
+                                       False, disparity=True)
+    assert_close(t.cpu(), t2, 1e-6, "t")
+    assert_close(c.cpu(), c2, 1e-5, "cov")
+
+
+def test_ipe_and_posenc(golden_ops):
+    from panonerf_b200.models import mip
+    g = golden_ops
+    enc = mip.integrated_pos_enc((T(g["ipe_mean"]).to(DEV), T(g["ipe_cov"]).to(DEV)), 0, 16)
+    assert float((enc.cpu() - T(g["ipe_out"])).abs().max()) < 2e-6
+    pe = mip.pos_enc(_rays(g).viewdirs, 0, 4, True)
+    assert float((pe.cpu() - T(g["posenc_out"])).abs().max()) < 1e-6
+    # large seeded case + the vjp / jvp pair against autograd
+    gen = torch.Generator().manual_seed(0)
+    mean = (torch.rand(4096, 3, generator=gen) * 10 - 5)
+    cov = torch.rand(4096, 3, generator=gen) * torch.tensor([1e-6, 1e-4, 1e-2])
+    mean_r = mean.clone().requires_grad_()
+    ref = O.ipe(mean_r, cov, 0, 16)
+    from panonerf_b200 import ops
+    out = torch.empty(4096, 96, device=DEV)
+    ops.ipe_into(mean.to(DEV), cov.to(DEV), 0, 16, out)
+    assert float((out.cpu() - ref.detach()).abs().max()) < 2e-6
+    gvec = torch.randn(4096, 96, generator=gen)
+    (gref,) = torch.autograd.grad((ref * gvec).sum(), mean_r)
+    gout = ops.ipe_vjp(mean.to(DEV), cov.to(DEV), 0, 16, gvec.to(DEV))
+    assert_close(gout.cpu(), gref, 2e-5, "ipe_vjp")
+    v = torch.randn(4096, 3, generator=gen)
+    jv = torch.empty(4096, 96, device=DEV)
+    ops.ipe_jvp_into(mean.to(DEV), cov.to(DEV), 0, 16, v.to(DEV), jv)
+    # <J v, g> == <v, J^T g>
+    lhs = float((jv.cpu().double() * gvec.double()).sum())
+    rhs = float((gref.double() * v.double()).sum())
+    assert abs(lhs - rhs) <= 1e-4 * max(abs(rhs), 1.0)
+    # bf16 output variant writes into a strided buffer
+    buf = torch.zeros(4096, 352, device=DEV, dtype=torch.bfloat16)
+    ops.ipe_into(mean.to(DEV), cov.to(DEV), 0, 16, buf[:, 256:])
+    assert float((buf[:, 256:].float().cpu() - ref.detach()).abs().max()) < 4e-3
+    assert float(buf[:, :256].abs().max()) == 0.0
+
+
+def test_composite_fwd_bwd(golden_ops):
+    from panonerf_b200 import ops
+    g = golden_ops
+    rgb = T(g["vr_rgb"]).to(DEV).requires_grad_()
+    den = T(g["vr_density"])[..., 0].contiguous().to(DEV).requires_grad_()
+    comp, dist, acc, w = ops.composite(rgb, den, T(g["vr_t"]).to(DEV), T(g["vr_dirs"]).to(DEV), True)
+    assert_close(comp.cpu(), T(g["vr_comp"]), 1e-5, "comp")
+    assert_close(dist.cpu(), T(g["vr_dist"]), 1e-5, "dist")
+    assert_close(acc.cpu(), T(g["vr_acc"]), 1e-5, "acc", floor=1e-3)
+    # alpha = 1 - exp(-x) cancels for small x: 1 ulp of expf is 6e-8 ABSOLUTE on a weight in [0,1]
+    assert_close(w.cpu(), T(g["vr_weights"]), 1e-5, "weights", floor=2e-2)
+    ((comp * T(g["vr_g_comp"]).to(DEV)).sum() + (dist * T(g["vr_g_dist"]).to(DEV)).sum() +
+     (acc * T(g["vr_g_acc"]).to(DEV)).sum() + (w * T(g["vr_g_w"]).to(DEV)).sum()).backward()
+    assert_close(rgb.grad.cpu(), T(g["vr_d_rgb"]), 1e-5, "d_rgb", floor=1e-4)
+    ref = T(g["vr_d_density"])[..., 0]
+    ok = ~torch.isnan(ref).any(dim=1)           # the empty ray: upstream returns NaN, the kernel a finite gradient
+    assert torch.isfinite(den.grad).all()
+    assert_close(den.grad.cpu()[ok], ref[ok], 2e-5, "d_density", floor=1e-3)
+
+
+def test_composite_seeded_large():
+    from panonerf_b200 import ops
+    gen = torch.Generator().manual_seed(5)
+    R, N = 2048, 128
+    rgb = torch.rand(R, N, 3, generator=gen)
+    den = -torch.log(torch.rand(R, N, generator=gen))
+    t = torch.sort(torch.rand(R, N + 1, generator=gen) * 10, dim=-1).values
+    dirs = torch.randn(R, 3, generator=gen)
+    rgb_r, den_r = rgb.clone().requires_grad_(), den.clone().requires_grad_()
+    ref = O.composite(rgb_r, den_r[..., None], t, dirs, False)
+    rgb_g, den_g = rgb.to(DEV).requires_grad_(), den.to(DEV).requires_grad_()
+    out = ops.composite(rgb_g, den_g, t.to(DEV), dirs.to(DEV), False)
+    gs = [torch.rand(x.shape, generator=gen) for x in ref]
+    sum((a * b).sum() for a, b in zip(ref, gs)).backward()
+    sum((a * b.to(DEV)).sum() for a, b in zip(out, gs)).backward()
+    for a, b, nm in zip(out, ref, ("comp", "dist", "acc", "w")):
+        assert_close(a.cpu(), b.detach(), 1e-5, nm, floor=2e-2)
+    assert_close(rgb_g.grad.cpu(), rgb_r.grad, 2e-5, "d_rgb", floor=1e-3)
+    assert_close(den_g.grad.cpu(), den_r.grad, 5e-5, "d_density", floor=1e-2)
+    # size-independent property: weights are a sub-stochastic partition of unity, acc = sum(w) in [0,1]
+    assert float(out[2].max()) <= 1.0 + 1e-6 and float(out[3].min()) >= 0.0
+
+
+def test_resample_bit_exact_indices(golden_ops):
+    from panonerf_b200.models import mip
+    g = golden_ops
+    r = _rays(g)
+    new_t, (m, c), inds = mip.resample_along_rays(r.origins, r.directions, r.radii, T(g["rs_t"]).to(DEV),
+                                                  T(g["rs_w"]).to(DEV), False, "cone", True, 0.01, return_inds=True)
+    assert torch.equal(inds.cpu(), T(g["rs_inds"])), "searchsorted indices must be bit-exact"
+    assert_close(new_t.cpu(), T(g["rs_new_t"]), 1e-5, "new_t")
+    assert_close(m.cpu(), T(g["rs_mean"]), 1e-5, "mean")
+    assert_close(c.cpu(), T(g["rs_cov"]), 1e-4, "cov", floor=1e-6)
+    assert bool((new_t[:, 1:] >= new_t[:, :-1]).all()), "resampled fence-posts must be sorted"
+    # randomized: same u -> same samples; plain sorted_piecewise_constant_pdf on pre-blurred weights
+    wb = O.blur_weights(T(g["rs_w"]), 0.01).to(DEV)
+    out = mip.sorted_piecewise_constant_pdf(T(g["rs_t"]).to(DEV), wb, 17, True, u=T(g["rs_u_r"]).to(DEV))
+    assert_close(out.cpu(), T(g["rs_new_t_r"]), 1e-5, "new_t_r")
+    with pytest.raises(NotImplementedError):
+        mip.resample_along_rays(r.origins, r.directions, r.radii, T(g["rs_t"]).to(DEV), T(g["rs_w"]).to(DEV), False,
+                                "cone", False, 0.01)
+
+
+@pytest.mark.parametrize("n", [64, 128, 256])
+def test_resample_seeded(n):
+    from panonerf_b200 import ops
+    gen = torch.Generator().manual_seed(n)
+    R = 4096
+    w = torch.rand(R, n, generator=gen) ** 4
+    w[0] = 0.0
+    w[1] = 0.0
+    w[1, n // 2] = 1.0
+    t = torch.sort(torch.rand(R, n + 1, generator=gen) * 10, dim=-1).values
+    ref, inds_ref, _ = O.pdf_sample(t, O.blur_weights(w, 0.01), n + 1, False, return_aux=True)
+    out, inds = ops.resample(t.to(DEV), w.to(DEV), 0.01, return_inds=True)
+    mism = int((inds.cpu() != inds_ref).sum())
+    # the only source of disagreement is the 1-ulp freedom of torch.sum's CPU reduction order in weight_sum (AVX
+    # lane order, not reproducible across hosts); the inverse CDF is continuous, so even then the sample agrees
+    assert mism <= R * (n + 1) // 20000, f"{mism} index mismatches"
+    assert_close(out.cpu(), ref, 5e-5, "new_t", floor=0.1)
+    assert bool((out[:, 1:] >= out[:, :-1]).all())
+    assert float(out.min()) >= float(t.min()) and float(out.max()) <= float(t.max())
+
+
+def test_activations_and_density_grad():
+    from panonerf_b200 import ops, _lib
+    gen = torch.Generator().manual_seed(1)
+    M, C = 5000, 5
+    raw_rgb = torch.randn(M, 3, generator=gen) * 8
+    raw_den = torch.randn(M, C, generator=gen) * 8
+    raw_rgb[0, 0], raw_den[0, 0] = 25.0, 30.0            # softplus threshold branch
+    rr, rd = raw_rgb.clone().requires_grad_(), raw_den.clone().requires_grad_()
+    rgb = O.softplus(rr) * (1 + 2 * 0.001) - 0.001
+    den = O.softplus(rd[..., :1] - 1.0)
+    alb = torch.sigmoid(rd[..., 1:-1]) * 0.77 + 0.03
+    g1, g2, g3 = torch.randn(M, 3, generator=gen), torch.randn(M, generator=gen), torch.randn(M, 3, generator=gen)
+    ((rgb * g1).sum() + (den[:, 0] * g2).sum() + (alb * g3).sum()).backward()
+    a, b = raw_rgb.to(DEV).requires_grad_(), raw_den.to(DEV).requires_grad_()
+    o1, o2, o3 = ops.activations(a, b, -1.0, 0.001, True)
+    assert_close(o1.cpu(), rgb.detach(), 1e-5, "rgb", floor=1e-3)
+    assert_close(o2.cpu(), den.detach()[:, 0], 1e-5, "density", floor=1e-3)
+    assert_close(o3.cpu(), alb.detach(), 1e-5, "albedo")
+    ((o1 * g1.to(DEV)).sum() + (o2 * g2.to(DEV)).sum() + (o3 * g3.to(DEV)).sum()).backward()
+    assert_close(a.grad.cpu(), rr.grad, 1e-5, "d_raw_rgb", floor=1e-3)
+    assert_close(b.grad.cpu(), rd.grad, 2e-5, "d_raw_den", floor=1e-3)
+
+
+def test_normals_aggregate_fwd_bwd():
+    from panonerf_b200 import ops
+    import torch.nn.functional as F
+    gen = torch.Generator().manual_seed(2)
+    R, N = 300, 64
+    n_raw = torch.randn(R, N, 3, generator=gen) * torch.rand(R, N, 1, generator=gen) * 10
+    w = torch.rand(R, N, generator=gen) ** 3
+    dirs = torch.randn(R, 3, generator=gen)
+    albs = torch.rand(R, N, 3, generator=gen)
+    a, b, c = n_raw.clone().requires_grad_(), w.clone().requires_grad_(), albs.clone().requires_grad_()
+    nh = F.normalize(a, dim=-1)
+    nw = b[..., None] / torch.sum(b, -1).view(-1, 1, 1)
+    normal = F.normalize(torch.sum(nw * nh, dim=1), dim=-1)
+    ort = torch.sum(nw * torch.relu(torch.bmm(nh, dirs.view(-1, 3, 1))) ** 2, dim=1)[:, 0]
+    alb = torch.sum(nw * c, dim=1)
+    g1, g2, g3 = torch.randn(R, 3, generator=gen), torch.randn(R, generator=gen), torch.randn(R, 3, generator=gen)
+    ((normal * g1).sum() + (ort * g2).sum() + (alb * g3).sum()).backward()
+    x, y, z = n_raw.to(DEV).requires_grad_(), w.to(DEV).requires_grad_(), albs.to(DEV).requires_grad_()
+    o1, o2, o3 = ops.normals_aggregate(x, y, dirs.to(DEV), z)
+    assert_close(o1.cpu(), normal.detach(), 2e-5, "normal", floor=1e-2)
+    assert_close(o2.cpu(), ort.detach(), 1e-5, "ort", floor=1e-3)
+    assert_close(o3.cpu(), alb.detach(), 1e-5, "albedo")
+    ((o1 * g1.to(DEV)).sum() + (o2 * g2.to(DEV)).sum() + (o3 * g3.to(DEV)).sum()).backward()
+    assert_close(x.grad.cpu(), a.grad, 5e-5, "d_n_raw", floor=float(a.grad.abs().mean()))
+    assert_close(y.grad.cpu(), b.grad, 5e-5, "d_weights", floor=float(b.grad.abs().mean()))
+    assert_close(z.grad.cpu(), c.grad, 1e-5, "d_albedos", floor=1e-4)
+
+
+def test_env_cast_and_shade(golden_ops):
+    from panonerf_b200 import ops
+    g = golden_ops
+    gen = torch.Generator().manual_seed(4)
+    r = O.Rays(*[T(g[f"raygen_{k}"])[:24] for k in O.Rays._fields])
+    env = O.Rays(*[T(g[f"env_{k}"]) for k in O.Rays._fields])
+    dist = (torch.rand(24, generator=gen) * 5).requires_grad_()
+    pts = r.origins + r.directions * dist.view(-1, 1)
+    t_ref, (m_ref, c_ref), _ = O.env_samples(pts, env, 10, False)
+    gm = torch.randn(m_ref.shape, generator=gen)
+    (m_ref * gm).sum().backward()
+    d = dist.detach().to(DEV).requires_grad_()
+    f = lambda x: x.to(DEV)
+    t, m, c = ops.env_cast(f(r.origins), f(r.directions), d, f(env.directions), f(env.radii), f(env.near), f(env.far), 10)
+    assert_close(t.cpu(), t_ref, 1e-6, "t")
+    assert_close(m.cpu(), m_ref.detach(), 1e-6, "means")
+    assert_close(c.cpu(), c_ref, 1e-5, "covs", floor=1e-6)
+    (m * gm.to(DEV)).sum().backward()
+    assert_close(d.grad.cpu(), dist.grad, 1e-5, "d_dist", floor=1e-2)
+    # shading fwd vs the reference vectors, bwd vs autograd of the oracle
+    e, a, n = T(g["sr_env"]).requires_grad_(), T(g["sr_albedo"]).requires_grad_(), T(g["sr_normal"]).requires_grad_()
+    rgb_ref, _, shd_ref = O.lambert_shade(e, a, n, T(g["sr_l"]), env.lossmult)
+    assert torch.allclose(rgb_ref, T(g["sr_rgb"]), rtol=1e-6)
+    g1, g2 = torch.randn(24, 3, generator=gen), torch.randn(24, 3, generator=gen)
+    ((rgb_ref * g1).sum() + (shd_ref * g2).sum()).backward()
+    e2, a2, n2 = [T(g[k]).to(DEV).requires_grad_() for k in ("sr_env", "sr_albedo", "sr_normal")]
+    rgb, shd = ops.shade(e2, a2, n2, f(env.directions), f(env.lossmult).reshape(-1).contiguous())
+    assert_close(rgb.cpu(), T(g["sr_rgb"]), 1e-5, "surface_rgb")
+    assert_close(shd.cpu(), T(g["sr_shading"]), 1e-5, "shading")
+    ((rgb * g1.to(DEV)).sum() + (shd * g2.to(DEV)).sum()).backward()
+    assert_close(e2.grad.cpu(), e.grad, 1e-5, "d_env", floor=1e-3)
+    assert_close(a2.grad.cpu(), a.grad, 1e-5, "d_albedo", floor=1e-3)
+    assert_close(n2.grad.cpu(), n.grad, 1e-5, "d_normal", floor=1e-3)
+
+
+def test_tonemap_losses(golden_ops):
+    from panonerf_b200 import ops
+    from panonerf_b200.utils.surface_rendering import hdr_to_ldr
+    import torch.nn.functional as F
+    g = golden_ops
+    x = T(g["tm_in"]).to(DEV)
+    assert_close(hdr_to_ldr(x).cpu(), T(g["tm_out"]), 1e-5, "ldr", floor=1e-2)
+    q = hdr_to_ldr(x, dtype="uint8").cpu()
+    assert float((q - T(g["tm_out_u8"])).abs().max()) < 1e-6, "uint8 quantisation must agree"
+    gen = torch.Generator().manual_seed(6)
+    R = 1000
+    pred = (torch.rand(R, 3, generator=gen) * 3 + 1e-3)
+    gt = O.hdr_to_ldr(torch.rand(R, 3, generator=gen) * 2, quantize=True)
+    mask = torch.ones(R, 1)
+    p = pred.clone().requires_grad_()
+    ref = (mask * (O.hdr_to_ldr(p) - gt) ** 2).sum() / mask.sum()
+    ref.backward()
+    p2 = pred.to(DEV).requires_grad_()
+    out = ops.tonemap_mse(p2, gt.to(DEV), mask.reshape(-1).to(DEV), 1.0 / R)
+    assert abs(float(out) - float(ref)) < 1e-6 * max(1.0, abs(float(ref)))
+    out.backward()
+    assert_close(p2.grad.cpu(), p.grad, 2e-5, "d_pred", floor=float(p.grad.abs().mean()))
+    alb = torch.rand(R, 3, generator=gen).requires_grad_()
+    ref = ((F.normalize(gt, dim=-1) - F.normalize(alb, dim=-1)) ** 2).mean()
+    ref.backward()
+    a2 = alb.detach().to(DEV).requires_grad_()
+    out = ops.chroma_loss(gt.to(DEV), a2)
+    assert abs(float(out) - float(ref)) < 1e-6
+    out.backward()
+    assert_close(a2.grad.cpu(), alb.grad, 2e-5, "d_albedo", floor=float(alb.grad.abs().mean()))
+
+
+def test_adam_matches_torch():
+    from panonerf_b200 import ops
+    gen = torch.Generator().manual_seed(7)
+    n = 100003
+    p0 = torch.randn(n, generator=gen)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=2e-4)
+    p = p0.to(DEV)
+    m, v = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    for step in range(1, 4):
+        g = torch.randn(n, generator=gen)
+        ref.grad = g.clone()
+        opt.step()
+        ops.adam_step(p, g.to(DEV), m, v, 2e-4, step)
+    assert_close(p.cpu(), ref.detach(), 1e-6, "adam")
+
+
+def test_no_cpu_fallback():
+    from panonerf_b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.pos_enc(torch.zeros(4, 3), 4)
