@@ -163,6 +163,12 @@ int pnb_gemm_f32(int mode, long long M, int N, long long K, const float* A, int 
                  float* C, int ldc, const float* bias, const float* row_bias, int row_group, const float* mask_src,
                  int ld_mask, int flags, void* stream);
 
+/* the same three GEMM modes on bf16-stored A/B/mask (fp32 FFMA arithmetic, C bf16 or fp32): the CUDA-core twin of
+ * the tensor-core path below, used to validate it on identical bf16 data. */
+int pnb_gemm_bf16_simt(int mode, long long M, int N, long long K, const void* A, int lda, const void* B, int ldb,
+                       void* C, int ldc, int c_dtype, const float* bias, const float* row_bias, int row_group,
+                       const void* mask_src, int ld_mask, int flags, void* stream);
+
 /* bf16 tensor-core path (tcgen05.mma, TMEM accumulators, TMA-fed):
  * C[M,Nout] = A[M,K](bf16, lda) * W[Nout,K]^T (bf16, ldw) with fp32 accumulation; epilogue flags as above;
  * C dtype = c_dtype (bf16 or fp32), bias fp32 [Nout], mask_src bf16 [M,Nout].  16 <= K <= 384 (K % 16 == 0).

@@ -17,11 +17,11 @@ __device__ __forceinline__ long long b_off(long long k, long long n, int ldb) {
   return MODE == 0 ? n * ldb + k : k * ldb + n;
 }
 
-template <int MODE>
+template <int MODE, typename TIn, typename TOut>
 __global__ void __launch_bounds__(256)
-gemm_f32_kernel(long long M, int N, long long K, long long k_chunk, const float* __restrict__ A, int lda,
-                const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc, const float* __restrict__ bias,
-                const float* __restrict__ row_bias, int row_group, const float* __restrict__ mask_src, int ld_mask,
+gemm_f32_kernel(long long M, int N, long long K, long long k_chunk, const TIn* __restrict__ A, int lda,
+                const TIn* __restrict__ B, int ldb, TOut* __restrict__ C, int ldc, const float* __restrict__ bias,
+                const float* __restrict__ row_bias, int row_group, const TIn* __restrict__ mask_src, int ld_mask,
                 int flags) {
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
@@ -48,7 +48,7 @@ gemm_f32_kernel(long long M, int N, long long K, long long k_chunk, const float*
         kk = tid & 15, mm = (tid >> 4) + 16 * p;
       }
       long long m = m0 + mm, k = k0 + kk;
-      As[kk][mm] = (m < M && k < k_end) ? A[a_off<MODE>(m, k, lda)] : 0.f;
+      As[kk][mm] = (m < M && k < k_end) ? to_f32<TIn>(A[a_off<MODE>(m, k, lda)]) : 0.f;
     }
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
@@ -59,9 +59,16 @@ gemm_f32_kernel(long long M, int N, long long K, long long k_chunk, const float*
         nn = tid & 63, kk = (tid >> 6) + 4 * p;
       }
       long long n = n0 + nn, k = k0 + kk;
-      Bs[kk][nn] = (n < N && k < k_end) ? B[b_off<MODE>(k, n, ldb)] : 0.f;
+      Bs[kk][nn] = (n < N && k < k_end) ? to_f32<TIn>(B[b_off<MODE>(k, n, ldb)]) : 0.f;
     }
     __syncthreads();
+    // two-level summation: a 16-term partial per k-block, then one add into the running total (error grows with
+    // K/16 + 16 instead of K terms - keeps the ill-conditioned Jacobian chain as accurate as a blocked CPU GEMM)
+    float part[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) part[i][j] = 0.f;
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
       float a[4], b[4];
@@ -72,8 +79,12 @@ gemm_f32_kernel(long long M, int N, long long K, long long k_chunk, const float*
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) part[i][j] = fmaf(a[i], b[j], part[i][j]);
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] += part[i][j];
     __syncthreads();
   }
 
@@ -87,14 +98,15 @@ gemm_f32_kernel(long long M, int N, long long K, long long k_chunk, const float*
       if (n >= N) continue;
       float v = acc[i][j];
       if (MODE == 2) {
-        atomicAdd(C + m * ldc + n, v);  // split over the sample axis; C is an accumulating gradient buffer
+        // split over the sample axis; C is an accumulating fp32 gradient buffer
+        atomicAdd(reinterpret_cast<float*>(C) + m * ldc + n, v);
       } else {
         if (flags & PNB_EPI_BIAS) v += bias[n];
         if (row_bias) v += row_bias[(m / row_group) * N + n];
-        if (flags & PNB_EPI_ACCUM) v += C[m * ldc + n];
+        if (flags & PNB_EPI_ACCUM) v += to_f32<TOut>(C[m * ldc + n]);
         if (flags & PNB_EPI_RELU) v = fmaxf(v, 0.f);
-        if (flags & PNB_EPI_MASK) v = mask_src[m * ld_mask + n] > 0.f ? v : 0.f;
-        C[m * ldc + n] = v;
+        if (flags & PNB_EPI_MASK) v = to_f32<TIn>(mask_src[m * ld_mask + n]) > 0.f ? v : 0.f;
+        C[m * ldc + n] = from_f32<TOut>(v);
       }
     }
   }
@@ -104,16 +116,11 @@ gemm_f32_kernel(long long M, int N, long long K, long long k_chunk, const float*
 
 using namespace pnb;
 
-extern "C" int pnb_gemm_f32(int mode, long long M, int N, long long K, const float* A, int lda, const float* B, int ldb,
-                            float* C, int ldc, const float* bias, const float* row_bias, int row_group,
-                            const float* mask_src, int ld_mask, int flags, void* stream) {
-  PNB_REQUIRE(mode >= 0 && mode <= 2 && M >= 0 && N > 0 && K >= 0, "gemm_f32: bad arguments");
-  PNB_REQUIRE(!(flags & PNB_EPI_BIAS) || bias != nullptr, "gemm_f32: bias flag without bias");
-  PNB_REQUIRE(!(flags & PNB_EPI_MASK) || mask_src != nullptr, "gemm_f32: mask flag without mask source");
-  PNB_REQUIRE(row_bias == nullptr || row_group > 0, "gemm_f32: row_bias needs row_group");
-  if (M == 0 || K == 0) return 0;
+template <typename TIn, typename TOut>
+static int launch_gemm(int mode, long long M, int N, long long K, const void* A, int lda, const void* B, int ldb, void* C,
+                       int ldc, const float* bias, const float* row_bias, int row_group, const void* mask_src,
+                       int ld_mask, int flags, void* stream) {
   long long gm = (M + BM - 1) / BM;
-  PNB_REQUIRE(gm < (1ll << 31), "gemm_f32: M too large");
   dim3 grid((unsigned)gm, (unsigned)((N + BN - 1) / BN), 1);
   long long k_chunk = K;
   if (mode == 2) {
@@ -127,14 +134,54 @@ extern "C" int pnb_gemm_f32(int mode, long long M, int N, long long K, const flo
     grid.z = (unsigned)((K + k_chunk - 1) / k_chunk);
   }
   cudaStream_t st = as_stream(stream);
+  const TIn* a = (const TIn*)A;
+  const TIn* b = (const TIn*)B;
+  const TIn* ms = (const TIn*)mask_src;
+  TOut* c = (TOut*)C;
   if (mode == 0)
-    gemm_f32_kernel<0><<<grid, 256, 0, st>>>(M, N, K, k_chunk, A, lda, B, ldb, C, ldc, bias, row_bias, row_group, mask_src,
-                                             ld_mask, flags);
+    gemm_f32_kernel<0, TIn, TOut><<<grid, 256, 0, st>>>(M, N, K, k_chunk, a, lda, b, ldb, c, ldc, bias, row_bias, row_group,
+                                                       ms, ld_mask, flags);
   else if (mode == 1)
-    gemm_f32_kernel<1><<<grid, 256, 0, st>>>(M, N, K, k_chunk, A, lda, B, ldb, C, ldc, bias, row_bias, row_group, mask_src,
-                                             ld_mask, flags);
+    gemm_f32_kernel<1, TIn, TOut><<<grid, 256, 0, st>>>(M, N, K, k_chunk, a, lda, b, ldb, c, ldc, bias, row_bias, row_group,
+                                                       ms, ld_mask, flags);
   else
-    gemm_f32_kernel<2><<<grid, 256, 0, st>>>(M, N, K, k_chunk, A, lda, B, ldb, C, ldc, bias, row_bias, row_group, mask_src,
-                                             ld_mask, flags);
-  return finish("gemm_f32");
+    gemm_f32_kernel<2, TIn, TOut><<<grid, 256, 0, st>>>(M, N, K, k_chunk, a, lda, b, ldb, c, ldc, bias, row_bias, row_group,
+                                                       ms, ld_mask, flags);
+  return finish("gemm_simt");
+}
+
+static int check_gemm_args(int mode, long long M, int N, long long K, const float* bias, const float* row_bias,
+                           int row_group, const void* mask_src, int flags) {
+  PNB_REQUIRE(mode >= 0 && mode <= 2 && M >= 0 && N > 0 && K >= 0, "gemm: bad arguments");
+  PNB_REQUIRE(!(flags & PNB_EPI_BIAS) || bias != nullptr, "gemm: bias flag without bias");
+  PNB_REQUIRE(!(flags & PNB_EPI_MASK) || mask_src != nullptr, "gemm: mask flag without mask source");
+  PNB_REQUIRE(row_bias == nullptr || row_group > 0, "gemm: row_bias needs row_group");
+  PNB_REQUIRE((M + BM - 1) / BM < (1ll << 31), "gemm: M too large");
+  return 0;
+}
+
+extern "C" int pnb_gemm_f32(int mode, long long M, int N, long long K, const float* A, int lda, const float* B, int ldb,
+                            float* C, int ldc, const float* bias, const float* row_bias, int row_group,
+                            const float* mask_src, int ld_mask, int flags, void* stream) {
+  int rc = check_gemm_args(mode, M, N, K, bias, row_bias, row_group, mask_src, flags);
+  if (rc) return rc;
+  if (M == 0 || K == 0) return 0;
+  return launch_gemm<float, float>(mode, M, N, K, A, lda, B, ldb, C, ldc, bias, row_bias, row_group, mask_src, ld_mask,
+                                   flags, stream);
+}
+
+// Same GEMMs on bf16-stored operands (fp32 FFMA arithmetic): the CUDA-core twin of the tcgen05 path, used by the
+// tests to check the tensor-core kernels on identical bf16 data (only the accumulation order differs).
+extern "C" int pnb_gemm_bf16_simt(int mode, long long M, int N, long long K, const void* A, int lda, const void* B,
+                                  int ldb, void* C, int ldc, int c_dtype, const float* bias, const float* row_bias,
+                                  int row_group, const void* mask_src, int ld_mask, int flags, void* stream) {
+  int rc = check_gemm_args(mode, M, N, K, bias, row_bias, row_group, mask_src, flags);
+  if (rc) return rc;
+  PNB_REQUIRE(mode != 2 || c_dtype == PNB_F32, "gemm_bf16_simt: wgrad accumulates into fp32");
+  if (M == 0 || K == 0) return 0;
+  if (c_dtype == PNB_BF16)
+    return launch_gemm<__nv_bfloat16, __nv_bfloat16>(mode, M, N, K, A, lda, B, ldb, C, ldc, bias, row_bias, row_group,
+                                                     mask_src, ld_mask, flags, stream);
+  return launch_gemm<__nv_bfloat16, float>(mode, M, N, K, A, lda, B, ldb, C, ldc, bias, row_bias, row_group, mask_src,
+                                           ld_mask, flags, stream);
 }

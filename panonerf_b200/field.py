@@ -231,12 +231,49 @@ class _TCBackend:
         dw.add_(tmp[:, :c].t())
 
 
+class _SimtBf16Backend(_TCBackend):
+    """CUDA-core twin of the tensor-core back-end: identical bf16 buffers, identical weight packs, identical
+    epilogues - only the GEMM engine differs (FFMA instead of tcgen05).  Exists so that the tests can check the
+    tcgen05 forward/backward on the same bf16-rounded data (precision='bf16_simt')."""
+    name = "simt_bf16"
+
+    def linear(self, a, w: _PackedWeight, out, bias=None, relu=False, mask=None, row_bias=None, group=0, accum=False):
+        flags = (EPI_BIAS if bias is not None else 0) | (EPI_RELU if relu else 0) | \
+                (EPI_MASK if mask is not None else 0) | (EPI_ACCUM if accum else 0)
+        m, k = a.shape
+        n = w.shape[0]
+        with torch.cuda.device(a.device):
+            check(_lib.lib().pnb_gemm_bf16_simt(0, m, n, k, _p(a), _ld(a), _p(w.fwd), _ld(w.fwd), _p(out), _ld(out),
+                                                ops.dt_code(out.dtype), _p(bias), _p(row_bias), group, _p(mask),
+                                                _ld(mask) if mask is not None else 0, flags, _stream()),
+                  "gemm_bf16_simt(NT)")
+
+    def dgrad(self, dz, w: _PackedWeight, out, mask=None, accum=False):
+        flags = (EPI_MASK if mask is not None else 0) | (EPI_ACCUM if accum else 0)
+        m, n = dz.shape
+        k = w.shape[1]
+        with torch.cuda.device(dz.device):
+            check(_lib.lib().pnb_gemm_bf16_simt(0, m, k, n, _p(dz), _ld(dz), _p(w.t), _ld(w.t), _p(out), _ld(out),
+                                                ops.dt_code(out.dtype), None, None, 0, _p(mask),
+                                                _ld(mask) if mask is not None else 0, flags, _stream()),
+                  "gemm_bf16_simt(dgrad)")
+
+    def wgrad(self, dz, x, dw):
+        m, n = dz.shape
+        k = x.shape[1]
+        with torch.cuda.device(dz.device):
+            check(_lib.lib().pnb_gemm_bf16_simt(2, n, k, m, _p(dz), _ld(dz), _p(x), _ld(x), _p(dw), _ld(dw), PNB_F32,
+                                                None, None, 0, None, 0, 0, _stream()), "gemm_bf16_simt(TN)")
+
+
 def make_backend(precision: str, params: Dict[str, torch.Tensor]):
     if precision == "fp32":
         return _F32Backend(params)
     if precision == "bf16":
         return _TCBackend(params)
-    raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+    if precision == "bf16_simt":
+        return _SimtBf16Backend(params)
+    raise ValueError(f"precision must be 'bf16', 'bf16_simt' or 'fp32', got {precision!r}")
 
 
 def _mask_scale(src, w_row, out):
@@ -311,22 +348,28 @@ class _Field(torch.autograd.Function):
         n_raw = None
         jac = None
         if cfg["with_normals"]:
-            # Jacobian sweep: a_i = relu'(h_i) * (a_{i+1} W_{i+1}), seeded with the sigma row of the density head
+            # Jacobian sweep: a_i = relu'(h_i) * (a_{i+1} W_{i+1}), seeded with the sigma row of the density head.
+            # `jac_precision='fp32'` runs this sweep (and its adjoint) on the fp32 FFMA path: the normals are the
+            # numerically delicate part of the model ("precision of the second-order path").
+            jb = _F32Backend(P) if cfg.get("jac_precision") == "fp32" and be.name != "f32" else be
+            jdt = jb.dtype
+            hs_j = [h.float() for h in hs] if jb is not be else hs
             a = [None] * depth
-            a[depth - 1] = torch.empty(M, width, device=dev, dtype=dt)
-            _mask_scale(hs[depth - 1], P["density_layer.weight"][0].contiguous(), a[depth - 1])
+            a[depth - 1] = torch.empty(M, width, device=dev, dtype=jdt)
+            _mask_scale(hs_j[depth - 1], P["density_layer.weight"][0].contiguous(), a[depth - 1])
             g_enc = torch.empty(M, xyz, device=dev, dtype=f32)
             skip_layers = [i for i in range(1, depth) if (i - 1) % skip == 0 and i > 1]
             first = True
             for i in range(depth - 1, 0, -1):
-                a[i - 1] = torch.empty(M, width, device=dev, dtype=dt)
+                a[i - 1] = torch.empty(M, width, device=dev, dtype=jdt)
                 if i in skip_layers:
-                    be.dgrad(a[i], be.w(f"layers.{i}.0.weight", 0, width), a[i - 1], mask=hs[i - 1])
-                    be.dgrad(a[i], be.w(f"layers.{i}.0.weight", width, width + xyz), g_enc, accum=not first)
+                    jb.dgrad(a[i], jb.w(f"layers.{i}.0.weight", 0, width), a[i - 1], mask=hs_j[i - 1])
+                    jb.dgrad(a[i], jb.w(f"layers.{i}.0.weight", width, width + xyz), g_enc, accum=not first)
                     first = False
                 else:
-                    be.dgrad(a[i], be.w(f"layers.{i}.0.weight"), a[i - 1], mask=hs[i - 1])
-            be.dgrad(a[0], be.w("layers.0.0.weight"), g_enc, accum=not first)
+                    jb.dgrad(a[i], jb.w(f"layers.{i}.0.weight"), a[i - 1], mask=hs_j[i - 1])
+            jb.dgrad(a[0], jb.w("layers.0.0.weight"), g_enc, accum=not first)
+            del hs_j
             v = ops.ipe_vjp(means2, covs2, cfg["min_deg"], cfg["max_deg"], g_enc)
             del g_enc
             n_raw = torch.empty(M, 3, device=dev, dtype=f32)
@@ -387,7 +430,10 @@ class _Field(torch.autograd.Function):
                                                       _p(d_raw0), _p(d_v), _stream()), "density_grad_bwd")
             d_raw_den[:, 0] += d_raw0
             # u = d L / d g_enc = J_ipe d_v ; forward-mode sweep q_i = relu'(h_i) * (q_{i-1} W_i^T)
-            ucat = torch.empty(M, width + xyz, device=dev, dtype=dt)
+            jb = _F32Backend(P) if cfg.get("jac_precision") == "fp32" and be.name != "f32" else be
+            jdt = jb.dtype
+            hs_j = [h.float() for h in hs] if jb is not be else hs
+            ucat = torch.empty(M, width + xyz, device=dev, dtype=jdt)
             u = ucat[:, width:]
             ops.ipe_jvp_into(means, covs, cfg["min_deg"], cfg["max_deg"], d_v, u)
             q_prev = u
@@ -395,18 +441,19 @@ class _Field(torch.autograd.Function):
                 wname = f"layers.{i}.0.weight"
                 # dW_i += a_i^T q_{i-1}
                 if i in skip_layers:
-                    be.wgrad(a[i], ucat[:, :width], G[wname][:, :width])
-                    be.wgrad(a[i], u, G[wname][:, width:])
+                    jb.wgrad(a[i], ucat[:, :width], G[wname][:, :width])
+                    jb.wgrad(a[i], u, G[wname][:, width:])
                 else:
-                    be.wgrad(a[i], q_prev, G[wname])
+                    jb.wgrad(a[i], q_prev, G[wname])
                 to_cat = (i % skip == 0 and i > 0)
-                q = ucat[:, :width] if to_cat else torch.empty(M, width, device=dev, dtype=dt)
-                be.linear(q_prev, be.w(wname), q, mask=hs[i])
+                q = ucat[:, :width] if to_cat else torch.empty(M, width, device=dev, dtype=jdt)
+                jb.linear(q_prev, jb.w(wname), q, mask=hs_j[i])
                 a[i] = None
                 q_prev = ucat if to_cat else q
             # d wd[0,:] += colsum(q_last)   (a_last = relu'(h_last) * wd[0])
             last = q_prev if q_prev.shape[1] == width else q_prev[:, :width]
             _colsum(last, G["density_layer.weight"][0])
+            del hs_j
             del ucat, q_prev
 
         # ---- heads ------------------------------------------------------------------------------------------
@@ -474,14 +521,15 @@ class _Field(torch.autograd.Function):
 
 
 def radiance_field(means, covs, venc, params: Dict[str, torch.Tensor], *, precision: str, samples_per_ray: int,
-                   min_deg: int, max_deg: int, density_bias: float, skip: int, with_normals: bool):
+                   min_deg: int, max_deg: int, density_bias: float, skip: int, with_normals: bool,
+                   jac_precision: Optional[str] = None):
     """Evaluate the MLP on [R,S,3] Gaussians. Returns raw_rgb [R,S,3], raw_den [R,S,C], n_raw [R,S,3] | None."""
     names = list(params.keys())
     depth = len([n for n in names if n.startswith("layers.") and n.endswith(".weight")])
     w0 = params["layers.0.0.weight"]
     cfg = dict(names=names, precision=precision, depth=depth, skip=skip, width=w0.shape[0], xyz_dim=w0.shape[1],
                samples_per_ray=samples_per_ray, min_deg=min_deg, max_deg=max_deg, density_bias=density_bias,
-               with_normals=with_normals)
+               with_normals=with_normals, jac_precision=jac_precision)
     if w0.shape[1] != 6 * (max_deg - min_deg):
         raise RuntimeError("IPE width does not match the first layer")
     R = means.shape[0]

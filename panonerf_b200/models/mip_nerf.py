@@ -81,6 +81,7 @@ class _NerfBase(torch.nn.Module):
         self.stop_resample_grad = kw["stop_resample_grad"]
         self.rgb_padding = kw["rgb_padding"]
         self.precision = kw.get("precision") or default_precision()
+        self.jac_precision = kw.get("jac_precision") or os.environ.get("PANONERF_JAC_PRECISION")
         if kw["rgb_activation"] != "softplus":
             raise NotImplementedError
         if kw["density_activation"] != "softplus":
@@ -107,7 +108,8 @@ class _NerfBase(torch.nn.Module):
         return field.radiance_field(means, covs, venc, self.mlp.named_field_params(), precision=self.precision,
                                     samples_per_ray=samples_per_ray, min_deg=self.min_deg_point,
                                     max_deg=self.max_deg_point, density_bias=self.density_bias,
-                                    skip=self.mlp.skip_index, with_normals=with_normals)
+                                    skip=self.mlp.skip_index, with_normals=with_normals,
+                                    jac_precision=self.jac_precision)
 
     def _prep_rays(self, rays):
         f = ops._f32c
