@@ -13,6 +13,7 @@
 // minimum: read A once, write C once.  wgrad: both operands are "MN-major" (the reduction axis is the slow axis
 // in memory), which tcgen05 consumes directly through MN-major shared-memory descriptors - no transposes.
 #include <cuda.h>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -395,6 +396,248 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// linear, fast path: bf16 output, epilogue flags known at compile time.
+//   * 8 epilogue warps (two per TMEM lane quadrant, alternating 64-column groups) hide instruction latency;
+//   * the epilogue is straight-line code (no per-element flag branches), bias comes from shared memory;
+//   * each warp stages its 32x64 bf16 sub-tile in 128B-swizzled shared memory and one lane issues a TMA store
+//     (cp.async.bulk.tensor, bulk-group tracked, double-buffered) -> fully coalesced 128-byte global writes.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kFastThreads = 64 + 8 * 32;
+constexpr int kStoreBoxBytes = 32 * 64 * 2;  // 32 rows x 64 bf16
+
+#define PNB_EPI_ROWBIAS 16  // compile-time only: row_bias pointer is present
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// issue two 32-column TMEM loads, then one wait
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]),
+        "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]),
+        "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]),
+        "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+      : "r"(taddr + 32)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int BLOCK_N, int EPI>
+__global__ void __launch_bounds__(kFastThreads, 1)
+linear_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                      const __grid_constant__ CUtensorMap tmC, LinearParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_1024(smem_raw);
+  constexpr int kWTileBytes = BLOCK_N * kBlockK * 2;
+  constexpr uint32_t kTmemCols = 2 * BLOCK_N;
+  constexpr int kGroups = BLOCK_N / 64;  // 64-column groups per tile
+  uint8_t* smem_w = smem;
+  uint8_t* smem_a = smem_w + (size_t)p.num_kb * kWTileBytes;
+  uint8_t* smem_c = smem_a + (size_t)p.stages * kATileBytes;          // 8 warps x 4 KB staging for the TMA stores
+  float* smem_bias = reinterpret_cast<float*>(smem_c + 8 * kStoreBoxBytes);
+  Barriers* bars = reinterpret_cast<Barriers*>(smem_bias + BLOCK_N);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.y * BLOCK_N;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmC);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&bars->full[s], 1);
+      mbar_init(&bars->empty[s], 1);
+    }
+    mbar_init(&bars->w_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&bars->tmem_full[b], 1);
+      mbar_init(&bars->tmem_empty[b], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&bars->tmem_base, kTmemCols);
+  if (EPI & PNB_EPI_BIAS) {
+    for (int i = threadIdx.x; i < BLOCK_N; i += kFastThreads) smem_bias[i] = (n0 + i < p.Nout) ? p.bias[n0 + i] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(&bars->w_full, (uint32_t)(p.num_kb * kWTileBytes));
+      for (int kb = 0; kb < p.num_kb; ++kb)
+        tma_load_2d(smem_w + (size_t)kb * kWTileBytes, &tmW, &bars->w_full, kb * kBlockK, n0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&bars->empty[stage], phase ^ 1);
+          mbar_expect_tx(&bars->full[stage], kATileBytes);
+          tma_load_2d(smem_a + (size_t)stage * kATileBytes, &tmA, &bars->full[stage], kb * kBlockK,
+                      (int)(tile * kBlockM));
+          if (++stage == p.stages) stage = 0, phase ^= 1;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = instr_desc_bf16(kBlockM, BLOCK_N, 0, 0);
+      mbar_wait(&bars->w_full, 0);
+      tc_fence_after();
+      int stage = 0;
+      uint32_t phase = 0;
+      long long it = 0;
+      for (long long tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, ++it) {
+        const uint32_t buf = (uint32_t)(it & 1);
+        mbar_wait(&bars->tmem_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1));
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * BLOCK_N;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&bars->full[stage], phase);
+          tc_fence_after();
+          const int nk16 = (kb == p.num_kb - 1) ? p.tail_k16 : kBlockK / 16;
+          const uint32_t a_addr = smem_u32(smem_a + (size_t)stage * kATileBytes);
+          const uint32_t b_addr = smem_u32(smem_w + (size_t)kb * kWTileBytes);
+          for (int k = 0; k < nk16; ++k) {
+            uint64_t ad = smem_desc_sw128(a_addr + k * 32, 16, 1024);
+            uint64_t bd = smem_desc_sw128(b_addr + k * 32, 16, 1024);
+            umma_f16(d_tmem, ad, bd, idesc, (uint32_t)((kb | k) != 0));
+          }
+          umma_commit(&bars->empty[stage]);
+          if (++stage == p.stages) stage = 0, phase ^= 1;
+        }
+        umma_commit(&bars->tmem_full[buf]);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int ew = warp - 2;       // 0..7
+    const int q = warp & 3;        // TMEM lane quadrant (hardware rule: warp id % 4)
+    const int half = ew >> 2;      // which of the two warps sharing this quadrant
+    uint8_t* stage_c = smem_c + (size_t)ew * kStoreBoxBytes;
+    const __nv_bfloat16* mask_base = p.mask_src;
+    __nv_bfloat16* c_base = reinterpret_cast<__nv_bfloat16*>(p.C);
+    long long it = 0;
+    for (long long tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, ++it) {
+      const uint32_t buf = (uint32_t)(it & 1);
+      mbar_wait(&bars->tmem_full[buf], (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      const long long m = tile * kBlockM + q * 32 + lane;
+      const bool row_ok = m < p.M;
+      const float* rb_row = nullptr;
+      if (EPI & PNB_EPI_ROWBIAS) rb_row = p.row_bias + (row_ok ? (m / p.row_group) : 0) * (long long)p.Nout;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BLOCK_N;
+#pragma unroll 1
+      for (int g = half; g < kGroups; g += 2) {
+        const int nb = n0 + g * 64;  // first global column of this group
+        uint32_t r[64];
+        tmem_ld64(taddr + g * 64, r);
+        float v[64];
+#pragma unroll
+        for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
+        if (EPI & PNB_EPI_BIAS) {
+#pragma unroll
+          for (int i = 0; i < 64; i += 4) {
+            float4 b4 = *reinterpret_cast<const float4*>(smem_bias + g * 64 + i);
+            v[i] += b4.x, v[i + 1] += b4.y, v[i + 2] += b4.z, v[i + 3] += b4.w;
+          }
+        }
+        if (EPI & PNB_EPI_ROWBIAS) {
+#pragma unroll
+          for (int i = 0; i < 64; i += 4) {
+            float4 b4 = *reinterpret_cast<const float4*>(rb_row + nb + i);
+            v[i] += b4.x, v[i + 1] += b4.y, v[i + 2] += b4.z, v[i + 3] += b4.w;
+          }
+        }
+        if (EPI & PNB_EPI_ACCUM) {
+          if (row_ok) {
+            const uint4* prow = reinterpret_cast<const uint4*>(c_base + m * p.ldc + nb);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              uint4 raw = prow[i];
+              const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&raw);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[8 * i + j] += __bfloat162float(h[j]);
+            }
+          }
+        }
+        if (EPI & PNB_EPI_RELU) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        if (EPI & PNB_EPI_MASK) {
+          if (row_ok) {
+            const uint4* mrow = reinterpret_cast<const uint4*>(mask_base + m * p.ld_mask + nb);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              uint4 raw = mrow[i];
+              const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&raw);
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (!(__bfloat162float(h[j]) > 0.f)) v[8 * i + j] = 0.f;
+            }
+          }
+        }
+        // the TMA store that last read this staging buffer must have finished reading it
+        if (lane == 0) bulk_wait_read<0>();
+        __syncwarp();
+        uint8_t* dst = stage_c + lane * 128;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          __nv_bfloat162 h[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[8 * i + 2 * j], v[8 * i + 2 * j + 1]);
+          *reinterpret_cast<uint4*>(dst + ((i ^ (lane & 7)) << 4)) = *reinterpret_cast<uint4*>(h);
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmC, stage_c, nb, (int)(tile * kBlockM + q * 32));
+          bulk_commit();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->tmem_empty[buf]);
+    }
+    if (lane == 0) bulk_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // wgrad: dW[Nw,Kw] += dZ^T X, both operands MN-major.  Each CTA reduces a contiguous slab of samples into TMEM
 // (Nw/128 accumulators of 128 x Kw fp32), then writes its partial to a workspace; a second kernel sums the
 // partials in a fixed order (deterministic) into the accumulating gradient buffer.
@@ -630,13 +873,64 @@ extern "C" int pnb_linear_tc(long long M, int Nout, int K, const void* A, int ld
   p.stages = smem_need(bn, 4) <= (size_t)kSmemLimit ? 4 : 3;
   PNB_REQUIRE(smem_need(bn, p.stages) <= (size_t)kSmemLimit, "linear_tc: weight does not fit shared memory");
   int grid_y = (Nout + bn - 1) / bn;
-  size_t smem_bytes = smem_need(bn, p.stages);
   CUtensorMap tmA, tmW;
   if (!make_map(&tmA, A, (unsigned long long)M, (unsigned long long)K, (unsigned long long)lda, kBlockK, kBlockM))
     return PNB_ERR_ARG;
+  cudaStream_t st = as_stream(stream);
+
+  // ---- fast path: bf16 output, 64-column-aligned tiles, epilogue specialised at compile time -----------------
+  const int epi = (flags & (PNB_EPI_BIAS | PNB_EPI_RELU | PNB_EPI_MASK | PNB_EPI_ACCUM)) | (row_bias ? PNB_EPI_ROWBIAS : 0);
+  const bool aligned_c = (ldc % 8 == 0) && ((uintptr_t)C % 16 == 0) &&
+                         (!(flags & PNB_EPI_MASK) || ((ld_mask % 8 == 0) && ((uintptr_t)mask_src % 16 == 0)));
+  if (c_dtype == PNB_BF16 && aligned_c && Nout % 64 == 0 && (bn == 128 || bn == 256) && !getenv("PNB_NO_FAST_EPILOGUE")) {
+    auto fast_need = [&](int bn_, int stages) {
+      return (size_t)p.num_kb * bn_ * kBlockK * 2 + (size_t)stages * kATileBytes + 8 * (size_t)kStoreBoxBytes +
+             (size_t)bn_ * 4 + sizeof(Barriers) + 1024;
+    };
+    int fbn = bn;
+    while (fbn > 128 && fast_need(fbn, 2) > (size_t)kSmemLimit) fbn /= 2;
+    int fst = 4;
+    while (fst > 2 && fast_need(fbn, fst) > (size_t)kSmemLimit) --fst;
+    if (fast_need(fbn, fst) <= (size_t)kSmemLimit) {
+      LinearParams fp = p;
+      fp.stages = fst;
+      int fgy = (Nout + fbn - 1) / fbn;
+      CUtensorMap tmC;
+      if (!make_map(&tmW, W, (unsigned long long)Nout, (unsigned long long)K, (unsigned long long)ldw, kBlockK, fbn))
+        return PNB_ERR_ARG;
+      if (!make_map(&tmC, C, (unsigned long long)M, (unsigned long long)Nout, (unsigned long long)ldc, 64, 32))
+        return PNB_ERR_ARG;
+      size_t fsm = fast_need(fbn, fst);
+      long long gx = fp.num_m_tiles < kNumSMs / fgy ? fp.num_m_tiles : kNumSMs / fgy;
+      if (gx < 1) gx = 1;
+      dim3 grid((unsigned)gx, (unsigned)fgy, 1);
+#define PNB_FAST_CASE(BN, E)                                                                                    \
+  if (fbn == BN && epi == (E)) {                                                                               \
+    auto kern = linear_tc_fast_kernel<BN, (E)>;                                                                \
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm);         \
+    if (e != cudaSuccess) {                                                                                    \
+      set_error("linear_tc_fast(smem attr)", e);                                                               \
+      return (int)e;                                                                                           \
+    }                                                                                                          \
+    kern<<<grid, kFastThreads, fsm, st>>>(tmA, tmW, tmC, fp);                                                  \
+    return finish("linear_tc_fast");                                                                           \
+  }
+#define PNB_FAST_BOTH(E) PNB_FAST_CASE(256, E) PNB_FAST_CASE(128, E)
+      PNB_FAST_BOTH(PNB_EPI_BIAS | PNB_EPI_RELU)
+      PNB_FAST_BOTH(PNB_EPI_BIAS)
+      PNB_FAST_BOTH(PNB_EPI_RELU | PNB_EPI_ROWBIAS)
+      PNB_FAST_BOTH(PNB_EPI_MASK)
+      PNB_FAST_BOTH(PNB_EPI_MASK | PNB_EPI_ACCUM)
+      PNB_FAST_BOTH(0)
+#undef PNB_FAST_BOTH
+#undef PNB_FAST_CASE
+    }
+  }
+
+  // ---- general path (fp32 outputs, narrow heads, unusual flag combinations) ------------------------------------
+  size_t smem_bytes = smem_need(bn, p.stages);
   if (!make_map(&tmW, W, (unsigned long long)Nout, (unsigned long long)K, (unsigned long long)ldw, kBlockK, bn))
     return PNB_ERR_ARG;
-  cudaStream_t st = as_stream(stream);
   switch (bn) {
     case 16: return launch_linear<16>(tmA, tmW, p, grid_y, smem_bytes, st);
     case 32: return launch_linear<32>(tmA, tmW, p, grid_y, smem_bytes, st);
