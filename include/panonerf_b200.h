@@ -174,10 +174,12 @@ int pnb_gemm_bf16_simt(int mode, long long M, int N, long long K, const void* A,
  * C dtype = c_dtype (bf16 or fp32), bias fp32 [Nout], mask_src bf16 [M,Nout].  16 <= K <= 384 (K % 16 == 0).
  * row_bias (nullable) is an fp32 [M/row_group, Nout] addend shared by each group of `row_group` consecutive rows
  * (the per-ray view-direction term of the view layer, models/pano_mip_nerf.py:109-112).
+ * colsum_out (nullable, fp32 [Nout], bf16 outputs with Nout % 64 == 0 only) is incremented by the column sums of C:
+ * in the backward pass that is the bias gradient of the layer whose dZ this call produces, for free.
  * The same entry point serves forward (W) and dgrad (pre-transposed W^T). */
 int pnb_linear_tc(long long M, int Nout, int K, const void* A, int lda, const void* W, int ldw, void* C, int ldc,
                   int c_dtype, const float* bias, const float* row_bias, int row_group, const void* mask_src,
-                  int ld_mask, int flags, void* stream);
+                  int ld_mask, int flags, float* colsum_out, void* stream);
 /* dW[Nw,Kw] (fp32, accumulated) += dZ[M,Nw]^T (bf16) * X[M,Kw] (bf16) ; reduction over the M samples.
  * Nw in {128,256}; 16 <= Kw <= 256.  workspace: pnb_wgrad_tc_workspace(Nw,Kw) bytes (per-CTA partials, summed in a
  * fixed order => deterministic). */

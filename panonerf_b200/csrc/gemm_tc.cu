@@ -170,6 +170,7 @@ struct LinearParams {
   const __nv_bfloat16* mask_src;
   int ld_mask, flags;
   long long num_m_tiles;
+  float* colsum;  // nullable: += column sums of the bf16 output (fast path only) = bias gradient of the producer
 };
 
 template <int BLOCK_N, typename OutT>
@@ -544,6 +545,7 @@ linear_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     uint8_t* stage_c = smem_c + (size_t)ew * kStoreBoxBytes;
     const __nv_bfloat16* mask_base = p.mask_src;
     __nv_bfloat16* c_base = reinterpret_cast<__nv_bfloat16*>(p.C);
+    float cs00 = 0.f, cs01 = 0.f, cs10 = 0.f, cs11 = 0.f;  // column-sum partials: [group slot][column pair]
     long long it = 0;
     for (long long tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, ++it) {
       const uint32_t buf = (uint32_t)(it & 1);
@@ -622,12 +624,40 @@ linear_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           tma_store_2d(&tmC, stage_c, nb, (int)(tile * kBlockM + q * 32));
           bulk_commit();
         }
+        if (p.colsum != nullptr) {
+          // bias gradient of the layer that produced this tile: column sums of the bf16-rounded values just staged.
+          // Lane l owns columns 2l, 2l+1 of the 64-column group; rows beyond M were computed from zero-filled
+          // operands and are exactly zero unless a bias/accumulate epilogue is active (never combined with colsum).
+          const int rows_valid = (int)((p.M - (tile * kBlockM + q * 32)) < 32 ? (p.M - (tile * kBlockM + q * 32)) : 32);
+          float s0 = 0.f, s1 = 0.f;
+          const int chunk = lane >> 2, within = (lane & 3) * 4;  // 16-byte chunk and byte offset inside it
+          for (int rr = 0; rr < rows_valid; ++rr) {
+            const uint8_t* src = stage_c + rr * 128 + ((chunk ^ (rr & 7)) << 4) + within;
+            __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(src);
+            s0 += __bfloat162float(h.x), s1 += __bfloat162float(h.y);
+          }
+          if (g < 2) {
+            cs00 += s0, cs01 += s1;
+          } else {
+            cs10 += s0, cs11 += s1;
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->tmem_empty[buf]);
     }
     if (lane == 0) bulk_wait_all();
+    if (p.colsum != nullptr) {
+      if (half < kGroups) {
+        atomicAdd(p.colsum + n0 + half * 64 + 2 * lane, cs00);
+        atomicAdd(p.colsum + n0 + half * 64 + 2 * lane + 1, cs01);
+      }
+      if (half + 2 < kGroups) {
+        atomicAdd(p.colsum + n0 + (half + 2) * 64 + 2 * lane, cs10);
+        atomicAdd(p.colsum + n0 + (half + 2) * 64 + 2 * lane + 1, cs11);
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -847,7 +877,7 @@ extern "C" int pnb_tc_available(void) {
 
 extern "C" int pnb_linear_tc(long long M, int Nout, int K, const void* A, int lda, const void* W, int ldw, void* C,
                              int ldc, int c_dtype, const float* bias, const float* row_bias, int row_group,
-                             const void* mask_src, int ld_mask, int flags, void* stream) {
+                             const void* mask_src, int ld_mask, int flags, float* colsum_out, void* stream) {
   PNB_REQUIRE(M >= 0 && Nout >= 1 && Nout <= 512 && K >= 16 && K <= 384 && K % 16 == 0,
               "linear_tc: need 1<=Nout<=512, 16<=K<=384, K%16==0");
   PNB_REQUIRE(lda % 8 == 0 && ldw % 8 == 0 && ((uintptr_t)A % 16 == 0) && ((uintptr_t)W % 16 == 0),
@@ -864,6 +894,7 @@ extern "C" int pnb_linear_tc(long long M, int Nout, int K, const void* A, int ld
   p.bias = bias, p.row_bias = row_bias, p.row_group = row_group;
   p.mask_src = (const __nv_bfloat16*)mask_src, p.ld_mask = ld_mask, p.flags = flags;
   p.num_m_tiles = (M + kBlockM - 1) / kBlockM;
+  p.colsum = nullptr;
   // smallest tile width covering Nout whose resident weight leaves room for >= 3 activation stages
   int bn = Nout <= 16 ? 16 : Nout <= 32 ? 32 : Nout <= 64 ? 64 : Nout <= 128 ? 128 : 256;
   auto smem_need = [&](int bn_, int stages) {
@@ -894,6 +925,7 @@ extern "C" int pnb_linear_tc(long long M, int Nout, int K, const void* A, int ld
     if (fast_need(fbn, fst) <= (size_t)kSmemLimit) {
       LinearParams fp = p;
       fp.stages = fst;
+      fp.colsum = colsum_out;
       int fgy = (Nout + fbn - 1) / fbn;
       CUtensorMap tmC;
       if (!make_map(&tmW, W, (unsigned long long)Nout, (unsigned long long)K, (unsigned long long)ldw, kBlockK, fbn))
@@ -928,6 +960,7 @@ extern "C" int pnb_linear_tc(long long M, int Nout, int K, const void* A, int ld
   }
 
   // ---- general path (fp32 outputs, narrow heads, unusual flag combinations) ------------------------------------
+  PNB_REQUIRE(colsum_out == nullptr, "linear_tc: colsum_out needs the bf16 fast path (Nout % 64 == 0, aligned)");
   size_t smem_bytes = smem_need(bn, p.stages);
   if (!make_map(&tmW, W, (unsigned long long)Nout, (unsigned long long)K, (unsigned long long)ldw, kBlockK, bn))
     return PNB_ERR_ARG;

@@ -114,7 +114,8 @@ composite_bwd_kernel(long long R, int N, const float* __restrict__ rgb, const fl
     for (int i = lane; i < N; i += 32) {
       const float* c = rgb + 3 * (r * N + i);
       float tm = 0.5f * (tr[i] + tr[i + 1]);
-      float G = gc0 * c[0] + gc1 * c[1] + gc2 * c[2] + ga + gd * (tm - draw) + (g_w ? g_w[r * N + i] : 0.f);
+      float G = gc0 * c[0] + gc1 * c[1] + gc2 * c[2] + ga + (g_w ? g_w[r * N + i] : 0.f);
+      if (gd != 0.f) G += gd * (tm - draw);  // `draw` is NaN on an empty ray; the reference would propagate it
       float w = sW[i];
       sQ[i] = G * w;
       sT[i] = G * (sT[i] - w);  // re-use: G_i (T_i - w_i)

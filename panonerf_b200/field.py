@@ -11,6 +11,7 @@ Two GEMM back-ends share the orchestration:
 from __future__ import annotations
 
 import ctypes
+import weakref
 from typing import Dict, List, Optional
 
 import torch
@@ -62,8 +63,8 @@ class _F32Backend:
                                           _p(row_bias), group, _p(mask), _ld(mask) if mask is not None else 0, flags,
                                           _stream()), "gemm_f32(NT)")
 
-    def dgrad(self, dz, w, out, mask=None, accum=False):
-        """out[M,K] = dz[M,N] @ w[N,K]"""
+    def dgrad(self, dz, w, out, mask=None, accum=False, colsum_out=None):
+        """out[M,K] = dz[M,N] @ w[N,K]   (colsum_out += column sums of out: the upstream layer's bias gradient)"""
         flags = (EPI_MASK if mask is not None else 0) | (EPI_ACCUM if accum else 0)
         m, n = dz.shape
         k = w.shape[1]
@@ -71,6 +72,8 @@ class _F32Backend:
             check(_lib.lib().pnb_gemm_f32(1, m, k, n, _p(dz), _ld(dz), _p(w), _ld(w), _p(out), _ld(out), None, None, 0,
                                           _p(mask), _ld(mask) if mask is not None else 0, flags, _stream()),
                   "gemm_f32(NN)")
+        if colsum_out is not None:
+            _colsum(out, colsum_out)
 
     dgrad_small = dgrad
 
@@ -158,13 +161,21 @@ class _TCBackend:
         if key not in self._packs:
             p = self.params[name]
             ck = (p.data_ptr(), p._version, _pack_epoch[0], c0, c1)
-            hit = _pack_cache.get(id(p), {}).get((c0, c1))
+            slot = _pack_cache.get(id(p))
+            if slot is not None and slot["ref"]() is not p:      # id() re-used by a different (newer) tensor
+                slot = None
+            if slot is None:
+                slot = _pack_cache[id(p)] = {"ref": weakref.ref(p), "packs": {}}
+                if len(_pack_cache) > 512:                       # drop entries of dead tensors
+                    for k in [k for k, v in _pack_cache.items() if v["ref"]() is None]:
+                        del _pack_cache[k]
+            hit = slot["packs"].get((c0, c1))
             if hit is not None and hit[0] == ck:
                 self._packs[key] = hit[1]
             else:
                 with torch.no_grad():
                     pk = _PackedWeight(p.detach() if c0 is None else p.detach()[:, c0:c1])
-                _pack_cache.setdefault(id(p), {})[(c0, c1)] = (ck, pk)
+                slot["packs"][(c0, c1)] = (ck, pk)
                 self._packs[key] = pk
         return self._packs[key]
 
@@ -187,19 +198,24 @@ class _TCBackend:
         with torch.cuda.device(a.device), _prof("linear_tc", nbytes, 2 * m * n * k):
             check(_lib.lib().pnb_linear_tc(m, n, k16, _p(a), _ld(a), _p(w.fwd), _ld(w.fwd), _p(out), _ld(out),
                                            ops.dt_code(out.dtype), _p(bias), _p(row_bias), group, _p(mask),
-                                           _ld(mask) if mask is not None else 0, flags, _stream()), "linear_tc")
+                                           _ld(mask) if mask is not None else 0, flags, None, _stream()), "linear_tc")
 
-    def dgrad(self, dz, w: _PackedWeight, out, mask=None, accum=False):
-        """out[M,K] = dz[M,N] @ W[N,K]  ==  linear with the pre-transposed pack W^T[K,N]"""
+    def dgrad(self, dz, w: _PackedWeight, out, mask=None, accum=False, colsum_out=None):
+        """out[M,K] = dz[M,N] @ W[N,K]  ==  linear with the pre-transposed pack W^T[K,N].  colsum_out (fp32 [K]) is
+        incremented by the column sums of `out` inside the epilogue (bias gradient of the upstream layer)."""
         flags = (EPI_MASK if mask is not None else 0) | (EPI_ACCUM if accum else 0)
         m, n = dz.shape
         k = w.shape[1]
         n16 = (n + 15) // 16 * 16
+        fused = colsum_out is not None and out.dtype == torch.bfloat16 and k % 64 == 0
         nbytes = m * n * 2 + m * k * out.element_size() * (2 if accum else 1) + (m * k * 2 if mask is not None else 0)
         with torch.cuda.device(dz.device), _prof("linear_tc", nbytes, 2 * m * n * k):
             check(_lib.lib().pnb_linear_tc(m, k, n16, _p(dz), _ld(dz), _p(w.t), _ld(w.t), _p(out), _ld(out),
                                            ops.dt_code(out.dtype), None, None, 0, _p(mask),
-                                           _ld(mask) if mask is not None else 0, flags, _stream()), "linear_tc(dgrad)")
+                                           _ld(mask) if mask is not None else 0, flags,
+                                           _p(colsum_out) if fused else None, _stream()), "linear_tc(dgrad)")
+        if colsum_out is not None and not fused:
+            _colsum(out, colsum_out)
 
     def _pad64(self, x32: torch.Tensor) -> torch.Tensor:
         """fp32 [M,C] head gradient -> bf16 [M,64] zero-padded (TMA rows must be 16-byte aligned)."""
@@ -209,9 +225,10 @@ class _TCBackend:
             check(_lib.lib().pnb_convert(m, c, _p(x32), _ld(x32), PNB_F32, _p(buf), 64, PNB_BF16, _stream()), "convert")
         return buf
 
-    def dgrad_small(self, dz32, w: _PackedWeight, out, mask=None, accum=False):
+    def dgrad_small(self, dz32, w: _PackedWeight, out, mask=None, accum=False, colsum_out=None):
         pad = self._pad64(dz32)
-        self.dgrad(pad[:, :16], w, out, mask=mask, accum=accum)   # K=16 slice of the padded buffer (ld stays 64)
+        # K=16 slice of the padded buffer (ld stays 64)
+        self.dgrad(pad[:, :16], w, out, mask=mask, accum=accum, colsum_out=colsum_out)
         return pad
 
     def wgrad(self, dz, x, dw):
@@ -248,7 +265,7 @@ class _SimtBf16Backend(_TCBackend):
                                                 _ld(mask) if mask is not None else 0, flags, _stream()),
                   "gemm_bf16_simt(NT)")
 
-    def dgrad(self, dz, w: _PackedWeight, out, mask=None, accum=False):
+    def dgrad(self, dz, w: _PackedWeight, out, mask=None, accum=False, colsum_out=None):
         flags = (EPI_MASK if mask is not None else 0) | (EPI_ACCUM if accum else 0)
         m, n = dz.shape
         k = w.shape[1]
@@ -257,6 +274,8 @@ class _SimtBf16Backend(_TCBackend):
                                                 ops.dt_code(out.dtype), None, None, 0, _p(mask),
                                                 _ld(mask) if mask is not None else 0, flags, _stream()),
                   "gemm_bf16_simt(dgrad)")
+        if colsum_out is not None:
+            _colsum(out, colsum_out)
 
     def wgrad(self, dz, x, dw):
         m, n = dz.shape
@@ -473,16 +492,16 @@ class _Field(torch.autograd.Function):
         _colsum(dvb, G["view_layers.0.0.bias"])
         f32be.wgrad(dvb, venc, G["view_layers.0.0.weight"][:, width:])
         d_bott = torch.empty(M, width, device=dev, dtype=dt)
-        be.dgrad(dzv, be.w("view_layers.0.0.weight", 0, width), d_bott)
+        be.dgrad(dzv, be.w("view_layers.0.0.weight", 0, width), d_bott, colsum_out=G["extra_layer.bias"])
         del dzv
         # extra + density heads -> d trunk_out (masked by the last ReLU)
-        _colsum(d_bott, G["extra_layer.bias"])
         be.wgrad(d_bott, trunk_out if trunk_out.shape[1] == width else trunk_out, G["extra_layer.weight"])
         _colsum(d_raw_den, G["density_layer.bias"])
         dz = torch.empty(M, width, device=dev, dtype=dt)
         h_last = hs[depth - 1]
         be.dgrad(d_bott, be.w("extra_layer.weight"), dz)
-        pad = be.dgrad_small(d_raw_den, be.w("density_layer.weight"), dz, mask=h_last, accum=True)
+        pad = be.dgrad_small(d_raw_den, be.w("density_layer.weight"), dz, mask=h_last, accum=True,
+                             colsum_out=G[f"layers.{depth - 1}.0.bias"])
         if isinstance(be, _TCBackend):
             be.wgrad_small(d_raw_den, h_last, G["density_layer.weight"], pad=pad)
         else:
@@ -493,8 +512,8 @@ class _Field(torch.autograd.Function):
         need_enc = ctx.need_means
         d_enc = torch.zeros(M, xyz, device=dev, dtype=f32) if need_enc else None
         for i in range(depth - 1, -1, -1):
-            wname, bname = f"layers.{i}.0.weight", f"layers.{i}.0.bias"
-            _colsum(dz, G[bname])
+            wname = f"layers.{i}.0.weight"
+            prev_bias = G[f"layers.{i - 1}.0.bias"] if i > 0 else None   # filled by this layer's dgrad epilogue
             if i == 0:
                 be.wgrad(dz, enc, G[wname])
                 if need_enc:
@@ -507,11 +526,11 @@ class _Field(torch.autograd.Function):
                 if need_enc:
                     be.dgrad(dz, be.w(wname, width, width + xyz), d_enc, accum=True)
                 nxt = torch.empty(M, width, device=dev, dtype=dt)
-                be.dgrad(dz, be.w(wname, 0, width), nxt, mask=x_prev)
+                be.dgrad(dz, be.w(wname, 0, width), nxt, mask=x_prev, colsum_out=prev_bias)
             else:
                 be.wgrad(dz, x_prev, G[wname])
                 nxt = torch.empty(M, width, device=dev, dtype=dt)
-                be.dgrad(dz, be.w(wname), nxt, mask=x_prev)
+                be.dgrad(dz, be.w(wname), nxt, mask=x_prev, colsum_out=prev_bias)
             dz = nxt
         d_means = None
         if need_enc:

@@ -53,7 +53,7 @@ def _tc():
         pytest.skip("not an sm_100 device")
 
 
-def _linear_tc(a, w_fwd, out, n, k, bias=None, relu=False, mask=None, row_bias=None, group=0, accum=False):
+def _linear_tc(a, w_fwd, out, n, k, bias=None, relu=False, mask=None, row_bias=None, group=0, accum=False, colsum=None):
     from panonerf_b200 import _lib, ops
     from panonerf_b200._lib import EPI_ACCUM, EPI_BIAS, EPI_MASK, EPI_RELU
     flags = (EPI_BIAS if bias is not None else 0) | (EPI_RELU if relu else 0) | (EPI_MASK if mask is not None else 0) | \
@@ -61,7 +61,7 @@ def _linear_tc(a, w_fwd, out, n, k, bias=None, relu=False, mask=None, row_bias=N
     p = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
     _lib.check(_lib.lib().pnb_linear_tc(a.shape[0], n, k, p(a), a.stride(0), p(w_fwd), w_fwd.stride(0), p(out),
                                         out.stride(0), ops.dt_code(out.dtype), p(bias), p(row_bias), group, p(mask),
-                                        mask.stride(0) if mask is not None else 0, flags,
+                                        mask.stride(0) if mask is not None else 0, flags, p(colsum),
                                         ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "linear_tc")
 
 
@@ -108,6 +108,15 @@ def test_linear_tc_epilogues_and_strides():
     _linear_tc(a, w, out, 128, 256, relu=True, row_bias=rb, group=S)
     ref = torch.relu(a.double() @ w.double().t() + rb.double().repeat_interleave(S, 0))
     assert_close(out.float(), ref.float(), 5e-3, "row_bias", floor=float(ref.abs().mean()))
+    # fused column sums (bias gradient) on a ragged M, bf16 mask+accum epilogue
+    mr = m - 37
+    prevb = torch.randn(mr, 128, generator=gen).to(DEV).to(torch.bfloat16)
+    outb = prevb.clone()
+    cs = torch.ones(128, device=DEV)
+    _linear_tc(a[:mr], w, outb, 128, 256, mask=mask[:mr], accum=True, colsum=cs)
+    ref = (a[:mr].double() @ w.double().t() + prevb.double()) * (mask[:mr].double() > 0)
+    assert_close(outb.float(), ref.float(), 5e-3, "bf16 mask+accum", floor=float(ref.abs().mean()))
+    assert_close(cs, (outb.double().sum(0) + 1.0).float(), 1e-4, "fused colsum", floor=float(outb.double().sum(0).abs().mean()))
     prev = torch.randn(m, 128, generator=gen).to(DEV)
     out32 = prev.clone()
     _linear_tc(a, w, out32, 128, 256, mask=mask, accum=True)
