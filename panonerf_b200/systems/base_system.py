@@ -51,10 +51,8 @@ class FlatAdam:
 
     def all_reduce_grads(self):
         """Sum over ranks (mean taken inside the Adam kernel via grad_scale = 1/world)."""
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)
-            return 1.0 / dist.get_world_size()
-        return 1.0
+        from ..parallel import all_reduce_flat_
+        return all_reduce_flat_(self.flat_g)
 
     def step(self):
         scale = self.all_reduce_grads()

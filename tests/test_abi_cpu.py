@@ -1,0 +1,106 @@
+"""CPU (no GPU needed): the C-ABI library builds for sm_100a, loads, and exports every symbol include/*.h declares;
+the host-side mirror keeps the reference's interface; CPU tensors are refused (no fallback)."""
+import ctypes
+import inspect
+import os
+import subprocess
+
+import pytest
+import torch
+
+from util import ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    from panonerf_b200 import _lib
+    names = _lib.declared_symbols()
+    assert len(names) >= 40
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(handle, n), f"{n} declared in include/panonerf_b200.h but not exported"
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
+    assert set(names) <= exported
+    assert _lib.lib().pnb_abi_version() == 1
+
+
+def test_library_contains_blackwell_tensor_core_code():
+    from panonerf_b200 import _lib
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCHMMA", "UTMALDG", "UTMASTG", "LDTM"):
+        assert mnemonic in sass, f"{mnemonic} missing: tcgen05 / TMA path not compiled in"
+
+
+def test_argument_validation_without_gpu():
+    from panonerf_b200 import _lib
+    lib = _lib.lib()
+    rc = lib.pnb_resample(4, 300, None, None, 0.01, 1, None, 0, None, None, None)        # N > 256
+    assert rc == 10001 and b"N <= 256" in lib.pnb_last_error()
+    rc = lib.pnb_linear_tc(128, 256, 100, None, 256, None, 256, None, 256, 1, None, None, 0, None, 0, 0, None, None)
+    assert rc == 10001                                                                  # K % 16 != 0
+
+
+def test_cpu_tensors_are_refused():
+    from panonerf_b200 import ops
+    from panonerf_b200.models import mip
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ops.pos_enc(torch.zeros(2, 3), 4)
+    with pytest.raises(RuntimeError):
+        mip.volumetric_rendering(torch.zeros(2, 4, 3), torch.zeros(2, 4, 1), torch.zeros(2, 5), torch.zeros(2, 3), False)
+
+
+def test_missing_library_fails_loudly(tmp_path, monkeypatch):
+    from panonerf_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.LibraryMissing):
+        _lib.lib()
+
+
+def test_module_interface_mirrors_reference():
+    from panonerf_b200.models.mip_nerf import MipNeRF
+    from panonerf_b200.models.pano_mip_nerf import PanoMipNeRF
+    from panonerf_b200.models import mip
+    from oracle.panonerf_oracle import mlp_shapes
+    m = MipNeRF(num_samples=64, rgb_activation="softplus", mlp_name="mipnerf", num_env_samples=10)   # extra kwargs swallowed
+    p = PanoMipNeRF(num_samples=64, rgb_activation="softplus", mlp_num_density_channels=5)
+    assert sum(x.numel() for x in m.mlp.parameters()) == 612740
+    assert sum(x.numel() for x in p.mlp.parameters()) == 613768
+    want = mlp_shapes(c_density=5)
+    got = {k: tuple(v.shape) for k, v in p.mlp.state_dict().items()}
+    assert list(got) == list(want) and got == dict(want)
+    assert list(inspect.signature(m.forward).parameters) == ["rays", "randomized", "white_bkgd", "use_ort_loss"]
+    assert list(inspect.signature(p.forward).parameters) == ["rays", "env_rays", "randomized", "white_bkgd",
+                                                             "enable_surf", "use_ort_loss"]
+    for fn, args in (("sample_along_rays", ["origins", "directions", "radii", "num_samples", "near", "far", "randomized",
+                                            "disparity", "ray_shape"]),
+                     ("resample_along_rays", ["origins", "directions", "radii", "t_samples", "weights", "randomized",
+                                              "ray_shape", "stop_grad", "resample_padding"]),
+                     ("cast_rays", ["t_samples", "origins", "directions", "radii", "ray_shape"]),
+                     ("volumetric_rendering", ["rgb", "density", "t_samples", "dirs", "white_bkgd"]),
+                     ("integrated_pos_enc", ["means_covs", "min_deg", "max_deg"]),
+                     ("pos_enc", ["x", "min_deg", "max_deg"])):
+        assert list(inspect.signature(getattr(mip, fn)).parameters)[:len(args)] == args, fn
+    with pytest.raises(NotImplementedError):
+        MipNeRF(rgb_activation="sigmoid")                                  # mip_nerf.py:155-158
+    with pytest.raises(NotImplementedError):
+        PanoMipNeRF(rgb_activation="softplus", mlp_net_activation="gelu")
+
+
+def test_lr_schedule_matches_reference_formula():
+    from panonerf_b200.systems.base_system import mip_lr_decay
+    from oracle.panonerf_oracle import mip_lr
+    for step in (0, 1, 60, 120, 121, 22000, 44000, 50000):
+        assert abs(mip_lr_decay(step, 2e-4, 2e-5, 44000, 120, 0.01) - mip_lr(step)) < 1e-15
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    """`bench.py --impl reference` is the CPU arm: it must run without a GPU and print one JSON line."""
+    import json
+    out = subprocess.run(["python", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cpu-rays", "16"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "train_rays_per_s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["e2e"]["h2d_bytes_per_step"] == 0
