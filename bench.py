@@ -235,6 +235,83 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_render(args):
+    """configs[2]: full-panorama inference render (1024x512 equirect = 524 288 rays), PanoMipNeRF with normals +
+    env irradiance + surface rendering (what the reference's render_image does), rows sharded over the ranks, no
+    inter-GPU communication.  `e2e` additionally copies the rendered HDR images back to pinned host memory."""
+    import torch.distributed as dist
+    from panonerf_b200 import ops
+    from panonerf_b200.datasets.pano_datasets import generate_rays
+    from panonerf_b200.parallel import shard_rows
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    system = make_system(dev)
+    H, W = args.render_hw
+    row0, nrows = shard_rows(H, rank, world)
+    chunk = args.render_chunk
+    host_out = torch.empty(nrows * W, 3 * 4 + 2, pin_memory=True)
+
+    def render(copy_back):
+        rays = generate_rays(H, W, camera(), 0.0, 10.0, dev, row0=row0, nrows=nrows)
+        rays = type(rays)(*[x.view(1, nrows, W, -1) for x in rays])
+        outs = system.render_image((rays, torch.empty(1, nrows, W, 3, device=dev)), chunk_size=chunk)
+        if copy_back:
+            c_rgb, f_rgb, c_dep, f_dep, nor, alb, _, sf, sd = outs
+            flat = torch.cat([x.permute(0, 2, 3, 1).reshape(nrows * W, -1) for x in (f_rgb, nor, alb, sf, c_dep, f_dep)], 1)
+            host_out.copy_(flat, non_blocking=True)
+            torch.cuda.synchronize()
+        return outs
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(copy_back, steps):
+        barrier()
+        sampler = ClockSampler(local)
+        sampler.start()
+        l0 = ops.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            render(copy_back)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), ops.launch_count() - l0, sampler.result()
+
+    for _ in range(max(args.warmup, 1)):
+        render(False)
+    ms, launches, clocks = timed(False, args.steps)
+    ms_e2e, _, _ = timed(True, args.steps)
+    rays_total = H * W * args.steps
+    flop_per_ray = (2 * N_SAMPLES + 100) * MLP_FLOP_PER_SAMPLE + N_SAMPLES * JAC_FLOP_PER_SAMPLE
+    line = {"metric": "render_rays_per_s", "value": rays_total / (ms / 1e3), "unit": "rays/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"full-panorama PanoMipNeRF render {W}x{H}, 64+64 samples, normals + 10x10 env "
+                                   f"irradiance + surface rendering, rows sharded over ranks, no collective",
+                       "chunk_rays": chunk, "parallelism": f"ray-shard{world}",
+                       "l2": "per-chunk activations are several GB (>> 126 MB L2)"},
+            "clocks": clocks,
+            "e2e": {"value": rays_total / (ms_e2e / 1e3), "unit": "rays/s", "h2d_bytes_per_step": 48,
+                    "d2h_bytes_per_step": int(host_out.numel() * 4), "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "step_tflops": H * W * flop_per_ray / (ms / args.steps / 1e3) / 1e12}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def step_flops():
     """Algorithmic MLP FLOPs of one 8192-ray Pano training step: 3x forward for every MLP
     evaluation (fwd + dgrad + wgrad) plus the normals Jacobian pass and its adjoint (3x one trunk pass)."""
@@ -279,7 +356,8 @@ def cpu_train_step(n_rays, threads):
     env = O.fibonacci_env_rays(10, float(rays.radii[0, 0]))
     env = O.Rays(*[x.float() for x in env])
     sd = {k: v.clone().requires_grad_() for k, v in O.synth_state_dict(seed=4, width=256, c_density=5).items()}
-    cfg = dict(num_samples=N_SAMPLES)
+    # normals exactly as the reference computes them: vmap(jacrev(compute_graph)) over every fine sample
+    cfg = dict(num_samples=N_SAMPLES, normals_impl="jacrev")
     params = list(sd.values())
     opt = torch.optim.Adam(params, lr=2e-4)
 
@@ -302,8 +380,8 @@ def cpu_baseline(n_rays):
     step()
     dt = time.perf_counter() - t0
     return {"value": n_rays / dt, "unit": "rays/s", "cores": threads, "kind": "port",
-            "sample": f"one fwd+bwd+Adam step of the same panonerf workload on {n_rays} rays (of 8192), fp32, "
-                      f"torch CPU ops of the oracle port, {dt:.1f} s"}
+            "sample": f"one fwd+bwd+Adam step of the same panonerf workload on {n_rays} rays (of 8192), fp32, oracle port "
+                      f"of the reference incl. its vmap(jacrev) normals, torch CPU ops, {dt:.1f} s"}
 
 
 def run_reference(args):
@@ -340,11 +418,16 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-rays", type=int, default=512)
+    ap.add_argument("--cpu-rays", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="train", choices=["train", "render"])
+    ap.add_argument("--render-hw", type=int, nargs=2, default=[512, 1024])
+    ap.add_argument("--render-chunk", type=int, default=32768)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "render":
+        run_render(args)
     else:
         run_ours(args)
 

@@ -288,8 +288,25 @@ DEFAULT_CFG = dict(num_samples=64, num_levels=2, resample_padding=0.01, min_deg_
 
 
 def _density_normals(sd, mean, cov, viewdirs, cfg, create_graph):
-    """n = -d(density)/d(mean), per sample; equals vmap(jacrev(compute_graph))[1] of pano_mip_nerf.py:299-302
-    (max abs diff 6e-7)."""
+    """n = -d(density)/d(mean), per sample.
+
+    cfg["normals_impl"] == "autograd" (default): one reverse pass, autograd.grad(density.sum(), mean) - equal to the
+    reference's result (max abs diff 6e-7) at a fraction of its cost.
+    cfg["normals_impl"] == "jacrev": literally what the reference executes, vmap(jacrev(compute_graph, argnums=0))
+    over every sample with all of compute_graph's outputs differentiated and only the density row kept
+    (models/pano_mip_nerf.py:299-302, models/mip_nerf.py:261-264).  bench.py times THIS variant as the CPU arm."""
+    if cfg.get("normals_impl", "autograd") == "jacrev":
+        from torch.func import jacrev, vmap
+
+        def compute_graph(m1, v1, d1):
+            f = radiance_field(sd, m1.view(1, 1, -1), v1.view(1, 1, -1), d1.view(1, -1), cfg)
+            keys = ("rgb", "density", "albedo", "roughness") if "albedo" in f else ("rgb", "density")
+            return tuple(f[k] for k in keys)
+
+        n = mean.shape[1]
+        vd = viewdirs.view(-1, 1, 3).repeat(1, n, 1).view(-1, 3)
+        jac = vmap(jacrev(compute_graph, argnums=0))(mean.reshape(-1, 3), cov.reshape(-1, 3), vd)[1]
+        return -jac.view(mean.shape[0], n, 3)
     m = mean.detach().requires_grad_(True) if not mean.requires_grad else mean
     with torch.enable_grad():
         vd = viewdirs
