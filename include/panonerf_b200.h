@@ -186,6 +186,24 @@ int pnb_linear_tc(long long M, int Nout, int K, const void* A, int lda, const vo
 long long pnb_wgrad_tc_workspace(int Nw, int Kw);
 int pnb_wgrad_tc(long long M, int Nw, int Kw, const void* dZ, int ldz, const void* X, int ldx, float* dW, int ldw,
                  float* workspace, void* stream);
+/* ---- fused MLP (the whole network of models/pano_mip_nerf.py:78-114 per 128-sample tile in one kernel) ------
+ * Weights are consumed from a packed blob of bf16 tiles (pre-swizzled shared-memory images, in MMA order) that
+ * pnb_mlp_fused_pack builds from the 24 fp32 parameters; `params_host` is a HOST array of 24 DEVICE pointers in
+ * state-dict order (layers.i.0.weight, layers.i.0.bias for i=0..7, density_layer.*, extra_layer.*,
+ * view_layers.0.0.*, color_layer.*).  Topology is the one of configs/*.yaml: depth 8, width 256, skip 4,
+ * view width 128, 96 IPE features, C <= 16 density-head channels. */
+long long pnb_mlp_fused_wblob_bytes(void);
+long long pnb_mlp_fused_bblob_floats(void);
+int pnb_mlp_fused_act_planes(void);
+int pnb_mlp_fused_pack(const void* const* params_host, int C, void* wblob, float* bblob, void* stream);
+/* enc: bf16 [M,96] IPE features (row stride ld_enc); row_bias: fp32 [ceil(M/S),128] per-ray view-direction term
+ * (incl. the view-layer bias); outputs raw_den fp32 [M,C], raw_rgb fp32 [M,3].
+ * acts (nullable): bf16 [18][M][256] planes written with TMA stores for the backward pass:
+ *   0..7 trunk activations h_i, 8 bottleneck, 9 view-layer activation (cols 0..127), 10..17 Jacobian rows a_0..a_7.
+ * g_enc (nullable): fp32 [M,96]; when given, the density-Jacobian sweep (pano_mip_nerf.py:295-302 without
+ * vmap/jacrev) runs in the same kernel and g_enc receives d raw_sigma / d enc. */
+int pnb_mlp_fused_fwd(long long M, int S, int C, const void* enc, int ld_enc, const void* wblob, const float* bblob,
+                      const float* row_bias, float* raw_den, float* raw_rgb, void* acts, float* g_enc, void* stream);
 /* out[g, n] = sum of the `group` consecutive rows of x belonging to group g (fp32 out [M/group, N]) */
 int pnb_group_sum(long long M, int N, int group, const void* x, int ldx, int dtype, float* out, void* stream);
 /* 1 when the tcgen05 path was compiled in and the device is sm_100 */

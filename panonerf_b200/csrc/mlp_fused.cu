@@ -1,0 +1,696 @@
+// K3-fused: the radiance/density MLP of models/pano_mip_nerf.py:78-114 (8x256 trunk with the skip connection,
+// density / extra / view / colour heads) evaluated for a 128-sample tile in ONE persistent kernel, optionally
+// followed - still on chip - by the density-Jacobian sweep that replaces vmap(jacrev) (pano_mip_nerf.py:295-302).
+//
+// Why: layer-by-layer GEMMs (gemm_tc.cu) stream every [M,256] activation through HBM and are bound by it at
+// ~0.3 of the tensor roofline.  Here activations never leave the SM:
+//
+//   warp 0      producer : streams the pre-swizzled bf16 weight tiles (cp.async.bulk, L2 -> SMEM ring of 32 KB slots)
+//                          and the two IPE k-blocks of the tile (TMA tensor load) in exactly the order the MMA warp
+//                          consumes them;
+//   warp 1      MMA      : one thread issues tcgen05.mma (M=128, N<=256, K=16, bf16 -> fp32 TMEM).  A comes from the
+//                          activation buffer in SMEM (128B-swizzled K-major, 4 k-blocks of 64 columns), B from the
+//                          ring.  Two 256-column TMEM accumulators (X, Y) alternate between consecutive layers;
+//   warps 2..9  epilogue : tcgen05.ld -> bias / ReLU / ReLU-mask -> bf16 -> written IN PLACE into the activation
+//                          buffer as the next layer's A operand, 32 columns ("unit") at a time.  Each unit has its own
+//                          mbarrier, so the next layer's MMAs start as soon as the first 32 columns exist and the
+//                          tensor pipe idles only for that first-unit latency per layer.
+//
+// ReLU sign bits of all 8 trunk layers stay in shared memory (4 KB per layer) so the Jacobian sweep
+// a_{i-1} = relu'(h_{i-1}) * (a_i W_i) can run right after the heads with the transposed weight tiles; the two
+// contributions to d sigma / d enc (through layer 0 and through the skip connection) are accumulated in fp32.
+// With `acts` given, every activation (and Jacobian row) is also written out with TMA stores straight from the
+// activation buffer - that is what the training backward consumes.
+#include "tc_common.cuh"
+
+namespace pnb {
+namespace fused {
+using namespace pnb::tc;
+
+constexpr int kTileM = 128;
+constexpr int kWidth = 256, kEncDim = 96, kCondW = 128;
+constexpr int kSlotBytes = 32768;  // ring slot: a weight tile of up to 256 rows x 64 bf16, or the two IPE k-blocks
+constexpr int kKbBytes = 16384;    // one k-block: 128 rows x 64 bf16, 128B-swizzled
+constexpr int kAbufBytes = 4 * kKbBytes;
+constexpr int kMaskBytes = 8 * 8 * kTileM * 4;  // [layer][unit][row] u32
+constexpr int kFThreads = 320;
+constexpr int kAccX = 0, kAccY = 256;
+constexpr int kMaxSteps = 88, kMaxEpi = 20, kFMaxStages = 6;
+constexpr int kNumParams = 12;  // weights (and biases) in state-dict order: layers 0..7, density, extra, view, colour
+
+// bias blob (fp32) layout
+constexpr int kBiasHE = 2048, kBiasHD = 2304, kBiasC = 2320, kWSigma = 2336, kBiasFloats = 2592;
+
+enum : uint8_t { F_AENC = 1, F_LOADENC = 2, F_RELENC = 4, F_FIRST = 8, F_WAIT = 16 };
+
+struct Step {          // one ring slot = one weight tile = up to four K=16 MMAs (all fields are whole words so the
+                       // MMA warp reads them through the uniform datapath)
+  uint32_t blob_off;   // byte offset of the tile in the weight blob
+  uint32_t bytes;      // tile bytes (rows * 128)
+  uint32_t idesc;      // tcgen05 instruction descriptor (M=128, N of this op, bf16 -> fp32)
+  uint32_t acc_col;    // TMEM column of the accumulator
+  uint32_t a_off16;    // A operand: byte offset >> 4 from the activation buffer (or from the IPE slot with F_AENC)
+  uint32_t flags;      // F_* | nk16 << 8 | commit << 12 (1 -> acc_full[0], 2 -> acc_full[1]) | first unit << 16
+};
+struct PackTile {      // where a tile's elements come from: tile(r,c) = W[r0+r, c0+c] (or W[r0+c, c0+r] transposed)
+  uint32_t blob_off;
+  int16_t param, transposed, r0, c0, vr, vc, rows, pad;
+};
+enum : uint8_t { E_RELU = 0, E_HEADS, E_VIEW, E_COLOR, E_JAC, E_JAC5, E_G0 };
+struct Epi {
+  uint8_t type, bar;
+  uint16_t acc_col;
+  uint16_t bias_off;
+  int8_t mask_idx, save_idx;
+};
+struct Tables {
+  Step steps[kMaxSteps];
+  Epi epis[kMaxEpi];
+  int n_steps, n_epi;
+};
+struct PackArgs {
+  const float* w[kNumParams];
+  const float* b[kNumParams];
+  int ld[kNumParams];
+  int C, n_tiles;
+  PackTile tiles[kMaxSteps];
+};
+
+struct FusedParams {
+  long long M, num_tiles;
+  int S, C, nstages, save;
+  const uint8_t* wblob;
+  const float* bblob;
+  const float* row_bias;
+  float* raw_den;
+  float* raw_rgb;
+  float* g_enc;
+};
+
+struct FBarriers {
+  uint64_t full[kFMaxStages];
+  uint64_t empty[kFMaxStages];
+  uint64_t a_ready[8];
+  uint64_t acc_full[2];
+  uint32_t tmem_base;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// schedule (host): the order of weight tiles == the order of MMA steps == the order of the producer's loads
+// ---------------------------------------------------------------------------------------------------------------
+struct Schedule {
+  Tables tab[2];  // [0] forward only, [1] forward + Jacobian sweep
+  PackTile pack[kMaxSteps];
+  int n_pack;
+  uint32_t blob_bytes;
+};
+
+static void add_step(Schedule& s, int& n, uint32_t& off, int param, int transposed, int r0, int c0, int vr, int vc,
+                     int rows, int n_mma, int acc_col, int a_kb, int nk16, int flags, int commit) {
+  Step st{};
+  st.blob_off = off;
+  st.bytes = (uint32_t)rows * 128u;
+  st.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_mma >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+  st.acc_col = (uint32_t)acc_col;
+  st.a_off16 = (uint32_t)(a_kb * kKbBytes) >> 4;
+  st.flags = (uint32_t)flags | ((uint32_t)nk16 << 8) | ((uint32_t)commit << 12) | ((uint32_t)(2 * a_kb) << 16);
+  s.tab[1].steps[n] = st;
+  PackTile pt{};
+  pt.blob_off = off;
+  pt.param = (int16_t)param, pt.transposed = (int16_t)transposed;
+  pt.r0 = (int16_t)r0, pt.c0 = (int16_t)c0, pt.vr = (int16_t)vr, pt.vc = (int16_t)vc, pt.rows = (int16_t)rows;
+  s.pack[n] = pt;
+  off += (uint32_t)rows * 128u;
+  ++n;
+}
+
+static const Schedule& schedule() {
+  static Schedule s;
+  static bool built = false;
+  if (built) return s;
+  int n = 0, ne = 0;
+  uint32_t off = 0;
+  auto epi = [&](int type, int bar, int acc_col, int bias_off, int mask_idx, int save_idx) {
+    Epi e{};
+    e.type = (uint8_t)type, e.bar = (uint8_t)bar, e.acc_col = (uint16_t)acc_col, e.bias_off = (uint16_t)bias_off;
+    e.mask_idx = (int8_t)mask_idx, e.save_idx = (int8_t)save_idx;
+    s.tab[1].epis[ne++] = e;
+  };
+  const int P_DEN = 8, P_EXTRA = 9, P_VIEW = 10, P_COL = 11;
+  // ---- trunk -----------------------------------------------------------------------------------------------
+  for (int i = 0; i < 8; ++i) {
+    const int acc = (i & 1) ? kAccY : kAccX, bar = (i & 1) ? 2 : 1;
+    if (i == 0) {
+      add_step(s, n, off, 0, 0, 0, 0, 256, 64, 256, 256, acc, 0, 4, F_AENC | F_LOADENC | F_FIRST, 0);
+      add_step(s, n, off, 0, 0, 0, 64, 256, 32, 256, 256, acc, 1, 2, F_AENC | F_RELENC, bar);
+    } else {
+      for (int kb = 0; kb < 4; ++kb)
+        add_step(s, n, off, i, 0, 0, kb * 64, 256, 64, 256, 256, acc, kb, 4, F_WAIT | (kb == 0 ? F_FIRST : 0),
+                 (kb == 3 && i != 5) ? bar : 0);
+      if (i == 5) {  // skip connection: input = [h4 | enc]  (models/pano_mip_nerf.py:99-100)
+        add_step(s, n, off, 5, 0, 0, 256, 256, 64, 256, 256, acc, 0, 4, F_AENC | F_LOADENC, 0);
+        add_step(s, n, off, 5, 0, 0, 320, 256, 32, 256, 256, acc, 1, 2, F_AENC | F_RELENC, bar);
+      }
+    }
+    epi(E_RELU, bar - 1, acc, i * 256, i, i);
+  }
+  // ---- heads: extra (-> X) and density (-> Y[0:16]) both read h7; one commit covers both -------------------------
+  for (int kb = 0; kb < 4; ++kb)
+    add_step(s, n, off, P_EXTRA, 0, 0, kb * 64, 256, 64, 256, 256, kAccX, kb, 4, F_WAIT | (kb == 0 ? F_FIRST : 0), 0);
+  for (int kb = 0; kb < 4; ++kb)
+    add_step(s, n, off, P_DEN, 0, 0, kb * 64, 16, 64, 16, 16, kAccY, kb, 4, (kb == 0 ? F_FIRST : 0), kb == 3 ? 1 : 0);
+  epi(E_HEADS, 0, kAccX, kBiasHE, -1, 8);
+  for (int kb = 0; kb < 4; ++kb)  // view layer, bottleneck columns (the view-direction columns are the row bias)
+    add_step(s, n, off, P_VIEW, 0, 0, kb * 64, 128, 64, 128, 128, kAccY + 128, kb, 4, F_WAIT | (kb == 0 ? F_FIRST : 0),
+             kb == 3 ? 2 : 0);
+  epi(E_VIEW, 1, kAccY + 128, 0, -1, 9);
+  for (int kb = 0; kb < 2; ++kb)
+    add_step(s, n, off, P_COL, 0, 0, kb * 64, 16, 64, 16, 16, kAccY, kb, 4, F_WAIT | (kb == 0 ? F_FIRST : 0),
+             kb == 1 ? 2 : 0);
+  epi(E_COLOR, 1, kAccY, kBiasC, 7, 17);
+  const int n_fwd = n, ne_fwd = ne;
+  // ---- density-Jacobian sweep: J_i computes a_{i-1} = relu'(h_{i-1}) * (a_i W_i) with the transposed tiles -------
+  for (int i = 7; i >= 1; --i) {
+    const int acc = (i & 1) ? kAccX : kAccY, bar = (i & 1) ? 1 : 2;
+    for (int kb = 0; kb < 4; ++kb)
+      add_step(s, n, off, i, 1, kb * 64, 0, 256, 64, 256, 256, acc, kb, 4, F_WAIT | (kb == 0 ? F_FIRST : 0),
+               (kb == 3 && i != 5) ? bar : 0);
+    if (i == 5) {  // skip connection: d sigma / d enc += a_5 W_5[:, 256:352]   (-> Y[0:96], J5 itself is in X)
+      for (int kb = 0; kb < 4; ++kb)
+        add_step(s, n, off, 5, 1, kb * 64, 256, 96, 64, 96, 96, kAccY, kb, 4, (kb == 0 ? F_FIRST : 0), kb == 3 ? bar : 0);
+      epi(E_JAC5, bar - 1, acc, 0, i - 1, 10 + i - 1);
+    } else {
+      epi(E_JAC, bar - 1, acc, 0, i - 1, 10 + i - 1);
+    }
+  }
+  for (int kb = 0; kb < 4; ++kb)  // d sigma / d enc += a_0 W_0
+    add_step(s, n, off, 0, 1, kb * 64, 0, 96, 64, 96, 96, kAccY, kb, 4, F_WAIT | (kb == 0 ? F_FIRST : 0), kb == 3 ? 2 : 0);
+  epi(E_G0, 1, kAccY, 0, -1, -1);
+  s.tab[1].n_steps = n, s.tab[1].n_epi = ne;
+  s.tab[0] = s.tab[1];
+  s.tab[0].n_steps = n_fwd, s.tab[0].n_epi = ne_fwd;
+  s.n_pack = n;
+  s.blob_bytes = off;
+  built = true;
+  return s;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// weight packing: fp32 parameters -> bf16 tiles in the 128B-swizzled K-major image tcgen05 reads from shared memory
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void pack_tiles_kernel(const __grid_constant__ PackArgs a, uint8_t* __restrict__ wblob) {
+  const PackTile t = a.tiles[blockIdx.x];
+  const float* W = a.w[t.param];
+  const int ld = a.ld[t.param];
+  const int chunks = t.rows * 8;  // 16-byte chunks (8 bf16)
+  for (int i = threadIdx.x; i < chunks; i += blockDim.x) {
+    const int r = i >> 3, j = i & 7;
+    __nv_bfloat162 h[4];
+#pragma unroll
+    for (int e = 0; e < 8; e += 2) {
+      float v[2];
+#pragma unroll
+      for (int d = 0; d < 2; ++d) {
+        const int c = j * 8 + e + d;
+        float x = 0.f;
+        if (r < t.vr && c < t.vc) x = t.transposed ? W[(size_t)(t.r0 + c) * ld + t.c0 + r] : W[(size_t)(t.r0 + r) * ld + t.c0 + c];
+        v[d] = x;
+      }
+      h[e >> 1] = __floats2bfloat162_rn(v[0], v[1]);
+    }
+    *reinterpret_cast<uint4*>(wblob + t.blob_off + r * 128 + ((j ^ (r & 7)) << 4)) = *reinterpret_cast<uint4*>(h);
+  }
+}
+
+__global__ void pack_bias_kernel(const __grid_constant__ PackArgs a, float* __restrict__ bblob) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kBiasFloats; i += gridDim.x * blockDim.x) {
+    float v = 0.f;
+    if (i < 2048) v = a.b[i >> 8][i & 255];
+    else if (i < kBiasHD) v = a.b[9][i - kBiasHE];
+    else if (i < kBiasC) v = (i - kBiasHD < a.C) ? a.b[8][i - kBiasHD] : 0.f;
+    else if (i < kWSigma) v = (i - kBiasC < 3) ? a.b[11][i - kBiasC] : 0.f;
+    else v = a.w[8][i - kWSigma];  // sigma row of the density head: seed of the Jacobian sweep
+    bblob[i] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32u(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// K-major, 128B-swizzled operand descriptor from (shared address >> 4): LBO = 16 B (unused), SBO = 1024 B, version 1
+__device__ __forceinline__ uint64_t desc_from16(uint32_t addr16) {
+  constexpr uint32_t kHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+  return ((uint64_t)kHi << 32) | (uint64_t)((addr16 & 0x3FFFu) | (1u << 16));
+}
+
+enum { M_RELU = 0, M_LINEAR = 1, M_VIEW = 2, M_JAC = 3, M_SEED = 4 };
+
+struct EpiCtx {
+  uint8_t* abuf;
+  uint32_t* masks;      // [layer][unit][row]
+  FBarriers* bars;
+  const CUtensorMap* tmActs;
+  int q, hf, lane, row, save, tile_row0;
+};
+
+// Rewrite this warp's part of the activation buffer (the next op's A operand) from accumulator `tacc`.
+// The two warps of a TMEM lane quadrant interleave the 32-column units (hf = 0: even units, hf = 1: odd units) so
+// that units become available in the order the MMA warp consumes them.  TMEM loads are software-pipelined: the
+// load of the next unit is in flight while the current one is processed.
+//   unit u covers columns [32u, 32u+32) = k-block u/2, 16-byte chunks (u&1)*4 .. +3 of the 128-byte row.
+template <int MODE, bool NORMALS>
+__device__ __forceinline__ void rewrite_abuf(const EpiCtx& c, uint32_t tacc, int nunits, const float* bias,
+                                             const float* rowbias, int mask_idx, int save_idx) {
+  uint32_t r[2][32];
+  const int n_mine = nunits >> 1;  // units handled by this warp: hf, hf+2, ...
+  if (MODE != M_SEED) tmem_ld32u(tacc + c.hf * 32, r[0]);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (i < n_mine) {
+      const int u = c.hf + 2 * i;
+      float v[32];
+      if (MODE == M_RELU || MODE == M_LINEAR || MODE == M_VIEW) {
+        const float4* src = reinterpret_cast<const float4*>(MODE == M_VIEW ? rowbias : bias) + u * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 t = __ldg(src + j);
+          v[4 * j] = t.x, v[4 * j + 1] = t.y, v[4 * j + 2] = t.z, v[4 * j + 3] = t.w;
+        }
+      }
+      if (MODE == M_SEED) {
+        const float4* src = reinterpret_cast<const float4*>(bias) + u * 8;  // sigma row of the density head
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 t = __ldg(src + j);
+          v[4 * j] = t.x, v[4 * j + 1] = t.y, v[4 * j + 2] = t.z, v[4 * j + 3] = t.w;
+        }
+      } else {
+        tmem_wait_ld();
+        if (i + 1 < n_mine) tmem_ld32u(tacc + (u + 2) * 32, r[(i + 1) & 1]);
+        if (MODE == M_JAC) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[i & 1][j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(r[i & 1][j]);
+        }
+        if (MODE == M_RELU || MODE == M_VIEW) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+      }
+      if (NORMALS && MODE == M_RELU) {
+        uint32_t bits = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) bits |= (v[j] > 0.f ? 1u : 0u) << j;
+        c.masks[(mask_idx * 8 + u) * kTileM + c.row] = bits;
+      }
+      if (MODE == M_JAC || MODE == M_SEED) {
+        const uint32_t bits = c.masks[(mask_idx * 8 + u) * kTileM + c.row];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? v[j] : 0.f;
+      }
+      if (c.save) {
+        // the TMA store that last read this k-block (issued by the hf = 0 warp of the pair) must be done reading it
+        if (c.hf == 0 && c.lane == 0) bulk_wait_read<0>();
+        named_bar_sync(1 + c.q, 64);
+      }
+      uint8_t* dst = c.abuf + (u >> 1) * kKbBytes + c.row * 128;
+      const int jb = (u & 1) * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        __nv_bfloat162 h[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(v[8 * j + 2 * k], v[8 * j + 2 * k + 1]);
+        *reinterpret_cast<uint4*>(dst + (((jb + j) ^ (c.row & 7)) << 4)) = *reinterpret_cast<uint4*>(h);
+      }
+      fence_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (c.lane == 0) mbar_arrive(&c.bars->a_ready[u]);
+      if (c.save) {
+        // both halves of k-block u/2 (rows of this quadrant) are in place: one thread of the pair stores the box
+        named_bar_sync(1 + c.q, 64);
+        if (save_idx >= 0 && c.hf == 0 && c.lane == 0) {
+          tma_store_3d(c.tmActs, c.abuf + (u >> 1) * kKbBytes + c.q * 4096, (u >> 1) * 64, c.tile_row0 + c.q * 32, save_idx);
+          bulk_commit();
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------------------------
+template <bool NORMALS>
+__global__ void __launch_bounds__(kFThreads, 1)
+mlp_fused_kernel(const __grid_constant__ CUtensorMap tmEnc, const __grid_constant__ CUtensorMap tmActs,
+                 const __grid_constant__ Tables tab, const FusedParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_1024(smem_raw);
+  uint8_t* abuf = smem;
+  uint8_t* ring = abuf + kAbufBytes;
+  uint32_t* masks = reinterpret_cast<uint32_t*>(ring + (size_t)p.nstages * kSlotBytes);
+  FBarriers* bars = reinterpret_cast<FBarriers*>(reinterpret_cast<uint8_t*>(masks) + (NORMALS ? kMaskBytes : 0));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int NS = p.nstages;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmEnc);
+    if (p.save) tma_prefetch_desc(&tmActs);
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&bars->full[s], 1);
+      mbar_init(&bars->empty[s], 1);
+    }
+    for (int u = 0; u < 8; ++u) mbar_init(&bars->a_ready[u], 4);
+    mbar_init(&bars->acc_full[0], 1);
+    mbar_init(&bars->acc_full[1], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&bars->tmem_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ================================ producer ==================================================================
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t ph = 0;
+      for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int row0 = (int)(tile * kTileM);
+        for (int s = 0; s < tab.n_steps; ++s) {
+          const uint32_t blob_off = tab.steps[s].blob_off;
+          const uint32_t bytes = tab.steps[s].bytes;
+          if (tab.steps[s].flags & F_LOADENC) {
+            mbar_wait(&bars->empty[slot], ph ^ 1);
+            mbar_expect_tx(&bars->full[slot], 2 * kKbBytes);
+            tma_load_2d(ring + (size_t)slot * kSlotBytes, &tmEnc, &bars->full[slot], 0, row0);
+            tma_load_2d(ring + (size_t)slot * kSlotBytes + kKbBytes, &tmEnc, &bars->full[slot], 64, row0);
+            if (++slot == NS) slot = 0, ph ^= 1;
+          }
+          mbar_wait(&bars->empty[slot], ph ^ 1);
+          mbar_expect_tx(&bars->full[slot], bytes);
+          bulk_load_1d(ring + (size_t)slot * kSlotBytes, p.wblob + blob_off, bytes, &bars->full[slot]);
+          if (++slot == NS) slot = 0, ph ^= 1;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================================================
+    // The whole warp runs this loop with warp-uniform values (descriptors stay in uniform registers); one elected
+    // lane issues the tcgen05 instructions.
+    int slot = 0, enc_slot = 0;
+    uint32_t ph = 0, unit_ph = 0;
+    const uint32_t abuf16 = smem_u32(abuf) >> 4, ring16 = smem_u32(ring) >> 4;
+    for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int s = 0; s < tab.n_steps; ++s) {
+        const uint32_t flags = tab.steps[s].flags;
+        const uint32_t idesc = tab.steps[s].idesc;
+        const uint32_t d_tmem = tmem_base + tab.steps[s].acc_col;
+        const uint32_t a_off16 = tab.steps[s].a_off16;
+        if (flags & F_LOADENC) {
+          mbar_wait(&bars->full[slot], ph);
+          enc_slot = slot;
+          if (++slot == NS) slot = 0, ph ^= 1;
+        }
+        mbar_wait(&bars->full[slot], ph);
+        const uint32_t a16 = ((flags & F_AENC) ? ring16 + (uint32_t)enc_slot * (kSlotBytes >> 4) : abuf16) + a_off16;
+        const uint32_t b16 = ring16 + (uint32_t)slot * (kSlotBytes >> 4);
+        const int u0 = (int)((flags >> 16) & 7u);
+        if (flags & F_WAIT) {
+          mbar_wait(&bars->a_ready[u0], (unit_ph >> u0) & 1u);
+          unit_ph ^= 1u << u0;
+        }
+        tc_fence_after();
+        if (elect_one()) {
+          umma_f16(d_tmem, desc_from16(a16), desc_from16(b16), idesc, (flags & F_FIRST) ? 0u : 1u);
+          umma_f16(d_tmem, desc_from16(a16 + 2), desc_from16(b16 + 2), idesc, 1u);
+        }
+        __syncwarp();
+        if (((flags >> 8) & 7u) == 4u) {
+          if (flags & F_WAIT) {
+            mbar_wait(&bars->a_ready[u0 + 1], (unit_ph >> (u0 + 1)) & 1u);
+            unit_ph ^= 1u << (u0 + 1);
+            tc_fence_after();
+          }
+          if (elect_one()) {
+            umma_f16(d_tmem, desc_from16(a16 + 4), desc_from16(b16 + 4), idesc, 1u);
+            umma_f16(d_tmem, desc_from16(a16 + 6), desc_from16(b16 + 6), idesc, 1u);
+          }
+          __syncwarp();
+        }
+        if (elect_one()) {
+          umma_commit(&bars->empty[slot]);
+          if (flags & F_RELENC) umma_commit(&bars->empty[enc_slot]);
+          const uint32_t cm = (flags >> 12) & 3u;
+          if (cm) umma_commit(&bars->acc_full[cm - 1]);
+        }
+        __syncwarp();
+        if (++slot == NS) slot = 0, ph ^= 1;
+      }
+    }
+  } else {
+    // ================================ epilogue warps ============================================================
+    EpiCtx c;
+    c.abuf = abuf, c.masks = masks, c.bars = bars, c.tmActs = &tmActs;
+    c.q = warp & 3;            // TMEM lane quadrant (hardware rule: warp id % 4)
+    c.hf = (warp - 2) >> 2;    // which of the two warps of the quadrant: even / odd 32-column units
+    c.lane = lane, c.row = c.q * 32 + lane, c.save = p.save;
+    const uint32_t tlane = tmem_base + ((uint32_t)(c.q * 32) << 16);
+    uint32_t acc_ph = 0;
+    for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const long long m = tile * kTileM + c.row;
+      const bool row_ok = m < p.M;
+      const long long m_safe = row_ok ? m : p.M - 1;
+      c.tile_row0 = (int)(tile * kTileM);
+      for (int e = 0; e < tab.n_epi; ++e) {
+        const Epi ep = tab.epis[e];
+        mbar_wait(&bars->acc_full[ep.bar], (acc_ph >> ep.bar) & 1u);
+        acc_ph ^= 1u << ep.bar;
+        tc_fence_after();
+        const uint32_t tacc = tlane + ep.acc_col;
+        switch (ep.type) {
+          case E_RELU:
+            rewrite_abuf<M_RELU, NORMALS>(c, tacc, 8, p.bblob + ep.bias_off, nullptr, ep.mask_idx, ep.save_idx);
+            break;
+          case E_HEADS:
+            if (c.hf == 0) {  // density head (Y[0:16]) before anything else
+              float v[16];
+              tmem_ld16(tlane + kAccY, v);
+              if (row_ok) {
+#pragma unroll
+                for (int ch = 0; ch < 16; ++ch)
+                  if (ch < p.C) p.raw_den[m * p.C + ch] = v[ch] + __ldg(p.bblob + kBiasHD + ch);
+              }
+            }
+            rewrite_abuf<M_LINEAR, NORMALS>(c, tacc, 8, p.bblob + ep.bias_off, nullptr, 0, ep.save_idx);
+            break;
+          case E_VIEW:
+            rewrite_abuf<M_VIEW, NORMALS>(c, tacc, 4, nullptr, p.row_bias + (m_safe / p.S) * kCondW, 0, ep.save_idx);
+            break;
+          case E_COLOR:
+            if (c.hf == 0) {
+              float v[16];
+              tmem_ld16(tacc, v);
+              if (row_ok) {
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) p.raw_rgb[m * 3 + ch] = v[ch] + __ldg(p.bblob + kBiasC + ch);
+              }
+            }
+            if (NORMALS)  // seed of the Jacobian sweep: a_7 = relu'(h_7) * w_sigma
+              rewrite_abuf<M_SEED, NORMALS>(c, tacc, 8, p.bblob + kWSigma, nullptr, ep.mask_idx, ep.save_idx);
+            else
+              tc_fence_before();
+            break;
+          case E_JAC5:
+          case E_G0:
+            if (c.hf == 0) {  // d sigma / d enc: skip-connection part first (stored), layer-0 part added at the end
+#pragma unroll 1
+              for (int c0 = 0; c0 < kEncDim; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32u(tlane + kAccY + c0, r);
+                tmem_wait_ld();
+                if (row_ok) {
+                  float4* dst = reinterpret_cast<float4*>(p.g_enc + m * kEncDim + c0);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    float4 o = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                           __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+                    if (ep.type == E_G0) {
+                      float4 prev = dst[i];
+                      o.x += prev.x, o.y += prev.y, o.z += prev.z, o.w += prev.w;
+                    }
+                    dst[i] = o;
+                  }
+                }
+              }
+            }
+            if (ep.type == E_G0) {
+              tc_fence_before();
+              break;
+            }
+            rewrite_abuf<M_JAC, NORMALS>(c, tacc, 8, nullptr, nullptr, ep.mask_idx, ep.save_idx);
+            break;
+          default:  // E_JAC
+            rewrite_abuf<M_JAC, NORMALS>(c, tacc, 8, nullptr, nullptr, ep.mask_idx, ep.save_idx);
+            break;
+        }
+      }
+    }
+    if (lane == 0) bulk_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+static bool make_map_enc(CUtensorMap* out, const void* base, unsigned long long rows, unsigned long long ld) {
+  return make_map(out, base, rows, kEncDim, ld, 64, kTileM);
+}
+
+static bool make_map_acts(CUtensorMap* out, const void* base, unsigned long long planes, unsigned long long rows) {
+  EncodeTiledFn enc = get_encode();
+  if (enc == nullptr) {
+    set_error_msg("cuTensorMapEncodeTiled not available from the driver");
+    return false;
+  }
+  cuuint64_t dims[3] = {(cuuint64_t)kWidth, rows, planes};
+  cuuint64_t strides[2] = {(cuuint64_t)kWidth * 2, rows * (cuuint64_t)kWidth * 2};
+  cuuint32_t box[3] = {64, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error_msg("cuTensorMapEncodeTiled failed for the activation planes");
+    return false;
+  }
+  return true;
+}
+
+}  // namespace fused
+}  // namespace pnb
+
+using namespace pnb;
+using namespace pnb::fused;
+
+extern "C" long long pnb_mlp_fused_wblob_bytes(void) { return (long long)schedule().blob_bytes; }
+extern "C" long long pnb_mlp_fused_bblob_floats(void) { return kBiasFloats; }
+extern "C" int pnb_mlp_fused_act_planes(void) { return 18; }
+
+extern "C" int pnb_mlp_fused_pack(const void* const* params_host, int C, void* wblob, float* bblob, void* stream) {
+  PNB_REQUIRE(params_host != nullptr && wblob != nullptr && bblob != nullptr, "mlp_fused_pack: null argument");
+  PNB_REQUIRE(C >= 1 && C <= 16, "mlp_fused_pack: need 1 <= C <= 16 density-head channels");
+  const Schedule& s = schedule();
+  static const int in_features[kNumParams] = {96, 256, 256, 256, 256, 352, 256, 256, 256, 256, 283, 128};
+  PackArgs a{};
+  for (int i = 0; i < kNumParams; ++i) {
+    a.w[i] = reinterpret_cast<const float*>(params_host[2 * i]);
+    a.b[i] = reinterpret_cast<const float*>(params_host[2 * i + 1]);
+    a.ld[i] = in_features[i];
+    PNB_REQUIRE(a.w[i] != nullptr && a.b[i] != nullptr, "mlp_fused_pack: null parameter pointer");
+  }
+  a.C = C;
+  a.n_tiles = s.n_pack;
+  for (int i = 0; i < s.n_pack; ++i) a.tiles[i] = s.pack[i];
+  for (int i = 0; i < s.n_pack; ++i) {  // density / colour heads have C / 3 valid rows
+    if (a.tiles[i].param == 8) a.tiles[i].vr = (int16_t)C;
+    if (a.tiles[i].param == 11) a.tiles[i].vr = 3;
+  }
+  cudaStream_t st = as_stream(stream);
+  pack_tiles_kernel<<<s.n_pack, 256, 0, st>>>(a, reinterpret_cast<uint8_t*>(wblob));
+  int rc = finish("mlp_fused_pack(tiles)");
+  if (rc) return rc;
+  pack_bias_kernel<<<4, 256, 0, st>>>(a, bblob);
+  return finish("mlp_fused_pack(bias)");
+}
+
+extern "C" int pnb_mlp_fused_fwd(long long M, int S, int C, const void* enc, int ld_enc, const void* wblob,
+                                 const float* bblob, const float* row_bias, float* raw_den, float* raw_rgb,
+                                 void* acts, float* g_enc, void* stream) {
+  PNB_REQUIRE(M >= 0 && S >= 1 && C >= 1 && C <= 16, "mlp_fused_fwd: bad sizes");
+  PNB_REQUIRE(enc && wblob && bblob && row_bias && raw_den && raw_rgb, "mlp_fused_fwd: null argument");
+  PNB_REQUIRE(ld_enc % 8 == 0 && ld_enc >= kEncDim && ((uintptr_t)enc % 16 == 0) && ((uintptr_t)wblob % 16 == 0) &&
+                  ((uintptr_t)bblob % 16 == 0) && ((uintptr_t)row_bias % 16 == 0),
+              "mlp_fused_fwd: enc / blobs / row_bias must be 16-byte aligned, ld_enc % 8 == 0");
+  PNB_REQUIRE(g_enc == nullptr || (uintptr_t)g_enc % 16 == 0, "mlp_fused_fwd: g_enc must be 16-byte aligned");
+  PNB_REQUIRE(acts == nullptr || (uintptr_t)acts % 128 == 0, "mlp_fused_fwd: acts must be 128-byte aligned");
+  PNB_REQUIRE(M < (1ll << 31) - kTileM, "mlp_fused_fwd: M too large for 32-bit TMA coordinates");
+  if (M == 0) return 0;
+  const Schedule& s = schedule();
+  const bool normals = g_enc != nullptr;
+  FusedParams p{};
+  p.M = M, p.num_tiles = (M + kTileM - 1) / kTileM;
+  p.S = S, p.C = C, p.save = acts != nullptr;
+  p.wblob = reinterpret_cast<const uint8_t*>(wblob), p.bblob = bblob, p.row_bias = row_bias;
+  p.raw_den = raw_den, p.raw_rgb = raw_rgb, p.g_enc = g_enc;
+  const size_t fixed = 1024 + kAbufBytes + (normals ? kMaskBytes : 0) + sizeof(FBarriers);
+  int ns = (int)(((size_t)kSmemLimit - fixed) / kSlotBytes);
+  if (ns > kFMaxStages) ns = kFMaxStages;
+  PNB_REQUIRE(ns >= 3, "mlp_fused_fwd: shared memory budget too small");
+  p.nstages = ns;
+  const size_t smem_bytes = fixed + (size_t)ns * kSlotBytes;
+  CUtensorMap tmEnc, tmActs;
+  if (!make_map_enc(&tmEnc, enc, (unsigned long long)M, (unsigned long long)ld_enc)) return PNB_ERR_ARG;
+  if (p.save) {
+    if (!make_map_acts(&tmActs, acts, 18, (unsigned long long)M)) return PNB_ERR_ARG;
+  } else {
+    tmActs = tmEnc;
+  }
+  const long long gx = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+  cudaStream_t st = as_stream(stream);
+  cudaError_t e;
+  if (normals) {
+    e = cudaFuncSetAttribute(mlp_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e == cudaSuccess) mlp_fused_kernel<true><<<(unsigned)gx, kFThreads, smem_bytes, st>>>(tmEnc, tmActs, s.tab[1], p);
+  } else {
+    e = cudaFuncSetAttribute(mlp_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e == cudaSuccess) mlp_fused_kernel<false><<<(unsigned)gx, kFThreads, smem_bytes, st>>>(tmEnc, tmActs, s.tab[0], p);
+  }
+  if (e != cudaSuccess) {
+    set_error("mlp_fused_fwd(smem attr)", e);
+    return (int)e;
+  }
+  return finish("mlp_fused_fwd");
+}

@@ -11,6 +11,7 @@ Two GEMM back-ends share the orchestration:
 from __future__ import annotations
 
 import ctypes
+import os
 import weakref
 from typing import Dict, List, Optional
 
@@ -285,6 +286,73 @@ class _SimtBf16Backend(_TCBackend):
                                                 None, None, 0, None, 0, 0, _stream()), "gemm_bf16_simt(TN)")
 
 
+
+# ----------------------------------------------------------------------------------------------------------------
+# fused MLP (csrc/mlp_fused.cu): weight blob cache and launcher
+# ----------------------------------------------------------------------------------------------------------------
+FUSED_TOPOLOGY = dict(depth=8, skip=4, width=256, xyz_dim=96, cond_width=128, view_in=283)
+_fused_cache: Dict[tuple, dict] = {}
+
+
+def fused_enabled() -> bool:
+    return not os.environ.get("PNB_NO_FUSED")
+
+
+def fused_supported(cfg, P) -> bool:
+    t = FUSED_TOPOLOGY
+    wv = P["view_layers.0.0.weight"]
+    return (cfg["depth"] == t["depth"] and cfg["skip"] == t["skip"] and cfg["width"] == t["width"]
+            and cfg["xyz_dim"] == t["xyz_dim"] and tuple(wv.shape) == (t["cond_width"], t["view_in"])
+            and P["density_layer.weight"].shape[0] <= 16 and P["color_layer.weight"].shape[0] == 3
+            and len([n for n in cfg["names"] if n.startswith("view_layers.") and n.endswith(".weight")]) == 1)
+
+
+def fused_pack(names: List[str], params) -> dict:
+    """bf16 tile blob + fp32 bias blob of the current parameter values (re-packed when any parameter changed)."""
+    key = tuple(id(p) for p in params)
+    ck = tuple((p.data_ptr(), p._version) for p in params) + (_pack_epoch[0],)
+    slot = _fused_cache.get(key)
+    if slot is not None and slot["ck"] == ck and all(r() is p for r, p in zip(slot["refs"], params)):
+        return slot
+    dev = params[0].device
+    lib = _lib.lib()
+    if slot is None or slot["wblob"].device != dev:
+        if len(_fused_cache) > 64:
+            _fused_cache.clear()
+        slot = dict(wblob=torch.empty(int(lib.pnb_mlp_fused_wblob_bytes()), device=dev, dtype=torch.uint8),
+                    bblob=torch.empty(int(lib.pnb_mlp_fused_bblob_floats()), device=dev, dtype=torch.float32))
+        _fused_cache[key] = slot
+    order = param_names(8, 1)
+    by_name = dict(zip(names, params))
+    ptrs = (ctypes.c_void_p * 24)(*[by_name[n].data_ptr() for n in order])
+    for n in order:
+        t = by_name[n]
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise RuntimeError(f"panonerf_b200: parameter {n} must be contiguous fp32")
+    C = by_name["density_layer.weight"].shape[0]
+    with torch.cuda.device(dev):
+        check(lib.pnb_mlp_fused_pack(ptrs, C, _p(slot["wblob"]), _p(slot["bblob"]), _stream()), "mlp_fused_pack")
+    slot["ck"] = ck
+    slot["refs"] = [weakref.ref(p) for p in params]
+    return slot
+
+
+def fused_forward(enc, vb, S, C, pack, acts, g_enc):
+    """Launch the fused kernel on bf16 IPE features `enc` [M,96]; returns (raw_den, raw_rgb)."""
+    M = enc.shape[0]
+    dev = enc.device
+    raw_den = torch.empty(M, C, device=dev, dtype=torch.float32)
+    raw_rgb = torch.empty(M, 3, device=dev, dtype=torch.float32)
+    flops = M * (2 * (96 * 256 + 6 * 256 * 256 + 352 * 256 + 256 * C + 256 * 256 + 256 * 128 + 128 * 3)
+                 + (2 * (6 * 256 * 256 + 2 * 96 * 256) if g_enc is not None else 0))
+    nbytes = M * (192 + 4 * C + 12 + (384 if g_enc is not None else 0)
+                  + (512 * (10 + (8 if g_enc is not None else 0)) if acts is not None else 0))
+    with torch.cuda.device(dev), _prof("mlp_fused", nbytes, flops):
+        check(_lib.lib().pnb_mlp_fused_fwd(M, S, C, _p(enc), _ld(enc), _p(pack["wblob"]), _p(pack["bblob"]), _p(vb),
+                                           _p(raw_den), _p(raw_rgb), _p(acts), _p(g_enc), _stream()), "mlp_fused_fwd")
+    return raw_den, raw_rgb
+
+
 def make_backend(precision: str, params: Dict[str, torch.Tensor]):
     if precision == "fp32":
         return _F32Backend(params)
@@ -335,6 +403,46 @@ class _Field(torch.autograd.Function):
         dt = be.dtype
         means2, covs2 = means.reshape(M, 3), covs.reshape(M, 3)
         f32 = torch.float32
+
+        fused = (be.name == "tc" and fused_enabled() and fused_supported(cfg, P)
+                 and not (cfg["with_normals"] and cfg.get("jac_precision") == "fp32"))
+        if fused:
+            need_bwd = any(ctx.needs_input_grad)
+            C = P["density_layer.weight"].shape[0]
+            enc = torch.empty(M, xyz, device=dev, dtype=dt)
+            ops.ipe_into(means2, covs2, cfg["min_deg"], cfg["max_deg"], enc)
+            wv = P["view_layers.0.0.weight"]
+            vb = torch.empty(venc.shape[0], wv.shape[0], device=dev, dtype=f32)
+            _F32Backend(P).linear(venc, wv[:, width:], vb, bias=P["view_layers.0.0.bias"])
+            pack = fused_pack(names, params)
+            planes = int(_lib.lib().pnb_mlp_fused_act_planes())
+            acts = torch.empty(planes, M, width, device=dev, dtype=dt) if need_bwd else None
+            g_enc = torch.empty(M, xyz, device=dev, dtype=f32) if cfg["with_normals"] else None
+            raw_den, raw_rgb = fused_forward(enc, vb, S, C, pack, acts, g_enc)
+            n_raw, jac = None, None
+            if cfg["with_normals"]:
+                v = ops.ipe_vjp(means2, covs2, cfg["min_deg"], cfg["max_deg"], g_enc)
+                del g_enc
+                n_raw = torch.empty(M, 3, device=dev, dtype=f32)
+                with torch.cuda.device(dev):
+                    check(_lib.lib().pnb_density_grad_fwd(M, C, _p(raw_den), float(cfg["density_bias"]), _p(v),
+                                                          _p(n_raw), _stream()), "density_grad_fwd")
+                if need_bwd:
+                    jac = ([acts[10 + i] for i in range(depth)], v)
+            ctx.cfg = cfg
+            ctx.n_params = len(params)
+            ctx.need_means = means.requires_grad
+            ctx.means_shape = means.shape
+            if need_bwd:
+                ctx.bufs = dict(means=means2, covs=covs2, venc=venc, enc=enc, hs=[acts[i] for i in range(depth)],
+                                bott=acts[8], hv=acts[9][:, :wv.shape[0]], vb_rows=venc.shape[0], raw_den=raw_den,
+                                jac=jac)
+            else:
+                ctx.bufs = None
+            ctx.params = params
+            if n_raw is None:
+                return raw_rgb, raw_den, None
+            return raw_rgb, raw_den, n_raw
 
         # cat = [h_skip | enc] (the input of the layer after the skip connection); enc lives only there
         cat = torch.empty(M, width + xyz, device=dev, dtype=dt)
@@ -403,7 +511,7 @@ class _Field(torch.autograd.Function):
         ctx.means_shape = means.shape
         # raw buffers are kept on ctx (not save_for_backward): they are private to this Function and never
         # modified in place afterwards
-        ctx.bufs = dict(means=means2, covs=covs2, venc=venc, cat=cat, hs=hs, bott=bott, hv=hv, vb_rows=venc.shape[0],
+        ctx.bufs = dict(means=means2, covs=covs2, venc=venc, enc=enc, hs=hs, bott=bott, hv=hv, vb_rows=venc.shape[0],
                         raw_den=raw_den, jac=jac)
         ctx.params = params
         if n_raw is None:
@@ -419,12 +527,11 @@ class _Field(torch.autograd.Function):
         f32be = _F32Backend(P)
         depth, skip, width, xyz = cfg["depth"], cfg["skip"], cfg["width"], cfg["xyz_dim"]
         S = cfg["samples_per_ray"]
-        cat, hs, bott, hv, raw_den = B["cat"], B["hs"], B["bott"], B["hv"], B["raw_den"]
+        enc, hs, bott, hv, raw_den = B["enc"], B["hs"], B["bott"], B["hv"], B["raw_den"]
         means, covs, venc = B["means"], B["covs"], B["venc"]
         M = means.shape[0]
         dev, dt, f32 = means.device, be.dtype, torch.float32
         C = raw_den.shape[1]
-        enc = cat[:, width:]
         skip_layers = [i for i in range(1, depth) if (i - 1) % skip == 0 and i > 1]
 
         # one flat, zero-initialised gradient buffer; per-parameter views are what autograd receives
@@ -476,7 +583,9 @@ class _Field(torch.autograd.Function):
             del ucat, q_prev
 
         # ---- heads ------------------------------------------------------------------------------------------
-        trunk_out = cat if ((depth - 1) % skip == 0 and depth - 1 > 0) else hs[depth - 1]
+        if (depth - 1) % skip == 0 and depth - 1 > 0:
+            raise NotImplementedError("a skip connection feeding the heads is not supported")
+        trunk_out = hs[depth - 1]
         # colour head
         _colsum(d_raw_rgb, G["color_layer.bias"])
         dzv = torch.empty(M, hv.shape[1], device=dev, dtype=dt)
@@ -521,7 +630,7 @@ class _Field(torch.autograd.Function):
                 break
             x_prev = hs[i - 1]
             if i in skip_layers:
-                be.wgrad(dz, cat[:, :width], G[wname][:, :width])
+                be.wgrad(dz, hs[i - 1], G[wname][:, :width])
                 be.wgrad(dz, enc, G[wname][:, width:])
                 if need_enc:
                     be.dgrad(dz, be.w(wname, width, width + xyz), d_enc, accum=True)

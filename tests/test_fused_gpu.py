@@ -1,0 +1,144 @@
+"""GPU parity of the fused MLP kernel (csrc/mlp_fused.cu) against the layer-by-layer tensor-core path it replaces
+(csrc/gemm_tc.cu), which is itself pinned to the fp32 parity path and the reference's golden vectors by
+tests/test_models_gpu.py.  Both paths push the same bf16 operands through tcgen05 with fp32 accumulation and the same
+epilogue order, so they must agree to bf16 rounding noise; the weight-blob packer is checked bit-exactly."""
+import os
+
+import pytest
+import torch
+
+from conftest import load_golden
+from util import assert_close, golden_rays, golden_state_dict
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _tc_or_skip():
+    from panonerf_b200 import _lib
+    if not _lib.lib().pnb_tc_available():
+        pytest.skip("not an sm_100 device")
+
+
+def _inputs(S, R=None, seed=0):
+    from panonerf_b200 import ops
+    g = load_golden("panonerf_w256.npz")
+    sd = golden_state_dict(g)
+    rays, _ = golden_rays(g, DEV)
+    if R is not None:
+        rays = type(rays)(*[x[:R].contiguous() for x in rays])
+    t, means, covs = ops.sample_cast(rays.origins, rays.directions, rays.radii, rays.near, rays.far, S)
+    venc = ops.pos_enc(rays.viewdirs, 4)
+    return sd, means, covs, venc
+
+
+def _field(sd, means, covs, venc, S, fused, with_normals, grads=None, need_means=False):
+    from panonerf_b200 import field
+    old = os.environ.pop("PNB_NO_FUSED", None)
+    if not fused:
+        os.environ["PNB_NO_FUSED"] = "1"
+    try:
+        params = {k: v.clone().to(DEV).requires_grad_(grads is not None) for k, v in sd.items()}
+        m = means.clone().requires_grad_(need_means)
+        ctx = torch.enable_grad() if grads is not None else torch.no_grad()
+        with ctx:
+            raw_rgb, raw_den, n_raw = field.radiance_field(m, covs, venc, params, precision="bf16", samples_per_ray=S,
+                                                           min_deg=0, max_deg=16, density_bias=-1.0, skip=4,
+                                                           with_normals=with_normals)
+            out = dict(raw_rgb=raw_rgb.detach(), raw_den=raw_den.detach(),
+                       n_raw=None if n_raw is None else n_raw.detach())
+            if grads is not None:
+                g1, g2, g3 = grads
+                loss = (raw_rgb * g1).sum() + (raw_den * g2).sum()
+                if n_raw is not None:
+                    loss = loss + (n_raw * g3).sum()
+                loss.backward()
+                out["grads"] = {k: p.grad.detach().double().flatten() for k, p in params.items()}
+                if need_means:
+                    out["d_means"] = m.grad.detach().double().flatten()
+        return out
+    finally:
+        os.environ.pop("PNB_NO_FUSED", None)
+        if old is not None:
+            os.environ["PNB_NO_FUSED"] = old
+
+
+def test_pack_blob_is_the_swizzled_bf16_image_of_the_weights():
+    """Un-swizzle two tiles of the blob on the host and compare with the parameters, bit-exactly."""
+    _tc_or_skip()
+    from panonerf_b200 import field
+    sd = golden_state_dict(load_golden("panonerf_w256.npz"))
+    names = field.param_names(8, 1)
+    params = [sd[n].to(DEV).contiguous() for n in names]
+    pack = field.fused_pack(names, params)
+    torch.cuda.synchronize()
+    blob = pack["wblob"].cpu()
+
+    def tile(off, rows):
+        raw = blob[off:off + rows * 128].view(rows, 8, 16)          # [row][stored chunk][bytes]
+        r = torch.arange(rows).view(rows, 1)
+        j = torch.arange(8).view(1, 8)
+        src = (j ^ (r & 7))                                           # logical chunk j lives at stored chunk j ^ (r&7)
+        logical = torch.gather(raw, 1, src.view(rows, 8, 1).expand(rows, 8, 16))
+        return logical.reshape(rows, 128).view(torch.bfloat16)       # [rows, 64]
+
+    w0 = sd["layers.0.0.weight"]
+    assert torch.equal(tile(0, 256).float(), w0[:, :64].bfloat16().float())
+    t1 = tile(256 * 128, 256).float()
+    assert torch.equal(t1[:, :32], w0[:, 64:96].bfloat16().float()) and float(t1[:, 32:].abs().max()) == 0.0
+    w1 = sd["layers.1.0.weight"]
+    assert torch.equal(tile(2 * 256 * 128 + 2 * 256 * 128, 256).float(), w1[:, 128:192].bfloat16().float())
+    bb = pack["bblob"].cpu()
+    assert torch.equal(bb[:256], sd["layers.0.0.bias"]) and torch.equal(bb[2048:2304], sd["extra_layer.bias"])
+    assert torch.equal(bb[2304:2309], sd["density_layer.bias"]) and torch.equal(bb[2320:2323], sd["color_layer.bias"])
+    assert torch.equal(bb[2336:2592], sd["density_layer.weight"][0])
+
+
+@pytest.mark.parametrize("S,R,normals", [(64, None, False), (64, None, True), (10, 77, True), (7, 3, False)])
+def test_fused_forward_matches_layered_path(S, R, normals):
+    """Same bf16 operands, same accumulation order: outputs agree to a few bf16 ulps (ragged tile tails included)."""
+    _tc_or_skip()
+    sd, means, covs, venc = _inputs(S, R)
+    a = _field(sd, means, covs, venc, S, True, normals)
+    b = _field(sd, means, covs, venc, S, False, normals)
+    assert_close(a["raw_rgb"], b["raw_rgb"], 1e-3, "raw_rgb", floor=float(b["raw_rgb"].abs().mean()))
+    assert_close(a["raw_den"], b["raw_den"], 1e-3, "raw_den", floor=float(b["raw_den"].abs().mean()))
+    if normals:
+        na, nb = a["n_raw"].reshape(-1, 3), b["n_raw"].reshape(-1, 3)
+        assert torch.isfinite(na).all()
+        cos = torch.nn.functional.cosine_similarity(na.double(), nb.double(), dim=-1)
+        big = nb.norm(dim=-1) > 1e-3 * float(nb.norm(dim=-1).mean())
+        assert float((cos[big] > 0.999).float().mean()) > 0.99, float((cos[big] > 0.999).float().mean())
+        assert_close(na.norm(dim=-1).mean(), nb.norm(dim=-1).mean(), 1e-2, "normal magnitude")
+
+
+@pytest.mark.parametrize("need_means", [False, True])
+def test_fused_forward_feeds_the_backward(need_means):
+    """Activations / Jacobian rows written by the fused kernel's TMA stores drive the hand-written backward: every
+    parameter gradient (incl. the adjoint of the Jacobian sweep) agrees with the layered path."""
+    _tc_or_skip()
+    S = 64
+    sd, means, covs, venc = _inputs(S)
+    R = means.shape[0]
+    gen = torch.Generator().manual_seed(3)
+    grads = (torch.randn(R, S, 3, generator=gen).to(DEV), torch.randn(R, S, 5, generator=gen).to(DEV),
+             (torch.randn(R, S, 3, generator=gen) * 1e-2).to(DEV))
+    a = _field(sd, means, covs, venc, S, True, True, grads, need_means)
+    b = _field(sd, means, covs, venc, S, False, True, grads, need_means)
+    for k in b["grads"]:
+        ga, gb = a["grads"][k], b["grads"][k]
+        cos = float((ga @ gb) / (ga.norm() * gb.norm() + 1e-30))
+        assert cos > 0.9995, (k, cos)
+        assert abs(float(ga.norm()) - float(gb.norm())) <= 0.01 * float(gb.norm()), k
+    if need_means:
+        ga, gb = a["d_means"], b["d_means"]
+        assert float((ga @ gb) / (ga.norm() * gb.norm() + 1e-30)) > 0.999
+
+
+def test_fused_kernel_is_deterministic():
+    _tc_or_skip()
+    sd, means, covs, venc = _inputs(64)
+    a = _field(sd, means, covs, venc, 64, True, True)
+    b = _field(sd, means, covs, venc, 64, True, True)
+    for k in ("raw_rgb", "raw_den", "n_raw"):
+        assert torch.equal(a[k], b[k]), k

@@ -1,0 +1,58 @@
+"""Micro-benchmark of the fused MLP kernel alone: TFLOP/s vs the measured bf16 peak (MEASURED_PEAKS.json).
+python tools/bench_fused.py [samples] [--normals] [--save]"""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from panonerf_b200 import field, ops  # noqa: E402
+
+
+def main():
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    M = int(args[0]) if args else 128 * 148 * 64
+    normals, save = "--normals" in sys.argv, "--save" in sys.argv
+    S, C = 64, 5
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    from oracle import panonerf_oracle as O
+    sd = O.synth_state_dict(seed=4, width=256, c_density=C)
+    names = field.param_names(8, 1)
+    params = [sd[n].to(dev).contiguous() for n in names]
+    pack = field.fused_pack(names, params)
+    means = (torch.rand(M, 3, device=dev) * 2 - 1) * 3
+    covs = torch.rand(M, 3, device=dev) * 1e-3
+    enc = torch.empty(M, 96, device=dev, dtype=torch.bfloat16)
+    ops.ipe_into(means, covs, 0, 16, enc)
+    vb = torch.randn((M + S - 1) // S, 128, device=dev)
+    acts = torch.empty(18, M, 256, device=dev, dtype=torch.bfloat16) if save else None
+    g_enc = torch.empty(M, 96, device=dev) if normals else None
+    flops = M * (2 * (96 * 256 + 6 * 256 * 256 + 352 * 256 + 256 * C + 256 * 256 + 256 * 128 + 128 * 3)
+                 + (2 * (6 * 256 * 256 + 2 * 96 * 256) if normals else 0))
+    for _ in range(3):
+        field.fused_forward(enc, vb, S, C, pack, acts, g_enc)
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        field.fused_forward(enc, vb, S, C, pack, acts, g_enc)
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    ms = sorted(times)[len(times) // 2]
+    peaks = {}
+    pp = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pp):
+        peaks = json.load(open(pp))
+    tf = flops / ms / 1e9
+    print(json.dumps({"kernel": "mlp_fused", "samples": M, "normals": normals, "save": save, "ms": ms,
+                      "tflops": tf, "frac_of_burst_peak": tf / peaks.get("bf16_tflops", 1685.0),
+                      "samples_per_s": M / ms * 1e3, "all_ms": times}))
+
+
+if __name__ == "__main__":
+    main()
