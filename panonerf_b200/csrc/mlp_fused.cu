@@ -21,6 +21,8 @@
 // contributions to d sigma / d enc (through layer 0 and through the skip connection) are accumulated in fp32.
 // With `acts` given, every activation (and Jacobian row) is also written out with TMA stores straight from the
 // activation buffer - that is what the training backward consumes.
+#include <utility>
+
 #include "tc_common.cuh"
 
 namespace pnb {
@@ -35,24 +37,29 @@ constexpr int kAbufBytes = 4 * kKbBytes;
 constexpr int kMaskBytes = 8 * 8 * kTileM * 4;  // [layer][unit][row] u32
 constexpr int kFThreads = 320;
 constexpr int kAccX = 0, kAccY = 256;
-constexpr int kMaxSteps = 88, kMaxEpi = 20, kFMaxStages = 6;
+constexpr int kMaxSteps = 80, kMaxPack = 88, kMaxEpi = 20, kFMaxStages = 6;
 constexpr int kNumParams = 12;  // weights (and biases) in state-dict order: layers 0..7, density, extra, view, colour
+constexpr int kActPlanes = 18;
 
 // bias blob (fp32) layout
 constexpr int kBiasHE = 2048, kBiasHD = 2304, kBiasC = 2320, kWSigma = 2336, kBiasFloats = 2592;
 
-enum : uint8_t { F_AENC = 1, F_LOADENC = 2, F_RELENC = 4, F_FIRST = 8, F_WAIT = 16 };
+enum : uint32_t { F_AENC = 1, F_LOADENC = 2, F_RELENC = 4, F_FIRST = 8, F_WAIT = 16 };
 
-struct Step {          // one ring slot = one weight tile = up to four K=16 MMAs (all fields are whole words so the
-                       // MMA warp reads them through the uniform datapath)
+// One step = one ring slot = one weight tile of `nk16` K=16 MMAs (a multiple of 2; 4 per 64-column k-block).
+struct Step {
   uint32_t blob_off;   // byte offset of the tile in the weight blob
-  uint32_t bytes;      // tile bytes (rows * 128)
+  uint32_t bytes;      // tile bytes
   uint32_t idesc;      // tcgen05 instruction descriptor (M=128, N of this op, bf16 -> fp32)
   uint32_t acc_col;    // TMEM column of the accumulator
   uint32_t a_off16;    // A operand: byte offset >> 4 from the activation buffer (or from the IPE slot with F_AENC)
-  uint32_t flags;      // F_* | nk16 << 8 | commit << 12 (1 -> acc_full[0], 2 -> acc_full[1]) | first unit << 16
+  uint32_t b_kb16;     // byte stride >> 4 between the k-blocks of the weight tile inside the slot
+  uint32_t flags;      // F_*
+  uint32_t nk16;       // K=16 MMAs in this step
+  uint32_t commit;     // 0 none, 1 -> acc_full[0], 2 -> acc_full[1] after this step
+  uint32_t u0;         // first 32-column unit of A this step reads (F_WAIT: wait a_ready[u0 + k/2] before MMA k)
 };
-struct PackTile {      // where a tile's elements come from: tile(r,c) = W[r0+r, c0+c] (or W[r0+c, c0+r] transposed)
+struct PackTile {      // one rows x 64 sub-tile: tile(r,c) = W[r0+r, c0+c] (or W[r0+c, c0+r] when transposed)
   uint32_t blob_off;
   int16_t param, transposed, r0, c0, vr, vc, rows, pad;
 };
@@ -63,22 +70,26 @@ struct Epi {
   uint16_t bias_off;
   int8_t mask_idx, save_idx;
 };
-struct Tables {
+struct Sched {
   Step steps[kMaxSteps];
   Epi epis[kMaxEpi];
-  int n_steps, n_epi;
+  PackTile pack[kMaxPack];
+  int n_fwd, n_all;    // steps of the forward-only / forward + Jacobian-sweep programs
+  int ne_fwd, ne_all;  // epilogue ops
+  int n_pack;
+  uint32_t blob_bytes;
 };
 struct PackArgs {
   const float* w[kNumParams];
   const float* b[kNumParams];
   int ld[kNumParams];
   int C, n_tiles;
-  PackTile tiles[kMaxSteps];
+  PackTile tiles[kMaxPack];
 };
 
 struct FusedParams {
   long long M, num_tiles;
-  int S, C, nstages, save;
+  int S, C, nstages, save, debug;
   const uint8_t* wblob;
   const float* bblob;
   const float* row_bias;
@@ -96,104 +107,100 @@ struct FBarriers {
 };
 
 // ---------------------------------------------------------------------------------------------------------------
-// schedule (host): the order of weight tiles == the order of MMA steps == the order of the producer's loads
+// schedule: the order of weight tiles == the order of MMA steps == the order of the producer's loads.
+// Built at compile time: the MMA warp's program is fully unrolled from it (every descriptor offset, flag and
+// barrier index is an immediate), the producer and epilogue warps read the same table from kernel parameters.
 // ---------------------------------------------------------------------------------------------------------------
-struct Schedule {
-  Tables tab[2];  // [0] forward only, [1] forward + Jacobian sweep
-  PackTile pack[kMaxSteps];
-  int n_pack;
-  uint32_t blob_bytes;
-};
-
-static void add_step(Schedule& s, int& n, uint32_t& off, int param, int transposed, int r0, int c0, int vr, int vc,
-                     int rows, int n_mma, int acc_col, int a_kb, int nk16, int flags, int commit) {
+constexpr void add_step(Sched& s, int& n, int param, int transposed, int r0, int c0, int vr, int vc, int rows,
+                        int nkb, int n_mma, int acc_col, int a_kb, int nk16, uint32_t flags, int commit) {
   Step st{};
-  st.blob_off = off;
-  st.bytes = (uint32_t)rows * 128u;
+  st.blob_off = s.blob_bytes;
+  st.bytes = (uint32_t)(rows * 128 * nkb);
   st.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_mma >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
   st.acc_col = (uint32_t)acc_col;
   st.a_off16 = (uint32_t)(a_kb * kKbBytes) >> 4;
-  st.flags = (uint32_t)flags | ((uint32_t)nk16 << 8) | ((uint32_t)commit << 12) | ((uint32_t)(2 * a_kb) << 16);
-  s.tab[1].steps[n] = st;
-  PackTile pt{};
-  pt.blob_off = off;
-  pt.param = (int16_t)param, pt.transposed = (int16_t)transposed;
-  pt.r0 = (int16_t)r0, pt.c0 = (int16_t)c0, pt.vr = (int16_t)vr, pt.vc = (int16_t)vc, pt.rows = (int16_t)rows;
-  s.pack[n] = pt;
-  off += (uint32_t)rows * 128u;
-  ++n;
+  st.b_kb16 = (uint32_t)(rows * 128) >> 4;
+  st.flags = flags;
+  st.nk16 = (uint32_t)nk16;
+  st.commit = (uint32_t)commit;
+  st.u0 = (uint32_t)(2 * a_kb);
+  s.steps[n++] = st;
+  for (int kb = 0; kb < nkb; ++kb) {  // consecutive 64-column k-blocks of the same rows
+    PackTile pt{};
+    pt.blob_off = s.blob_bytes;
+    pt.param = (int16_t)param, pt.transposed = (int16_t)transposed;
+    pt.r0 = (int16_t)(transposed ? r0 + 64 * kb : r0), pt.c0 = (int16_t)(transposed ? c0 : c0 + 64 * kb);
+    pt.vr = (int16_t)vr, pt.vc = (int16_t)vc, pt.rows = (int16_t)rows;
+    s.pack[s.n_pack++] = pt;
+    s.blob_bytes += (uint32_t)rows * 128u;
+  }
+}
+constexpr void add_epi(Sched& s, int& ne, int type, int bar, int acc_col, int bias_off, int mask_idx, int save_idx) {
+  Epi e{};
+  e.type = (uint8_t)type, e.bar = (uint8_t)bar, e.acc_col = (uint16_t)acc_col, e.bias_off = (uint16_t)bias_off;
+  e.mask_idx = (int8_t)mask_idx, e.save_idx = (int8_t)save_idx;
+  s.epis[ne++] = e;
 }
 
-static const Schedule& schedule() {
-  static Schedule s;
-  static bool built = false;
-  if (built) return s;
+constexpr Sched make_sched() {
+  Sched s{};
   int n = 0, ne = 0;
-  uint32_t off = 0;
-  auto epi = [&](int type, int bar, int acc_col, int bias_off, int mask_idx, int save_idx) {
-    Epi e{};
-    e.type = (uint8_t)type, e.bar = (uint8_t)bar, e.acc_col = (uint16_t)acc_col, e.bias_off = (uint16_t)bias_off;
-    e.mask_idx = (int8_t)mask_idx, e.save_idx = (int8_t)save_idx;
-    s.tab[1].epis[ne++] = e;
-  };
   const int P_DEN = 8, P_EXTRA = 9, P_VIEW = 10, P_COL = 11;
   // ---- trunk -----------------------------------------------------------------------------------------------
   for (int i = 0; i < 8; ++i) {
     const int acc = (i & 1) ? kAccY : kAccX, bar = (i & 1) ? 2 : 1;
     if (i == 0) {
-      add_step(s, n, off, 0, 0, 0, 0, 256, 64, 256, 256, acc, 0, 4, F_AENC | F_LOADENC | F_FIRST, 0);
-      add_step(s, n, off, 0, 0, 0, 64, 256, 32, 256, 256, acc, 1, 2, F_AENC | F_RELENC, bar);
+      add_step(s, n, 0, 0, 0, 0, 256, 64, 256, 1, 256, acc, 0, 4, F_AENC | F_LOADENC | F_FIRST, 0);
+      add_step(s, n, 0, 0, 0, 64, 256, 32, 256, 1, 256, acc, 1, 2, F_AENC | F_RELENC, bar);
     } else {
       for (int kb = 0; kb < 4; ++kb)
-        add_step(s, n, off, i, 0, 0, kb * 64, 256, 64, 256, 256, acc, kb, 4, F_WAIT | (kb == 0 ? F_FIRST : 0),
+        add_step(s, n, i, 0, 0, kb * 64, 256, 64, 256, 1, 256, acc, kb, 4, F_WAIT | (kb == 0 ? F_FIRST : 0),
                  (kb == 3 && i != 5) ? bar : 0);
       if (i == 5) {  // skip connection: input = [h4 | enc]  (models/pano_mip_nerf.py:99-100)
-        add_step(s, n, off, 5, 0, 0, 256, 256, 64, 256, 256, acc, 0, 4, F_AENC | F_LOADENC, 0);
-        add_step(s, n, off, 5, 0, 0, 320, 256, 32, 256, 256, acc, 1, 2, F_AENC | F_RELENC, bar);
+        add_step(s, n, 5, 0, 0, 256, 256, 64, 256, 1, 256, acc, 0, 4, F_AENC | F_LOADENC, 0);
+        add_step(s, n, 5, 0, 0, 320, 256, 32, 256, 1, 256, acc, 1, 2, F_AENC | F_RELENC, bar);
       }
     }
-    epi(E_RELU, bar - 1, acc, i * 256, i, i);
+    add_epi(s, ne, E_RELU, bar - 1, acc, i * 256, i, i);
   }
-  // ---- heads: extra (-> X) and density (-> Y[0:16]) both read h7; one commit covers both -------------------------
+  // ---- heads: extra (-> X) and density (-> Y[0:16], one step over all 4 k-blocks) both read h7; one commit -------
   for (int kb = 0; kb < 4; ++kb)
-    add_step(s, n, off, P_EXTRA, 0, 0, kb * 64, 256, 64, 256, 256, kAccX, kb, 4, F_WAIT | (kb == 0 ? F_FIRST : 0), 0);
-  for (int kb = 0; kb < 4; ++kb)
-    add_step(s, n, off, P_DEN, 0, 0, kb * 64, 16, 64, 16, 16, kAccY, kb, 4, (kb == 0 ? F_FIRST : 0), kb == 3 ? 1 : 0);
-  epi(E_HEADS, 0, kAccX, kBiasHE, -1, 8);
+    add_step(s, n, P_EXTRA, 0, 0, kb * 64, 256, 64, 256, 1, 256, kAccX, kb, 4, F_WAIT | (kb == 0 ? F_FIRST : 0), 0);
+  add_step(s, n, P_DEN, 0, 0, 0, 16, 64, 16, 4, 16, kAccY, 0, 16, F_FIRST, 1);
+  add_epi(s, ne, E_HEADS, 0, kAccX, kBiasHE, -1, 8);
   for (int kb = 0; kb < 4; ++kb)  // view layer, bottleneck columns (the view-direction columns are the row bias)
-    add_step(s, n, off, P_VIEW, 0, 0, kb * 64, 128, 64, 128, 128, kAccY + 128, kb, 4, F_WAIT | (kb == 0 ? F_FIRST : 0),
+    add_step(s, n, P_VIEW, 0, 0, kb * 64, 128, 64, 128, 1, 128, kAccY + 128, kb, 4, F_WAIT | (kb == 0 ? F_FIRST : 0),
              kb == 3 ? 2 : 0);
-  epi(E_VIEW, 1, kAccY + 128, 0, -1, 9);
-  for (int kb = 0; kb < 2; ++kb)
-    add_step(s, n, off, P_COL, 0, 0, kb * 64, 16, 64, 16, 16, kAccY, kb, 4, F_WAIT | (kb == 0 ? F_FIRST : 0),
-             kb == 1 ? 2 : 0);
-  epi(E_COLOR, 1, kAccY, kBiasC, 7, 17);
-  const int n_fwd = n, ne_fwd = ne;
+  add_epi(s, ne, E_VIEW, 1, kAccY + 128, 0, -1, 9);
+  add_step(s, n, P_COL, 0, 0, 0, 16, 64, 16, 2, 16, kAccY, 0, 8, F_WAIT | F_FIRST, 2);
+  add_epi(s, ne, E_COLOR, 1, kAccY, kBiasC, 7, 17);
+  s.n_fwd = n, s.ne_fwd = ne;
   // ---- density-Jacobian sweep: J_i computes a_{i-1} = relu'(h_{i-1}) * (a_i W_i) with the transposed tiles -------
   for (int i = 7; i >= 1; --i) {
     const int acc = (i & 1) ? kAccX : kAccY, bar = (i & 1) ? 1 : 2;
     for (int kb = 0; kb < 4; ++kb)
-      add_step(s, n, off, i, 1, kb * 64, 0, 256, 64, 256, 256, acc, kb, 4, F_WAIT | (kb == 0 ? F_FIRST : 0),
+      add_step(s, n, i, 1, kb * 64, 0, 256, 64, 256, 1, 256, acc, kb, 4, F_WAIT | (kb == 0 ? F_FIRST : 0),
                (kb == 3 && i != 5) ? bar : 0);
     if (i == 5) {  // skip connection: d sigma / d enc += a_5 W_5[:, 256:352]   (-> Y[0:96], J5 itself is in X)
-      for (int kb = 0; kb < 4; ++kb)
-        add_step(s, n, off, 5, 1, kb * 64, 256, 96, 64, 96, 96, kAccY, kb, 4, (kb == 0 ? F_FIRST : 0), kb == 3 ? bar : 0);
-      epi(E_JAC5, bar - 1, acc, 0, i - 1, 10 + i - 1);
+      add_step(s, n, 5, 1, 0, 256, 96, 64, 96, 2, 96, kAccY, 0, 8, F_FIRST, 0);
+      add_step(s, n, 5, 1, 128, 256, 96, 64, 96, 2, 96, kAccY, 2, 8, 0, bar);
+      add_epi(s, ne, E_JAC5, bar - 1, acc, 0, i - 1, 10 + i - 1);
     } else {
-      epi(E_JAC, bar - 1, acc, 0, i - 1, 10 + i - 1);
+      add_epi(s, ne, E_JAC, bar - 1, acc, 0, i - 1, 10 + i - 1);
     }
   }
-  for (int kb = 0; kb < 4; ++kb)  // d sigma / d enc += a_0 W_0
-    add_step(s, n, off, 0, 1, kb * 64, 0, 96, 64, 96, 96, kAccY, kb, 4, F_WAIT | (kb == 0 ? F_FIRST : 0), kb == 3 ? 2 : 0);
-  epi(E_G0, 1, kAccY, 0, -1, -1);
-  s.tab[1].n_steps = n, s.tab[1].n_epi = ne;
-  s.tab[0] = s.tab[1];
-  s.tab[0].n_steps = n_fwd, s.tab[0].n_epi = ne_fwd;
-  s.n_pack = n;
-  s.blob_bytes = off;
-  built = true;
+  // d sigma / d enc += a_0 W_0
+  add_step(s, n, 0, 1, 0, 0, 96, 64, 96, 2, 96, kAccY, 0, 8, F_WAIT | F_FIRST, 0);
+  add_step(s, n, 0, 1, 128, 0, 96, 64, 96, 2, 96, kAccY, 2, 8, F_WAIT, 2);
+  add_epi(s, ne, E_G0, 1, kAccY, 0, -1, -1);
+  s.n_all = n, s.ne_all = ne;
   return s;
 }
+constexpr Sched kSched = make_sched();
+static_assert(kSched.n_all <= kMaxSteps && kSched.n_pack <= kMaxPack && kSched.ne_all <= kMaxEpi, "schedule tables");
+
+// The producer and the epilogue warps walk the same schedule at run time from constant memory.
+__constant__ Sched c_sched = kSched;
 
 // ---------------------------------------------------------------------------------------------------------------
 // weight packing: fp32 parameters -> bf16 tiles in the 128B-swizzled K-major image tcgen05 reads from shared memory
@@ -283,7 +290,7 @@ struct EpiCtx {
   uint32_t* masks;      // [layer][unit][row]
   FBarriers* bars;
   const CUtensorMap* tmActs;
-  int q, hf, lane, row, save, tile_row0;
+  int q, hf, lane, row, save, tile_row0, skip;
 };
 
 // Rewrite this warp's part of the activation buffer (the next op's A operand) from accumulator `tacc`.
@@ -296,6 +303,12 @@ __device__ __forceinline__ void rewrite_abuf(const EpiCtx& c, uint32_t tacc, int
                                              const float* rowbias, int mask_idx, int save_idx) {
   uint32_t r[2][32];
   const int n_mine = nunits >> 1;  // units handled by this warp: hf, hf+2, ...
+  if (c.skip) {  // timing experiment: the epilogue costs nothing
+    tc_fence_before();
+    if (c.lane == 0)
+      for (int i = 0; i < n_mine; ++i) mbar_arrive(&c.bars->a_ready[c.hf + 2 * i]);
+    return;
+  }
   if (MODE != M_SEED) tmem_ld32u(tacc + c.hf * 32, r[0]);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -374,12 +387,64 @@ __device__ __forceinline__ void rewrite_abuf(const EpiCtx& c, uint32_t tacc, int
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// MMA program
+// ---------------------------------------------------------------------------------------------------------------
+struct MmaCtx {
+  FBarriers* bars;
+  int slot, enc_slot, ns;
+  uint32_t ph, unit_ph;
+  uint32_t abuf16, ring16, tmem_base;
+};
+
+template <int S>
+__device__ __forceinline__ void mma_step(MmaCtx& c) {
+  constexpr Step st = kSched.steps[S];
+  if constexpr ((st.flags & F_LOADENC) != 0) {
+    mbar_wait(&c.bars->full[c.slot], c.ph);
+    c.enc_slot = c.slot;
+    if (++c.slot == c.ns) c.slot = 0, c.ph ^= 1;
+  }
+  mbar_wait(&c.bars->full[c.slot], c.ph);
+  const uint32_t a16 =
+      (((st.flags & F_AENC) != 0) ? c.ring16 + (uint32_t)c.enc_slot * (kSlotBytes >> 4) : c.abuf16) + st.a_off16;
+  const uint32_t b16 = c.ring16 + (uint32_t)c.slot * (kSlotBytes >> 4);
+  const uint32_t d_tmem = c.tmem_base + st.acc_col;
+  if constexpr ((st.flags & F_WAIT) == 0) tc_fence_after();
+#pragma unroll
+  for (int k = 0; k < (int)st.nk16; ++k) {
+    if constexpr ((st.flags & F_WAIT) != 0) {
+      if ((k & 1) == 0) {
+        const int u = (int)st.u0 + (k >> 1);
+        mbar_wait(&c.bars->a_ready[u], (c.unit_ph >> u) & 1u);
+        c.unit_ph ^= 1u << u;
+        tc_fence_after();
+      }
+    }
+    const uint32_t ak = (uint32_t)((k >> 2) * (kKbBytes >> 4) + (k & 3) * 2);
+    const uint32_t bk = (uint32_t)(k >> 2) * st.b_kb16 + (uint32_t)(k & 3) * 2;
+    umma_f16(d_tmem, desc_from16(a16 + ak), desc_from16(b16 + bk), st.idesc,
+             (k == 0 && (st.flags & F_FIRST) != 0) ? 0u : 1u);
+  }
+  umma_commit(&c.bars->empty[c.slot]);
+  if constexpr ((st.flags & F_RELENC) != 0) umma_commit(&c.bars->empty[c.enc_slot]);
+  if constexpr (st.commit != 0) umma_commit(&c.bars->acc_full[st.commit - 1]);
+  if (++c.slot == c.ns) c.slot = 0, c.ph ^= 1;
+}
+
+template <int... S>
+__device__ __forceinline__ void mma_program(MmaCtx& c, std::integer_sequence<int, S...>) {
+  (mma_step<S>(c), ...);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------------
 template <bool NORMALS>
 __global__ void __launch_bounds__(kFThreads, 1)
 mlp_fused_kernel(const __grid_constant__ CUtensorMap tmEnc, const __grid_constant__ CUtensorMap tmActs,
-                 const __grid_constant__ Tables tab, const FusedParams p) {
+                 const FusedParams p) {
+  constexpr int kSteps = NORMALS ? kSched.n_all : kSched.n_fwd;
+  constexpr int kEpis = NORMALS ? kSched.ne_all : kSched.ne_fwd;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_1024(smem_raw);
   uint8_t* abuf = smem;
@@ -415,10 +480,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmEnc, const __grid_constan
       uint32_t ph = 0;
       for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int row0 = (int)(tile * kTileM);
-        for (int s = 0; s < tab.n_steps; ++s) {
-          const uint32_t blob_off = tab.steps[s].blob_off;
-          const uint32_t bytes = tab.steps[s].bytes;
-          if (tab.steps[s].flags & F_LOADENC) {
+        for (int s = 0; s < kSteps; ++s) {
+          const uint32_t blob_off = c_sched.steps[s].blob_off;
+          const uint32_t bytes = c_sched.steps[s].bytes;
+          if (c_sched.steps[s].flags & F_LOADENC) {
             mbar_wait(&bars->empty[slot], ph ^ 1);
             mbar_expect_tx(&bars->full[slot], 2 * kKbBytes);
             tma_load_2d(ring + (size_t)slot * kSlotBytes, &tmEnc, &bars->full[slot], 0, row0);
@@ -426,8 +491,12 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmEnc, const __grid_constan
             if (++slot == NS) slot = 0, ph ^= 1;
           }
           mbar_wait(&bars->empty[slot], ph ^ 1);
-          mbar_expect_tx(&bars->full[slot], bytes);
-          bulk_load_1d(ring + (size_t)slot * kSlotBytes, p.wblob + blob_off, bytes, &bars->full[slot]);
+          if (p.debug & 1) {  // experiment: no weight traffic (the MMAs read whatever the slot holds)
+            mbar_arrive(&bars->full[slot]);
+          } else {
+            mbar_expect_tx(&bars->full[slot], bytes);
+            bulk_load_1d(ring + (size_t)slot * kSlotBytes, p.wblob + blob_off, bytes, &bars->full[slot]);
+          }
           if (++slot == NS) slot = 0, ph ^= 1;
         }
       }
@@ -435,65 +504,23 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmEnc, const __grid_constan
     __syncwarp();
   } else if (warp == 1) {
     // ================================ MMA issuer ================================================================
-    // The whole warp runs this loop with warp-uniform values (descriptors stay in uniform registers); one elected
-    // lane issues the tcgen05 instructions.
-    int slot = 0, enc_slot = 0;
-    uint32_t ph = 0, unit_ph = 0;
-    const uint32_t abuf16 = smem_u32(abuf) >> 4, ring16 = smem_u32(ring) >> 4;
-    for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      for (int s = 0; s < tab.n_steps; ++s) {
-        const uint32_t flags = tab.steps[s].flags;
-        const uint32_t idesc = tab.steps[s].idesc;
-        const uint32_t d_tmem = tmem_base + tab.steps[s].acc_col;
-        const uint32_t a_off16 = tab.steps[s].a_off16;
-        if (flags & F_LOADENC) {
-          mbar_wait(&bars->full[slot], ph);
-          enc_slot = slot;
-          if (++slot == NS) slot = 0, ph ^= 1;
-        }
-        mbar_wait(&bars->full[slot], ph);
-        const uint32_t a16 = ((flags & F_AENC) ? ring16 + (uint32_t)enc_slot * (kSlotBytes >> 4) : abuf16) + a_off16;
-        const uint32_t b16 = ring16 + (uint32_t)slot * (kSlotBytes >> 4);
-        const int u0 = (int)((flags >> 16) & 7u);
-        if (flags & F_WAIT) {
-          mbar_wait(&bars->a_ready[u0], (unit_ph >> u0) & 1u);
-          unit_ph ^= 1u << u0;
-        }
-        tc_fence_after();
-        if (elect_one()) {
-          umma_f16(d_tmem, desc_from16(a16), desc_from16(b16), idesc, (flags & F_FIRST) ? 0u : 1u);
-          umma_f16(d_tmem, desc_from16(a16 + 2), desc_from16(b16 + 2), idesc, 1u);
-        }
-        __syncwarp();
-        if (((flags >> 8) & 7u) == 4u) {
-          if (flags & F_WAIT) {
-            mbar_wait(&bars->a_ready[u0 + 1], (unit_ph >> (u0 + 1)) & 1u);
-            unit_ph ^= 1u << (u0 + 1);
-            tc_fence_after();
-          }
-          if (elect_one()) {
-            umma_f16(d_tmem, desc_from16(a16 + 4), desc_from16(b16 + 4), idesc, 1u);
-            umma_f16(d_tmem, desc_from16(a16 + 6), desc_from16(b16 + 6), idesc, 1u);
-          }
-          __syncwarp();
-        }
-        if (elect_one()) {
-          umma_commit(&bars->empty[slot]);
-          if (flags & F_RELENC) umma_commit(&bars->empty[enc_slot]);
-          const uint32_t cm = (flags >> 12) & 3u;
-          if (cm) umma_commit(&bars->acc_full[cm - 1]);
-        }
-        __syncwarp();
-        if (++slot == NS) slot = 0, ph ^= 1;
-      }
+    // One thread runs the schedule, fully unrolled at compile time (mma_step<S>): descriptor offsets, instruction
+    // descriptors, accumulate flags and barrier indices are immediates; only the ring position is dynamic.
+    if (lane == 0) {
+      MmaCtx mc;
+      mc.bars = bars, mc.slot = 0, mc.enc_slot = 0, mc.ph = 0, mc.unit_ph = 0, mc.ns = NS;
+      mc.abuf16 = smem_u32(abuf) >> 4, mc.ring16 = smem_u32(ring) >> 4, mc.tmem_base = tmem_base;
+      for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x)
+        mma_program(mc, std::make_integer_sequence<int, kSteps>{});
     }
+    __syncwarp();
   } else {
     // ================================ epilogue warps ============================================================
     EpiCtx c;
     c.abuf = abuf, c.masks = masks, c.bars = bars, c.tmActs = &tmActs;
     c.q = warp & 3;            // TMEM lane quadrant (hardware rule: warp id % 4)
     c.hf = (warp - 2) >> 2;    // which of the two warps of the quadrant: even / odd 32-column units
-    c.lane = lane, c.row = c.q * 32 + lane, c.save = p.save;
+    c.lane = lane, c.row = c.q * 32 + lane, c.save = p.save, c.skip = (p.debug & 2) != 0;
     const uint32_t tlane = tmem_base + ((uint32_t)(c.q * 32) << 16);
     uint32_t acc_ph = 0;
     for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -501,8 +528,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmEnc, const __grid_constan
       const bool row_ok = m < p.M;
       const long long m_safe = row_ok ? m : p.M - 1;
       c.tile_row0 = (int)(tile * kTileM);
-      for (int e = 0; e < tab.n_epi; ++e) {
-        const Epi ep = tab.epis[e];
+      for (int e = 0; e < kEpis; ++e) {
+        const Epi ep = c_sched.epis[e];
         mbar_wait(&bars->acc_full[ep.bar], (acc_ph >> ep.bar) & 1u);
         acc_ph ^= 1u << ep.bar;
         tc_fence_after();
@@ -615,14 +642,14 @@ static bool make_map_acts(CUtensorMap* out, const void* base, unsigned long long
 using namespace pnb;
 using namespace pnb::fused;
 
-extern "C" long long pnb_mlp_fused_wblob_bytes(void) { return (long long)schedule().blob_bytes; }
+extern "C" long long pnb_mlp_fused_wblob_bytes(void) { return (long long)kSched.blob_bytes; }
 extern "C" long long pnb_mlp_fused_bblob_floats(void) { return kBiasFloats; }
-extern "C" int pnb_mlp_fused_act_planes(void) { return 18; }
+extern "C" int pnb_mlp_fused_act_planes(void) { return kActPlanes; }
 
 extern "C" int pnb_mlp_fused_pack(const void* const* params_host, int C, void* wblob, float* bblob, void* stream) {
   PNB_REQUIRE(params_host != nullptr && wblob != nullptr && bblob != nullptr, "mlp_fused_pack: null argument");
   PNB_REQUIRE(C >= 1 && C <= 16, "mlp_fused_pack: need 1 <= C <= 16 density-head channels");
-  const Schedule& s = schedule();
+  const Sched& s = kSched;
   static const int in_features[kNumParams] = {96, 256, 256, 256, 256, 352, 256, 256, 256, 256, 283, 128};
   PackArgs a{};
   for (int i = 0; i < kNumParams; ++i) {
@@ -658,11 +685,11 @@ extern "C" int pnb_mlp_fused_fwd(long long M, int S, int C, const void* enc, int
   PNB_REQUIRE(acts == nullptr || (uintptr_t)acts % 128 == 0, "mlp_fused_fwd: acts must be 128-byte aligned");
   PNB_REQUIRE(M < (1ll << 31) - kTileM, "mlp_fused_fwd: M too large for 32-bit TMA coordinates");
   if (M == 0) return 0;
-  const Schedule& s = schedule();
   const bool normals = g_enc != nullptr;
   FusedParams p{};
   p.M = M, p.num_tiles = (M + kTileM - 1) / kTileM;
   p.S = S, p.C = C, p.save = acts != nullptr;
+  if (const char* dbg = getenv("PNB_FUSED_DEBUG")) p.debug = atoi(dbg);  // timing experiments only (wrong results)
   p.wblob = reinterpret_cast<const uint8_t*>(wblob), p.bblob = bblob, p.row_bias = row_bias;
   p.raw_den = raw_den, p.raw_rgb = raw_rgb, p.g_enc = g_enc;
   const size_t fixed = 1024 + kAbufBytes + (normals ? kMaskBytes : 0) + sizeof(FBarriers);
@@ -674,7 +701,7 @@ extern "C" int pnb_mlp_fused_fwd(long long M, int S, int C, const void* enc, int
   CUtensorMap tmEnc, tmActs;
   if (!make_map_enc(&tmEnc, enc, (unsigned long long)M, (unsigned long long)ld_enc)) return PNB_ERR_ARG;
   if (p.save) {
-    if (!make_map_acts(&tmActs, acts, 18, (unsigned long long)M)) return PNB_ERR_ARG;
+    if (!make_map_acts(&tmActs, acts, kActPlanes, (unsigned long long)M)) return PNB_ERR_ARG;
   } else {
     tmActs = tmEnc;
   }
@@ -683,10 +710,10 @@ extern "C" int pnb_mlp_fused_fwd(long long M, int S, int C, const void* enc, int
   cudaError_t e;
   if (normals) {
     e = cudaFuncSetAttribute(mlp_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    if (e == cudaSuccess) mlp_fused_kernel<true><<<(unsigned)gx, kFThreads, smem_bytes, st>>>(tmEnc, tmActs, s.tab[1], p);
+    if (e == cudaSuccess) mlp_fused_kernel<true><<<(unsigned)gx, kFThreads, smem_bytes, st>>>(tmEnc, tmActs, p);
   } else {
     e = cudaFuncSetAttribute(mlp_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    if (e == cudaSuccess) mlp_fused_kernel<false><<<(unsigned)gx, kFThreads, smem_bytes, st>>>(tmEnc, tmActs, s.tab[0], p);
+    if (e == cudaSuccess) mlp_fused_kernel<false><<<(unsigned)gx, kFThreads, smem_bytes, st>>>(tmEnc, tmActs, p);
   }
   if (e != cudaSuccess) {
     set_error("mlp_fused_fwd(smem attr)", e);
