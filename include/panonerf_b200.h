@@ -195,15 +195,33 @@ int pnb_wgrad_tc(long long M, int Nw, int Kw, const void* dZ, int ldz, const voi
 long long pnb_mlp_fused_wblob_bytes(void);
 long long pnb_mlp_fused_bblob_floats(void);
 int pnb_mlp_fused_act_planes(void);
+int pnb_mlp_fused_bwd_planes(void);
+int pnb_mlp_fused_adj_planes(void);
+/* 32-bit words of the ReLU sign bit-plane buffer: per_tile = 1 -> one record per 128-sample tile of an M-sample
+ * batch (what the backward kernels read), per_tile = 0 -> a per-CTA scratch (inference with normals). */
+long long pnb_mlp_fused_mask_words(long long M, int per_tile);
 int pnb_mlp_fused_pack(const void* const* params_host, int C, void* wblob, float* bblob, void* stream);
 /* enc: bf16 [M,96] IPE features (row stride ld_enc); row_bias: fp32 [ceil(M/S),128] per-ray view-direction term
  * (incl. the view-layer bias); outputs raw_den fp32 [M,C], raw_rgb fp32 [M,3].
  * acts (nullable): bf16 [18][M][256] planes written with TMA stores for the backward pass:
  *   0..7 trunk activations h_i, 8 bottleneck, 9 view-layer activation (cols 0..127), 10..17 Jacobian rows a_0..a_7.
  * g_enc (nullable): fp32 [M,96]; when given, the density-Jacobian sweep (pano_mip_nerf.py:295-302 without
- * vmap/jacrev) runs in the same kernel and g_enc receives d raw_sigma / d enc. */
+ * vmap/jacrev) runs in the same kernel and g_enc receives d raw_sigma / d enc.
+ * masks: uint32 [pnb_mlp_fused_mask_words(M, masks_per_tile)] sign bits of the 9 ReLU layers; required with g_enc,
+ * required per tile when the backward kernels will run, nullable otherwise. */
 int pnb_mlp_fused_fwd(long long M, int S, int C, const void* enc, int ld_enc, const void* wblob, const float* bblob,
-                      const float* row_bias, float* raw_den, float* raw_rgb, void* acts, float* g_enc, void* stream);
+                      const float* row_bias, float* raw_den, float* raw_rgb, void* acts, float* g_enc, void* masks,
+                      int masks_per_tile, void* stream);
+/* Data-gradient chain of the backward pass (the autograd of pano_mip_nerf.py:78-114 w.r.t. activations):
+ * d_rgb fp32 [M,3], d_den fp32 [M,C], masks from the forward (per tile) ->
+ * dz_planes bf16 [10][M][256]: 0 dz_view (cols 0..127), 1 d_bottleneck, 2..9 dz_7..dz_0 (pre-activation gradients),
+ * d_enc (nullable) fp32 [M,96] gradient w.r.t. the IPE features. */
+int pnb_mlp_fused_bwd(long long M, int C, const void* wblob, const float* bblob, const float* d_rgb,
+                      const float* d_den, const void* masks, void* dz_planes, float* d_enc, void* stream);
+/* Adjoint of the density-Jacobian sweep (second-order terms of the normals): u bf16 [M,96] = J_ipe d_v ->
+ * q_planes bf16 [8][M][256], q_i = relu'(h_i) * (q_{i-1} W_i^T) (q_5 also takes u through the skip connection). */
+int pnb_mlp_fused_jadj(long long M, const void* u, int ld_u, const void* wblob, const void* masks, void* q_planes,
+                       void* stream);
 /* out[g, n] = sum of the `group` consecutive rows of x belonging to group g (fp32 out [M/group, N]) */
 int pnb_group_sum(long long M, int N, int group, const void* x, int ldx, int dtype, float* out, void* stream);
 /* 1 when the tcgen05 path was compiled in and the device is sm_100 */

@@ -1,26 +1,32 @@
 // K3-fused: the radiance/density MLP of models/pano_mip_nerf.py:78-114 (8x256 trunk with the skip connection,
-// density / extra / view / colour heads) evaluated for a 128-sample tile in ONE persistent kernel, optionally
-// followed - still on chip - by the density-Jacobian sweep that replaces vmap(jacrev) (pano_mip_nerf.py:295-302).
+// density / extra / view / colour heads), the density-Jacobian sweep that replaces vmap(jacrev)
+// (pano_mip_nerf.py:295-302), the data-gradient chain of its backward pass and the adjoint (forward-mode) sweep of the
+// Jacobian - each as ONE persistent kernel in which activations never leave the SM.
 //
 // Why: layer-by-layer GEMMs (gemm_tc.cu) stream every [M,256] activation through HBM and are bound by it at
-// ~0.3 of the tensor roofline.  Here activations never leave the SM:
+// ~0.3 of the tensor roofline.  Here a CTA owns TWO 128-sample tiles at a time and ping-pongs between them:
 //
 //   warp 0      producer : streams the pre-swizzled bf16 weight tiles (cp.async.bulk, L2 -> SMEM ring of 32 KB slots)
-//                          and the two IPE k-blocks of the tile (TMA tensor load) in exactly the order the MMA warp
+//                          and the IPE k-blocks of each tile (TMA tensor load) in exactly the order the MMA warp
 //                          consumes them;
 //   warp 1      MMA      : one thread issues tcgen05.mma (M=128, N<=256, K=16, bf16 -> fp32 TMEM).  A comes from the
-//                          activation buffer in SMEM (128B-swizzled K-major, 4 k-blocks of 64 columns), B from the
-//                          ring.  Two 256-column TMEM accumulators (X, Y) alternate between consecutive layers;
-//   warps 2..9  epilogue : tcgen05.ld -> bias / ReLU / ReLU-mask -> bf16 -> written IN PLACE into the activation
-//                          buffer as the next layer's A operand, 32 columns ("unit") at a time.  Each unit has its own
-//                          mbarrier, so the next layer's MMAs start as soon as the first 32 columns exist and the
-//                          tensor pipe idles only for that first-unit latency per layer.
+//                          tile's activation buffer in SMEM (128B-swizzled K-major, 4 k-blocks of 64 columns), B from
+//                          the ring, D is the tile's own 256-column TMEM accumulator.  The program alternates
+//                          tile 0 / tile 1 op by op, so while the epilogue warps rewrite one tile's activations the
+//                          tensor pipe is busy with the other tile;
+//   warps 2..9  epilogue : tcgen05.ld -> bias / ReLU / mask -> bf16 -> written IN PLACE into the tile's activation
+//                          buffer as the next op's A operand; one mbarrier hand-shake per (op, tile) in each direction.
 //
-// ReLU sign bits of all 8 trunk layers stay in shared memory (4 KB per layer) so the Jacobian sweep
-// a_{i-1} = relu'(h_{i-1}) * (a_i W_i) can run right after the heads with the transposed weight tiles; the two
-// contributions to d sigma / d enc (through layer 0 and through the skip connection) are accumulated in fp32.
-// With `acts` given, every activation (and Jacobian row) is also written out with TMA stores straight from the
-// activation buffer - that is what the training backward consumes.
+// ReLU sign bits go to a small global (L2-resident) bit-plane buffer: the Jacobian sweep
+// a_{i-1} = relu'(h_{i-1}) * (a_i W_i) reads them back in the same kernel, the backward kernels read them instead of
+// the activations.  With `acts` given, every activation is also written out with TMA stores straight from the
+// activation buffer - that is what the weight-gradient GEMMs consume.
+//
+// Programs (compile-time schedules, one kernel instantiation each):
+//   P_FWD   trunk + heads
+//   P_FWDJ  trunk + heads + density-Jacobian sweep (d sigma / d enc)
+//   P_BWD   d(raw_rgb), d(raw_sigma...) -> dz of every layer (and d enc), the dgrad chain of the backward pass
+//   P_JADJ  u = J_ipe d_v -> q_i = relu'(h_i) * (q_{i-1} W_i^T): adjoint of the Jacobian sweep (second-order terms)
 #include <utility>
 
 #include "tc_common.cuh"
@@ -34,48 +40,67 @@ constexpr int kWidth = 256, kEncDim = 96, kCondW = 128;
 constexpr int kSlotBytes = 32768;  // ring slot: a weight tile of up to 256 rows x 64 bf16, or the two IPE k-blocks
 constexpr int kKbBytes = 16384;    // one k-block: 128 rows x 64 bf16, 128B-swizzled
 constexpr int kAbufBytes = 4 * kKbBytes;
-constexpr int kMaskBytes = 8 * 8 * kTileM * 4;  // [layer][unit][row] u32
 constexpr int kFThreads = 320;
-constexpr int kAccX = 0, kAccY = 256;
-constexpr int kMaxSteps = 80, kMaxPack = 88, kMaxEpi = 20, kFMaxStages = 6;
+constexpr int kMaxSteps = 80, kMaxOps = 24, kMaxPack = 160, kFMaxStages = 3;
 constexpr int kNumParams = 12;  // weights (and biases) in state-dict order: layers 0..7, density, extra, view, colour
-constexpr int kActPlanes = 18;
+constexpr int kActPlanes = 18, kBwdPlanes = 10, kAdjPlanes = 8;
+constexpr int kMaskPlanes = 9;  // ReLU sign bits: trunk layers 0..7, view layer
+constexpr int kMaskWordsPerTile = kMaskPlanes * 8 * kTileM;
+// Every CTA streams the same weight tiles in the same order; with a single copy all 148 SMs hammer the same few L2
+// slices at the same time.  The packer therefore writes kReplicas copies of the blob at different addresses and
+// CTA b reads copy b % replicas.
+constexpr int kReplicas = 1;
 
 // bias blob (fp32) layout
-constexpr int kBiasHE = 2048, kBiasHD = 2304, kBiasC = 2320, kWSigma = 2336, kBiasFloats = 2592;
+constexpr int kBiasHE = 2048, kBiasHD = 2304, kBiasC = 2320, kWDen = 2336, kWCol = kWDen + 16 * 256,
+              kBiasFloats = kWCol + 4 * 128;
 
-enum : uint32_t { F_AENC = 1, F_LOADENC = 2, F_RELENC = 4, F_FIRST = 8, F_WAIT = 16 };
+enum : uint32_t { F_AENC = 1, F_LOADENC = 2, F_RELENC = 4, F_FIRST = 8 };
+enum { P_FWD = 0, P_FWDJ = 1, P_BWD = 2, P_JADJ = 3, kNumProgs = 4 };
 
-// One step = one ring slot = one weight tile of `nk16` K=16 MMAs (a multiple of 2; 4 per 64-column k-block).
+// One step = one ring slot = one weight tile of `nk16` K=16 MMAs.
 struct Step {
   uint32_t blob_off;   // byte offset of the tile in the weight blob
   uint32_t bytes;      // tile bytes
   uint32_t idesc;      // tcgen05 instruction descriptor (M=128, N of this op, bf16 -> fp32)
-  uint32_t acc_col;    // TMEM column of the accumulator
+  uint32_t acc_col;    // accumulator column inside the tile's 256-column TMEM region
   uint32_t a_off16;    // A operand: byte offset >> 4 from the activation buffer (or from the IPE slot with F_AENC)
   uint32_t b_kb16;     // byte stride >> 4 between the k-blocks of the weight tile inside the slot
   uint32_t flags;      // F_*
   uint32_t nk16;       // K=16 MMAs in this step
-  uint32_t commit;     // 0 none, 1 -> acc_full[0], 2 -> acc_full[1] after this step
-  uint32_t u0;         // first 32-column unit of A this step reads (F_WAIT: wait a_ready[u0 + k/2] before MMA k)
 };
 struct PackTile {      // one rows x 64 sub-tile: tile(r,c) = W[r0+r, c0+c] (or W[r0+c, c0+r] when transposed)
   uint32_t blob_off;
   int16_t param, transposed, r0, c0, vr, vc, rows, pad;
 };
-enum : uint8_t { E_RELU = 0, E_HEADS, E_VIEW, E_COLOR, E_JAC, E_JAC5, E_G0 };
-struct Epi {
-  uint8_t type, bar;
-  uint16_t acc_col;
-  uint16_t bias_off;
-  int8_t mask_idx, save_idx;
+enum : uint8_t {
+  E_RELU = 0,  // acc + bias -> ReLU (sign bits -> mask plane) -> abuf
+  E_DEN,       // acc[0:16] + bias -> raw_den
+  E_EXTRA,     // acc + bias -> abuf
+  E_VIEW,      // acc + per-ray view-direction term -> ReLU -> abuf[0:128]
+  E_COLOR,     // acc[128:144] + bias -> raw_rgb ; P_FWDJ: seed of the Jacobian sweep -> abuf
+  E_MASK,      // acc * mask plane -> abuf
+  E_GSKIP,     // acc[0:96] -> g_enc
+  E_G0,        // acc[0:96] + g_enc -> g_enc
+  E_BSEED,     // no MMA: relu'(hv) * (d_rgb W_col) -> abuf[0:128]
+  E_LIN,       // acc -> abuf
+  E_BDZ7       // (acc + d_den W_den) * mask plane 7 -> abuf
+};
+struct Op {
+  int16_t s0, s1;      // steps [s0, s1)
+  uint8_t epi, has_mma;
+  int16_t acc_col;     // accumulator column the epilogue reads
+  int16_t bias_off;
+  int8_t mask_plane, save_plane, nunits, pad;
+};
+struct Prog {
+  Step steps[kMaxSteps];
+  Op ops[kMaxOps];
+  int n_steps, n_ops;
 };
 struct Sched {
-  Step steps[kMaxSteps];
-  Epi epis[kMaxEpi];
+  Prog prog[kNumProgs];
   PackTile pack[kMaxPack];
-  int n_fwd, n_all;    // steps of the forward-only / forward + Jacobian-sweep programs
-  int ne_fwd, ne_all;  // epilogue ops
   int n_pack;
   uint32_t blob_bytes;
 };
@@ -84,129 +109,205 @@ struct PackArgs {
   const float* b[kNumParams];
   int ld[kNumParams];
   int C, n_tiles;
-  PackTile tiles[kMaxPack];
 };
 
 struct FusedParams {
-  long long M, num_tiles;
-  int S, C, nstages, save, debug;
+  long long M, num_tiles, num_pairs;
+  int S, C, nstages, save, debug, masks_per_tile, replicas;
+  long long blob_stride;
   const uint8_t* wblob;
   const float* bblob;
   const float* row_bias;
   float* raw_den;
   float* raw_rgb;
-  float* g_enc;
+  float* g_enc;          // P_FWDJ: d sigma / d enc out ; P_BWD: d L / d enc out (nullable)
+  uint32_t* masks;       // ReLU sign bit-planes (nullable in P_FWD without `save`)
+  const float* d_rgb;    // P_BWD inputs
+  const float* d_den;
+  unsigned long long* prof;  // timing experiments: [grid][8] cycle counters (nullable)
 };
 
 struct FBarriers {
   uint64_t full[kFMaxStages];
   uint64_t empty[kFMaxStages];
-  uint64_t a_ready[8];
+  uint64_t abuf_ready[2];
   uint64_t acc_full[2];
   uint32_t tmem_base;
 };
 
 // ---------------------------------------------------------------------------------------------------------------
-// schedule: the order of weight tiles == the order of MMA steps == the order of the producer's loads.
+// schedules: the order of weight tiles == the order of MMA steps == the order of the producer's loads.
 // Built at compile time: the MMA warp's program is fully unrolled from it (every descriptor offset, flag and
-// barrier index is an immediate), the producer and epilogue warps read the same table from kernel parameters.
+// barrier index is an immediate), the producer and epilogue warps read the same tables from constant memory.
+// Identical weight tiles are shared between the programs (one blob).
 // ---------------------------------------------------------------------------------------------------------------
-constexpr void add_step(Sched& s, int& n, int param, int transposed, int r0, int c0, int vr, int vc, int rows,
-                        int nkb, int n_mma, int acc_col, int a_kb, int nk16, uint32_t flags, int commit) {
-  Step st{};
-  st.blob_off = s.blob_bytes;
-  st.bytes = (uint32_t)(rows * 128 * nkb);
-  st.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_mma >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-  st.acc_col = (uint32_t)acc_col;
-  st.a_off16 = (uint32_t)(a_kb * kKbBytes) >> 4;
-  st.b_kb16 = (uint32_t)(rows * 128) >> 4;
-  st.flags = flags;
-  st.nk16 = (uint32_t)nk16;
-  st.commit = (uint32_t)commit;
-  st.u0 = (uint32_t)(2 * a_kb);
-  s.steps[n++] = st;
-  for (int kb = 0; kb < nkb; ++kb) {  // consecutive 64-column k-blocks of the same rows
-    PackTile pt{};
-    pt.blob_off = s.blob_bytes;
-    pt.param = (int16_t)param, pt.transposed = (int16_t)transposed;
-    pt.r0 = (int16_t)(transposed ? r0 + 64 * kb : r0), pt.c0 = (int16_t)(transposed ? c0 : c0 + 64 * kb);
-    pt.vr = (int16_t)vr, pt.vc = (int16_t)vc, pt.rows = (int16_t)rows;
-    s.pack[s.n_pack++] = pt;
-    s.blob_bytes += (uint32_t)rows * 128u;
-  }
-}
-constexpr void add_epi(Sched& s, int& ne, int type, int bar, int acc_col, int bias_off, int mask_idx, int save_idx) {
-  Epi e{};
-  e.type = (uint8_t)type, e.bar = (uint8_t)bar, e.acc_col = (uint16_t)acc_col, e.bias_off = (uint16_t)bias_off;
-  e.mask_idx = (int8_t)mask_idx, e.save_idx = (int8_t)save_idx;
-  s.epis[ne++] = e;
-}
-
-constexpr Sched make_sched() {
+struct Builder {
   Sched s{};
-  int n = 0, ne = 0;
-  const int P_DEN = 8, P_EXTRA = 9, P_VIEW = 10, P_COL = 11;
-  // ---- trunk -----------------------------------------------------------------------------------------------
-  for (int i = 0; i < 8; ++i) {
-    const int acc = (i & 1) ? kAccY : kAccX, bar = (i & 1) ? 2 : 1;
+  // per-step tile identity for de-duplication
+  int key[kMaxPack][8] = {};
+  uint32_t key_off[kMaxPack] = {};
+  int n_keys = 0;
+
+  constexpr uint32_t tile(int param, int transposed, int r0, int c0, int vr, int vc, int rows, int nkb) {
+    for (int i = 0; i < n_keys; ++i)
+      if (key[i][0] == param && key[i][1] == transposed && key[i][2] == r0 && key[i][3] == c0 && key[i][4] == vr &&
+          key[i][5] == vc && key[i][6] == rows && key[i][7] == nkb)
+        return key_off[i];
+    const uint32_t off = s.blob_bytes;
+    key[n_keys][0] = param, key[n_keys][1] = transposed, key[n_keys][2] = r0, key[n_keys][3] = c0;
+    key[n_keys][4] = vr, key[n_keys][5] = vc, key[n_keys][6] = rows, key[n_keys][7] = nkb;
+    key_off[n_keys++] = off;
+    for (int kb = 0; kb < nkb; ++kb) {  // consecutive 64-column k-blocks of the same rows
+      PackTile pt{};
+      pt.blob_off = s.blob_bytes;
+      pt.param = (int16_t)param, pt.transposed = (int16_t)transposed;
+      pt.r0 = (int16_t)(transposed ? r0 + 64 * kb : r0), pt.c0 = (int16_t)(transposed ? c0 : c0 + 64 * kb);
+      pt.vr = (int16_t)vr, pt.vc = (int16_t)vc, pt.rows = (int16_t)rows;
+      s.pack[s.n_pack++] = pt;
+      s.blob_bytes += (uint32_t)rows * 128u;
+    }
+    return off;
+  }
+  constexpr void step(int P, int param, int transposed, int r0, int c0, int vr, int vc, int rows, int nkb, int n_mma,
+                      int acc_col, int a_kb, int nk16, uint32_t flags) {
+    Prog& g = s.prog[P];
+    Step st{};
+    st.blob_off = tile(param, transposed, r0, c0, vr, vc, rows, nkb);
+    st.bytes = (uint32_t)(rows * 128 * nkb);
+    st.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_mma >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    st.acc_col = (uint32_t)acc_col;
+    st.a_off16 = (uint32_t)(a_kb * kKbBytes) >> 4;
+    st.b_kb16 = (uint32_t)(rows * 128) >> 4;
+    st.flags = flags;
+    st.nk16 = (uint32_t)nk16;
+    g.steps[g.n_steps++] = st;
+  }
+  constexpr void op(int P, int s0, int epi, int acc_col, int bias_off, int mask_plane, int save_plane, int nunits) {
+    Prog& g = s.prog[P];
+    Op o{};
+    o.s0 = (int16_t)s0, o.s1 = (int16_t)g.n_steps;
+    o.epi = (uint8_t)epi, o.has_mma = (uint8_t)(g.n_steps > s0 ? 1 : 0);
+    o.acc_col = (int16_t)acc_col, o.bias_off = (int16_t)bias_off;
+    o.mask_plane = (int8_t)mask_plane, o.save_plane = (int8_t)save_plane, o.nunits = (int8_t)nunits;
+    g.ops[g.n_ops++] = o;
+  }
+  // trunk layer i, forward direction (weights W_i[256, K]); `epi` = E_RELU (forward) or E_MASK (adjoint sweep)
+  constexpr void trunk_layer(int P, int i, int epi, int save_plane) {
+    const int s0 = s.prog[P].n_steps;
     if (i == 0) {
-      add_step(s, n, 0, 0, 0, 0, 256, 64, 256, 1, 256, acc, 0, 4, F_AENC | F_LOADENC | F_FIRST, 0);
-      add_step(s, n, 0, 0, 0, 64, 256, 32, 256, 1, 256, acc, 1, 2, F_AENC | F_RELENC, bar);
+      step(P, 0, 0, 0, 0, 256, 64, 256, 1, 256, 0, 0, 4, F_AENC | F_LOADENC | F_FIRST);
+      step(P, 0, 0, 0, 64, 256, 32, 256, 1, 256, 0, 1, 2, F_AENC | F_RELENC);
     } else {
-      for (int kb = 0; kb < 4; ++kb)
-        add_step(s, n, i, 0, 0, kb * 64, 256, 64, 256, 1, 256, acc, kb, 4, F_WAIT | (kb == 0 ? F_FIRST : 0),
-                 (kb == 3 && i != 5) ? bar : 0);
+      for (int kb = 0; kb < 4; ++kb) step(P, i, 0, 0, kb * 64, 256, 64, 256, 1, 256, 0, kb, 4, kb == 0 ? F_FIRST : 0);
       if (i == 5) {  // skip connection: input = [h4 | enc]  (models/pano_mip_nerf.py:99-100)
-        add_step(s, n, 5, 0, 0, 256, 256, 64, 256, 1, 256, acc, 0, 4, F_AENC | F_LOADENC, 0);
-        add_step(s, n, 5, 0, 0, 320, 256, 32, 256, 1, 256, acc, 1, 2, F_AENC | F_RELENC, bar);
+        step(P, 5, 0, 0, 256, 256, 64, 256, 1, 256, 0, 0, 4, F_AENC | F_LOADENC);
+        step(P, 5, 0, 0, 320, 256, 32, 256, 1, 256, 0, 1, 2, F_AENC | F_RELENC);
       }
     }
-    add_epi(s, ne, E_RELU, bar - 1, acc, i * 256, i, i);
+    op(P, s0, epi, 0, i * 256, i, save_plane, 8);
   }
-  // ---- heads: extra (-> X) and density (-> Y[0:16], one step over all 4 k-blocks) both read h7; one commit -------
-  for (int kb = 0; kb < 4; ++kb)
-    add_step(s, n, P_EXTRA, 0, 0, kb * 64, 256, 64, 256, 1, 256, kAccX, kb, 4, F_WAIT | (kb == 0 ? F_FIRST : 0), 0);
-  add_step(s, n, P_DEN, 0, 0, 0, 16, 64, 16, 4, 16, kAccY, 0, 16, F_FIRST, 1);
-  add_epi(s, ne, E_HEADS, 0, kAccX, kBiasHE, -1, 8);
-  for (int kb = 0; kb < 4; ++kb)  // view layer, bottleneck columns (the view-direction columns are the row bias)
-    add_step(s, n, P_VIEW, 0, 0, kb * 64, 128, 64, 128, 1, 128, kAccY + 128, kb, 4, F_WAIT | (kb == 0 ? F_FIRST : 0),
-             kb == 3 ? 2 : 0);
-  add_epi(s, ne, E_VIEW, 1, kAccY + 128, 0, -1, 9);
-  add_step(s, n, P_COL, 0, 0, 0, 16, 64, 16, 2, 16, kAccY, 0, 8, F_WAIT | F_FIRST, 2);
-  add_epi(s, ne, E_COLOR, 1, kAccY, kBiasC, 7, 17);
-  s.n_fwd = n, s.ne_fwd = ne;
-  // ---- density-Jacobian sweep: J_i computes a_{i-1} = relu'(h_{i-1}) * (a_i W_i) with the transposed tiles -------
-  for (int i = 7; i >= 1; --i) {
-    const int acc = (i & 1) ? kAccX : kAccY, bar = (i & 1) ? 1 : 2;
-    for (int kb = 0; kb < 4; ++kb)
-      add_step(s, n, i, 1, kb * 64, 0, 256, 64, 256, 1, 256, acc, kb, 4, F_WAIT | (kb == 0 ? F_FIRST : 0),
-               (kb == 3 && i != 5) ? bar : 0);
-    if (i == 5) {  // skip connection: d sigma / d enc += a_5 W_5[:, 256:352]   (-> Y[0:96], J5 itself is in X)
-      add_step(s, n, 5, 1, 0, 256, 96, 64, 96, 2, 96, kAccY, 0, 8, F_FIRST, 0);
-      add_step(s, n, 5, 1, 128, 256, 96, 64, 96, 2, 96, kAccY, 2, 8, 0, bar);
-      add_epi(s, ne, E_JAC5, bar - 1, acc, 0, i - 1, 10 + i - 1);
-    } else {
-      add_epi(s, ne, E_JAC, bar - 1, acc, 0, i - 1, 10 + i - 1);
+  // a_{i-1} = relu'(h_{i-1}) * (a_i W_i) for i = 7..1 with the transposed tiles, then the two contributions to the
+  // gradient w.r.t. the encoding (through the skip connection and through layer 0)
+  constexpr void input_gradient_chain(int P, int save_base) {
+    for (int i = 7; i >= 1; --i) {
+      if (i == 5) {  // skip connection: g_enc = a_5 W_5[:, 256:352]
+        const int s0 = s.prog[P].n_steps;
+        step(P, 5, 1, 0, 256, 96, 64, 96, 2, 96, 0, 0, 8, F_FIRST);
+        step(P, 5, 1, 128, 256, 96, 64, 96, 2, 96, 0, 2, 8, 0);
+        op(P, s0, E_GSKIP, 0, 0, -1, -1, 0);
+      }
+      const int s0 = s.prog[P].n_steps;
+      for (int kb = 0; kb < 4; ++kb) step(P, i, 1, kb * 64, 0, 256, 64, 256, 1, 256, 0, kb, 4, kb == 0 ? F_FIRST : 0);
+      op(P, s0, E_MASK, 0, 0, i - 1, save_base + (i - 1), 8);
     }
+    const int s0 = s.prog[P].n_steps;
+    step(P, 0, 1, 0, 0, 96, 64, 96, 2, 96, 0, 0, 8, F_FIRST);
+    step(P, 0, 1, 128, 0, 96, 64, 96, 2, 96, 0, 2, 8, 0);
+    op(P, s0, E_G0, 0, 0, -1, -1, 0);
   }
-  // d sigma / d enc += a_0 W_0
-  add_step(s, n, 0, 1, 0, 0, 96, 64, 96, 2, 96, kAccY, 0, 8, F_WAIT | F_FIRST, 0);
-  add_step(s, n, 0, 1, 128, 0, 96, 64, 96, 2, 96, kAccY, 2, 8, F_WAIT, 2);
-  add_epi(s, ne, E_G0, 1, kAccY, 0, -1, -1);
-  s.n_all = n, s.ne_all = ne;
-  return s;
+};
+
+constexpr Sched make_sched() {
+  Builder b{};
+  const int W_DEN = 8, W_EXTRA = 9, W_VIEW = 10, W_COL = 11;
+  for (int P = P_FWD; P <= P_FWDJ; ++P) {
+    for (int i = 0; i < 8; ++i) b.trunk_layer(P, i, E_RELU, i);
+    // density head first (its 16 columns are read out before the extra layer overwrites the accumulator)
+    int s0 = b.s.prog[P].n_steps;
+    b.step(P, W_DEN, 0, 0, 0, 16, 64, 16, 4, 16, 0, 0, 16, F_FIRST);
+    b.op(P, s0, E_DEN, 0, kBiasHD, -1, -1, 0);
+    s0 = b.s.prog[P].n_steps;
+    for (int kb = 0; kb < 4; ++kb) b.step(P, W_EXTRA, 0, 0, kb * 64, 256, 64, 256, 1, 256, 0, kb, 4, kb == 0 ? F_FIRST : 0);
+    b.op(P, s0, E_EXTRA, 0, kBiasHE, -1, 8, 8);
+    // view layer, bottleneck columns (the view-direction columns are the per-ray row bias)
+    s0 = b.s.prog[P].n_steps;
+    for (int h = 0; h < 2; ++h) b.step(P, W_VIEW, 0, 0, h * 128, 128, 64, 128, 2, 128, 0, 2 * h, 8, h == 0 ? F_FIRST : 0);
+    b.op(P, s0, E_VIEW, 0, 0, 8, 9, 4);
+    s0 = b.s.prog[P].n_steps;
+    b.step(P, W_COL, 0, 0, 0, 16, 64, 16, 2, 16, 128, 0, 8, F_FIRST);
+    b.op(P, s0, E_COLOR, 128, kBiasC, 7, 17, 8);
+    if (P == P_FWDJ) b.input_gradient_chain(P, 10);
+  }
+  {  // ---- backward: dgrad chain -------------------------------------------------------------------------------
+    const int P = P_BWD;
+    b.op(P, 0, E_BSEED, 0, 0, 8, 0, 4);  // dzv = relu'(hv) * (d_rgb W_col)
+    int s0 = b.s.prog[P].n_steps;        // d_bott = dzv W_view[:, :256]
+    for (int kb = 0; kb < 2; ++kb) b.step(P, W_VIEW, 1, kb * 64, 0, 256, 64, 256, 1, 256, 0, kb, 4, kb == 0 ? F_FIRST : 0);
+    b.op(P, s0, E_LIN, 0, 0, -1, 1, 8);
+    s0 = b.s.prog[P].n_steps;            // dz_7 = relu'(h_7) * (d_bott W_extra + d_den W_den)
+    for (int kb = 0; kb < 4; ++kb) b.step(P, W_EXTRA, 1, kb * 64, 0, 256, 64, 256, 1, 256, 0, kb, 4, kb == 0 ? F_FIRST : 0);
+    b.op(P, s0, E_BDZ7, 0, 0, 7, 2, 8);
+    // dz_{i-1} -> plane 2 + (7 - (i-1)) = 9 - (i-1)
+    for (int i = 7; i >= 1; --i) {
+      if (i == 5) {
+        const int g0 = b.s.prog[P].n_steps;
+        b.step(P, 5, 1, 0, 256, 96, 64, 96, 2, 96, 0, 0, 8, F_FIRST);
+        b.step(P, 5, 1, 128, 256, 96, 64, 96, 2, 96, 0, 2, 8, 0);
+        b.op(P, g0, E_GSKIP, 0, 0, -1, -1, 0);
+      }
+      const int j0 = b.s.prog[P].n_steps;
+      for (int kb = 0; kb < 4; ++kb) b.step(P, i, 1, kb * 64, 0, 256, 64, 256, 1, 256, 0, kb, 4, kb == 0 ? F_FIRST : 0);
+      b.op(P, j0, E_MASK, 0, 0, i - 1, 9 - (i - 1), 8);
+    }
+    const int g0 = b.s.prog[P].n_steps;
+    b.step(P, 0, 1, 0, 0, 96, 64, 96, 2, 96, 0, 0, 8, F_FIRST);
+    b.step(P, 0, 1, 128, 0, 96, 64, 96, 2, 96, 0, 2, 8, 0);
+    b.op(P, g0, E_G0, 0, 0, -1, -1, 0);
+  }
+  for (int i = 0; i < 8; ++i) b.trunk_layer(P_JADJ, i, E_MASK, i);
+  return b.s;
 }
 constexpr Sched kSched = make_sched();
-static_assert(kSched.n_all <= kMaxSteps && kSched.n_pack <= kMaxPack && kSched.ne_all <= kMaxEpi, "schedule tables");
+static_assert(kSched.n_pack <= kMaxPack, "pack table");
+static_assert(kSched.prog[P_FWDJ].n_steps <= kMaxSteps && kSched.prog[P_FWDJ].n_ops <= kMaxOps, "schedule tables");
+static_assert(kSched.prog[P_BWD].n_steps <= kMaxSteps && kSched.prog[P_BWD].n_ops <= kMaxOps, "schedule tables");
+
+// Bias blob staged in the constant bank before every launch (stream-ordered device-to-device copy): the epilogue's
+// per-column addends are uniform across a warp, so they come through the constant cache / uniform datapath instead of
+// exposing a global-load latency in front of every FADD.
+__constant__ float c_bblob[kBiasFloats];
 
 // The producer and the epilogue warps walk the same schedule at run time from constant memory.
-__constant__ Sched c_sched = kSched;
+__constant__ Prog c_prog[kNumProgs] = {kSched.prog[0], kSched.prog[1], kSched.prog[2], kSched.prog[3]};
 
 // ---------------------------------------------------------------------------------------------------------------
 // weight packing: fp32 parameters -> bf16 tiles in the 128B-swizzled K-major image tcgen05 reads from shared memory
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void pack_tiles_kernel(const __grid_constant__ PackArgs a, uint8_t* __restrict__ wblob) {
-  const PackTile t = a.tiles[blockIdx.x];
+struct PackTable {
+  PackTile t[kMaxPack];
+};
+constexpr PackTable make_pack_table() {
+  PackTable pt{};
+  for (int i = 0; i < kSched.n_pack; ++i) pt.t[i] = kSched.pack[i];
+  return pt;
+}
+__constant__ PackTable c_pack = make_pack_table();
+
+__global__ void pack_tiles_kernel(const PackArgs a, uint8_t* __restrict__ wblob, long long blob_stride) {
+  PackTile t = c_pack.t[blockIdx.x];
+  wblob += (size_t)blockIdx.y * blob_stride;
+  if (t.param == 8) t.vr = (int16_t)(t.transposed ? t.vr : a.C);  // density head: C valid rows
+  if (t.param == 11) t.vr = 3;                                   // colour head: 3 valid rows
   const float* W = a.w[t.param];
   const int ld = a.ld[t.param];
   const int chunks = t.rows * 8;  // 16-byte chunks (8 bf16)
@@ -229,14 +330,20 @@ __global__ void pack_tiles_kernel(const __grid_constant__ PackArgs a, uint8_t* _
   }
 }
 
-__global__ void pack_bias_kernel(const __grid_constant__ PackArgs a, float* __restrict__ bblob) {
+__global__ void pack_bias_kernel(const PackArgs a, float* __restrict__ bblob) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kBiasFloats; i += gridDim.x * blockDim.x) {
     float v = 0.f;
     if (i < 2048) v = a.b[i >> 8][i & 255];
     else if (i < kBiasHD) v = a.b[9][i - kBiasHE];
     else if (i < kBiasC) v = (i - kBiasHD < a.C) ? a.b[8][i - kBiasHD] : 0.f;
-    else if (i < kWSigma) v = (i - kBiasC < 3) ? a.b[11][i - kBiasC] : 0.f;
-    else v = a.w[8][i - kWSigma];  // sigma row of the density head: seed of the Jacobian sweep
+    else if (i < kWDen) v = (i - kBiasC < 3) ? a.b[11][i - kBiasC] : 0.f;
+    else if (i < kWCol) {  // density head weights [16][256]; row 0 = sigma row, the seed of the Jacobian sweep
+      const int c = (i - kWDen) >> 8, k = (i - kWDen) & 255;
+      v = c < a.C ? a.w[8][c * 256 + k] : 0.f;
+    } else {               // colour head weights [4][128]
+      const int c = (i - kWCol) >> 7, k = (i - kWCol) & 127;
+      v = c < 3 ? a.w[11][c * 128 + k] : 0.f;
+    }
     bblob[i] = v;
   }
 }
@@ -269,121 +376,182 @@ __device__ __forceinline__ void tmem_ld32u(uint32_t taddr, uint32_t* r) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 // K-major, 128B-swizzled operand descriptor from (shared address >> 4): LBO = 16 B (unused), SBO = 1024 B, version 1
 __device__ __forceinline__ uint64_t desc_from16(uint32_t addr16) {
   constexpr uint32_t kHi = (1024u >> 4) | (1u << 14) | (2u << 29);
   return ((uint64_t)kHi << 32) | (uint64_t)((addr16 & 0x3FFFu) | (1u << 16));
 }
 
-enum { M_RELU = 0, M_LINEAR = 1, M_VIEW = 2, M_JAC = 3, M_SEED = 4 };
-
 struct EpiCtx {
-  uint8_t* abuf;
-  uint32_t* masks;      // [layer][unit][row]
-  FBarriers* bars;
+  uint8_t* abuf;            // this tile's activation buffer
+  uint32_t* mask;           // this tile's sign bit-planes [plane][unit][row] (nullptr: not kept)
+  uint64_t* acc_full;
+  uint64_t* abuf_ready;
   const CUtensorMap* tmActs;
-  int q, hf, lane, row, save, tile_row0, skip;
+  uint32_t tacc;            // TMEM address of this tile's accumulator, lane quadrant applied
+  uint32_t acc_parity;
+  long long m;              // global sample row of this thread
+  int q, hf, lane, row, tile_row0;
+  bool row_ok, save, skip;
 };
 
-// Rewrite this warp's part of the activation buffer (the next op's A operand) from accumulator `tacc`.
-// The two warps of a TMEM lane quadrant interleave the 32-column units (hf = 0: even units, hf = 1: odd units) so
-// that units become available in the order the MMA warp consumes them.  TMEM loads are software-pipelined: the
-// load of the next unit is in flight while the current one is processed.
+enum { M_BIAS_RELU = 0, M_BIAS, M_ROWBIAS_RELU, M_MASK, M_LIN, M_SEED, M_BSEED, M_BDZ7 };
+
+// Rewrite this warp's part of the tile's activation buffer (the next op's A operand) from the accumulator.
+// The two warps of a TMEM lane quadrant split the 32-column units: warp hf handles units [hf*n/2, (hf+1)*n/2), i.e.
+// whole 64-column k-blocks, so each warp can TMA-store its 32-row x 64-column boxes on its own.
 //   unit u covers columns [32u, 32u+32) = k-block u/2, 16-byte chunks (u&1)*4 .. +3 of the 128-byte row.
-template <int MODE, bool NORMALS>
-__device__ __forceinline__ void rewrite_abuf(const EpiCtx& c, uint32_t tacc, int nunits, const float* bias,
-                                             const float* rowbias, int mask_idx, int save_idx) {
-  uint32_t r[2][32];
-  const int n_mine = nunits >> 1;  // units handled by this warp: hf, hf+2, ...
-  if (c.skip) {  // timing experiment: the epilogue costs nothing
-    tc_fence_before();
-    if (c.lane == 0)
-      for (int i = 0; i < n_mine; ++i) mbar_arrive(&c.bars->a_ready[c.hf + 2 * i]);
-    return;
+__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// HF (which of the two warps of the lane quadrant) is a template parameter so that every column offset - and with it
+// every constant-bank address of the bias - is an immediate on top of a warp-uniform base.
+template <int MODE, int HF>
+__device__ __forceinline__ void rewrite_abuf_hf(const EpiCtx& c, const FusedParams& p, const Op& op, const float* aux,
+                                                int coff) {
+  constexpr bool kReadsAcc = MODE != M_SEED && MODE != M_BSEED;
+  constexpr bool kAppliesMask = MODE == M_MASK || MODE == M_SEED || MODE == M_BSEED || MODE == M_BDZ7;
+  constexpr bool kWritesMask = MODE == M_BIAS_RELU || MODE == M_ROWBIAS_RELU;
+  constexpr bool kAddsAux = MODE == M_BIAS_RELU || MODE == M_BIAS || MODE == M_ROWBIAS_RELU;
+  constexpr int n_mine = (MODE == M_ROWBIAS_RELU || MODE == M_BSEED) ? 2 : 4;  // units per warp (op.nunits / 2)
+  constexpr int ub = HF * n_mine;
+  // sign-bit words of this thread's units: bit (31 - j) of word u <-> column 32u + j is positive.
+  // Loaded before the accumulator wait: the L2 round trip hides behind the MMAs.
+  uint32_t bw[n_mine];
+  if (kAppliesMask) {
+    const uint32_t* mp = c.mask + (op.mask_plane * 8 + ub) * kTileM + c.row;
+#pragma unroll
+    for (int i = 0; i < n_mine; ++i) bw[i] = mp[i * kTileM];
   }
-  if (MODE != M_SEED) tmem_ld32u(tacc + c.hf * 32, r[0]);
+  float rb[MODE == M_ROWBIAS_RELU ? n_mine : 1][32];
+  if (MODE == M_ROWBIAS_RELU) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    if (i < n_mine) {
-      const int u = c.hf + 2 * i;
-      float v[32];
-      if (MODE == M_RELU || MODE == M_LINEAR || MODE == M_VIEW) {
-        const float4* src = reinterpret_cast<const float4*>(MODE == M_VIEW ? rowbias : bias) + u * 8;
+    for (int i = 0; i < n_mine; ++i) {
+      const float4* src = reinterpret_cast<const float4*>(aux) + (ub + i) * 8;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 t = __ldg(src + j);
-          v[4 * j] = t.x, v[4 * j + 1] = t.y, v[4 * j + 2] = t.z, v[4 * j + 3] = t.w;
-        }
-      }
-      if (MODE == M_SEED) {
-        const float4* src = reinterpret_cast<const float4*>(bias) + u * 8;  // sigma row of the density head
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 t = __ldg(src + j);
-          v[4 * j] = t.x, v[4 * j + 1] = t.y, v[4 * j + 2] = t.z, v[4 * j + 3] = t.w;
-        }
-      } else {
-        tmem_wait_ld();
-        if (i + 1 < n_mine) tmem_ld32u(tacc + (u + 2) * 32, r[(i + 1) & 1]);
-        if (MODE == M_JAC) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[i & 1][j]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(r[i & 1][j]);
-        }
-        if (MODE == M_RELU || MODE == M_VIEW) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
-      }
-      if (NORMALS && MODE == M_RELU) {
-        uint32_t bits = 0;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) bits |= (v[j] > 0.f ? 1u : 0u) << j;
-        c.masks[(mask_idx * 8 + u) * kTileM + c.row] = bits;
-      }
-      if (MODE == M_JAC || MODE == M_SEED) {
-        const uint32_t bits = c.masks[(mask_idx * 8 + u) * kTileM + c.row];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? v[j] : 0.f;
-      }
-      if (c.save) {
-        // the TMA store that last read this k-block (issued by the hf = 0 warp of the pair) must be done reading it
-        if (c.hf == 0 && c.lane == 0) bulk_wait_read<0>();
-        named_bar_sync(1 + c.q, 64);
-      }
-      uint8_t* dst = c.abuf + (u >> 1) * kKbBytes + c.row * 128;
-      const int jb = (u & 1) * 4;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        __nv_bfloat162 h[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(v[8 * j + 2 * k], v[8 * j + 2 * k + 1]);
-        *reinterpret_cast<uint4*>(dst + (((jb + j) ^ (c.row & 7)) << 4)) = *reinterpret_cast<uint4*>(h);
-      }
-      fence_async_smem();
-      tc_fence_before();
-      __syncwarp();
-      if (c.lane == 0) mbar_arrive(&c.bars->a_ready[u]);
-      if (c.save) {
-        // both halves of k-block u/2 (rows of this quadrant) are in place: one thread of the pair stores the box
-        named_bar_sync(1 + c.q, 64);
-        if (save_idx >= 0 && c.hf == 0 && c.lane == 0) {
-          tma_store_3d(c.tmActs, c.abuf + (u >> 1) * kKbBytes + c.q * 4096, (u >> 1) * 64, c.tile_row0 + c.q * 32, save_idx);
-          bulk_commit();
-        }
+      for (int j = 0; j < 8; ++j) {
+        float4 t = __ldg(src + j);
+        rb[i][4 * j] = t.x, rb[i][4 * j + 1] = t.y, rb[i][4 * j + 2] = t.z, rb[i][4 * j + 3] = t.w;
       }
     }
   }
+  float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+  if (MODE == M_BSEED && c.row_ok) d0 = __ldg(p.d_rgb + c.m * 3), d1 = __ldg(p.d_rgb + c.m * 3 + 1), d2 = __ldg(p.d_rgb + c.m * 3 + 2);
+  if (op.has_mma) {
+    mbar_wait(c.acc_full, c.acc_parity);
+    tc_fence_after();
+  }
+  if (c.skip) {  // timing experiment: the epilogue costs nothing
+    tc_fence_before();
+    __syncwarp();
+    if (c.lane == 0) mbar_arrive(c.abuf_ready);
+    return;
+  }
+  uint32_t r[2][32];
+  if (kReadsAcc) tmem_ld32u(c.tacc + op.acc_col + ub * 32, r[0]);
+  if (c.save) {
+    // TMA stores issued by this warp that still read this tile's buffer (the op before the other tile's) must be
+    // done; at most the other tile's two newer groups may stay pending.
+    if (c.lane == 0) bulk_wait_read<2>();
+    __syncwarp();
+  }
+#pragma unroll
+  for (int i = 0; i < n_mine; ++i) {
+    const int u = ub + i;
+    float x[32];
+    if (MODE == M_SEED) {  // sigma row of the density head
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = c_bblob[coff + u * 32 + j];
+    }
+    if (MODE == M_BSEED) {  // d_rgb W_col: 3 x 32 FMAs
+      const float* w = c_bblob + kWCol + u * 32;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = fmaf(d2, w[256 + j], fmaf(d1, w[128 + j], d0 * w[j]));
+    }
+    if (kReadsAcc) {
+      tmem_wait_ld();
+      if (i + 1 < n_mine) tmem_ld32u(c.tacc + op.acc_col + (u + 1) * 32, r[(i + 1) & 1]);  // next unit in flight
+      if (MODE == M_ROWBIAS_RELU) {  // + per-ray view-direction term (prefetched above)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r[i & 1][j]) + rb[i][j];
+      } else if (kAddsAux) {         // + bias (per column)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r[i & 1][j]) + c_bblob[coff + u * 32 + j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r[i & 1][j]);
+      }
+    }
+    if (MODE == M_BDZ7) {  // + d_den W_den (C x 32 FMAs; the density head is too narrow for its own MMA pass)
+      for (int ch = 0; ch < p.C; ++ch) {
+        const float* w = c_bblob + kWDen + ch * 256 + u * 32;
+        const float d = c.row_ok ? __ldg(p.d_den + c.m * p.C + ch) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = fmaf(d, w[j], x[j]);
+      }
+    }
+    if (kWritesMask) {
+      if (c.mask != nullptr) {  // funnel shifts collect the sign bits (positive <-> sign bit clear), 4 independent chains
+        uint32_t sg[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) sg[g] = __funnelshift_l(__float_as_uint(x[8 * g + j]), sg[g], 1);
+        }
+        c.mask[(op.mask_plane * 8 + u) * kTileM + c.row] = ~((sg[0] << 24) | (sg[1] << 16) | (sg[2] << 8) | sg[3]);
+      }
+    }
+    if (kAppliesMask) {
+      const uint32_t b = bw[i];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = (b & (0x80000000u >> j)) ? x[j] : 0.f;
+    }
+    uint32_t h[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      __nv_bfloat162 t = __floats2bfloat162_rn(x[2 * k], x[2 * k + 1]);
+      if (MODE == M_BIAS_RELU || MODE == M_ROWBIAS_RELU) t = __hmax2(t, __floats2bfloat162_rn(0.f, 0.f));
+      h[k] = *reinterpret_cast<uint32_t*>(&t);
+    }
+    const uint32_t dst = smem_u32(c.abuf) + (u >> 1) * kKbBytes + c.row * 128;
+    const int jb = (u & 1) * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      sts128(dst + (((jb + j) ^ (c.row & 7)) << 4), h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+    if (c.save && (u & 1) && op.save_plane >= 0) {
+      // both halves of k-block u/2 (this warp's 32 rows) are in place: store the 32 x 64 box
+      fence_async_smem();
+      __syncwarp();
+      if (c.lane == 0) {
+        tma_store_3d(c.tmActs, c.abuf + (u >> 1) * kKbBytes + c.q * 4096, (u >> 1) * 64, c.tile_row0 + c.q * 32,
+                     op.save_plane);
+        bulk_commit();
+      }
+    }
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncwarp();
+  if (c.lane == 0) mbar_arrive(c.abuf_ready);
+}
+
+template <int MODE>
+__device__ __forceinline__ void rewrite_abuf(const EpiCtx& c, const FusedParams& p, const Op& op, const float* aux,
+                                             int coff) {
+  if (c.hf == 0) rewrite_abuf_hf<MODE, 0>(c, p, op, aux, coff);
+  else rewrite_abuf_hf<MODE, 1>(c, p, op, aux, coff);
+}
+
+// Epilogues that only read a few accumulator columns (heads, encoding gradients) and leave the buffer alone.
+__device__ __forceinline__ void epi_wait(const EpiCtx& c) {
+  mbar_wait(c.acc_full, c.acc_parity);
+  tc_fence_after();
+}
+__device__ __forceinline__ void epi_done(const EpiCtx& c) {
+  tc_fence_before();
+  __syncwarp();
+  if (c.lane == 0) mbar_arrive(c.abuf_ready);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -392,34 +560,35 @@ __device__ __forceinline__ void rewrite_abuf(const EpiCtx& c, uint32_t tacc, int
 struct MmaCtx {
   FBarriers* bars;
   int slot, enc_slot, ns;
-  uint32_t ph, unit_ph;
+  uint32_t ph, ab_ph;
   uint32_t abuf16, ring16, tmem_base;
+  bool prof;
+  long long t_ab, t_full;
 };
 
-template <int S>
-__device__ __forceinline__ void mma_step(MmaCtx& c) {
-  constexpr Step st = kSched.steps[S];
+template <int P, int S>
+__device__ __forceinline__ void mma_step(MmaCtx& c, int t) {
+  constexpr Step st = kSched.prog[P].steps[S];
   if constexpr ((st.flags & F_LOADENC) != 0) {
     mbar_wait(&c.bars->full[c.slot], c.ph);
     c.enc_slot = c.slot;
     if (++c.slot == c.ns) c.slot = 0, c.ph ^= 1;
   }
-  mbar_wait(&c.bars->full[c.slot], c.ph);
-  const uint32_t a16 =
-      (((st.flags & F_AENC) != 0) ? c.ring16 + (uint32_t)c.enc_slot * (kSlotBytes >> 4) : c.abuf16) + st.a_off16;
+  if (c.prof) {
+    const long long t0 = clock64();
+    mbar_wait(&c.bars->full[c.slot], c.ph);
+    c.t_full += clock64() - t0;
+  } else {
+    mbar_wait(&c.bars->full[c.slot], c.ph);
+  }
+  tc_fence_after();
+  const uint32_t a16 = (((st.flags & F_AENC) != 0) ? c.ring16 + (uint32_t)c.enc_slot * (kSlotBytes >> 4)
+                                                  : c.abuf16 + (uint32_t)t * (kAbufBytes >> 4)) +
+                       st.a_off16;
   const uint32_t b16 = c.ring16 + (uint32_t)c.slot * (kSlotBytes >> 4);
-  const uint32_t d_tmem = c.tmem_base + st.acc_col;
-  if constexpr ((st.flags & F_WAIT) == 0) tc_fence_after();
+  const uint32_t d_tmem = c.tmem_base + (uint32_t)t * 256u + st.acc_col;
 #pragma unroll
   for (int k = 0; k < (int)st.nk16; ++k) {
-    if constexpr ((st.flags & F_WAIT) != 0) {
-      if ((k & 1) == 0) {
-        const int u = (int)st.u0 + (k >> 1);
-        mbar_wait(&c.bars->a_ready[u], (c.unit_ph >> u) & 1u);
-        c.unit_ph ^= 1u << u;
-        tc_fence_after();
-      }
-    }
     const uint32_t ak = (uint32_t)((k >> 2) * (kKbBytes >> 4) + (k & 3) * 2);
     const uint32_t bk = (uint32_t)(k >> 2) * st.b_kb16 + (uint32_t)(k & 3) * 2;
     umma_f16(d_tmem, desc_from16(a16 + ak), desc_from16(b16 + bk), st.idesc,
@@ -427,32 +596,57 @@ __device__ __forceinline__ void mma_step(MmaCtx& c) {
   }
   umma_commit(&c.bars->empty[c.slot]);
   if constexpr ((st.flags & F_RELENC) != 0) umma_commit(&c.bars->empty[c.enc_slot]);
-  if constexpr (st.commit != 0) umma_commit(&c.bars->acc_full[st.commit - 1]);
   if (++c.slot == c.ns) c.slot = 0, c.ph ^= 1;
 }
 
-template <int... S>
-__device__ __forceinline__ void mma_program(MmaCtx& c, std::integer_sequence<int, S...>) {
-  (mma_step<S>(c), ...);
+template <int P, int S0, int... S>
+__device__ __forceinline__ void mma_steps(MmaCtx& c, int t, std::integer_sequence<int, S...>) {
+  (mma_step<P, S0 + S>(c, t), ...);
+}
+
+template <int P, int OP>
+__device__ __forceinline__ void mma_op(MmaCtx& c) {
+  constexpr Op op = kSched.prog[P].ops[OP];
+#pragma unroll 1
+  for (int t = 0; t < 2; ++t) {
+    // the tile's previous epilogue has drained the accumulator and rewritten the activation buffer
+    if (c.prof) {
+      const long long t0 = clock64();
+      mbar_wait(&c.bars->abuf_ready[t], (c.ab_ph >> t) & 1u);
+      c.t_ab += clock64() - t0;
+    } else {
+      mbar_wait(&c.bars->abuf_ready[t], (c.ab_ph >> t) & 1u);
+    }
+    c.ab_ph ^= 1u << t;
+    if constexpr (op.has_mma != 0) {
+      tc_fence_after();
+      mma_steps<P, op.s0>(c, t, std::make_integer_sequence<int, op.s1 - op.s0>{});
+      umma_commit(&c.bars->acc_full[t]);
+    }
+  }
+}
+
+template <int P, int... OPS>
+__device__ __forceinline__ void mma_program(MmaCtx& c, std::integer_sequence<int, OPS...>) {
+  (mma_op<P, OPS>(c), ...);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------------
-template <bool NORMALS>
+template <int P>
 __global__ void __launch_bounds__(kFThreads, 1)
 mlp_fused_kernel(const __grid_constant__ CUtensorMap tmEnc, const __grid_constant__ CUtensorMap tmActs,
                  const FusedParams p) {
-  constexpr int kSteps = NORMALS ? kSched.n_all : kSched.n_fwd;
-  constexpr int kEpis = NORMALS ? kSched.ne_all : kSched.ne_fwd;
+  constexpr int kOps = kSched.prog[P].n_ops;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_1024(smem_raw);
-  uint8_t* abuf = smem;
-  uint8_t* ring = abuf + kAbufBytes;
-  uint32_t* masks = reinterpret_cast<uint32_t*>(ring + (size_t)p.nstages * kSlotBytes);
-  FBarriers* bars = reinterpret_cast<FBarriers*>(reinterpret_cast<uint8_t*>(masks) + (NORMALS ? kMaskBytes : 0));
+  uint8_t* abuf = smem;                       // [2 tiles][4 k-blocks]
+  uint8_t* ring = abuf + 2 * kAbufBytes;
+  FBarriers* bars = reinterpret_cast<FBarriers*>(ring + (size_t)p.nstages * kSlotBytes);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // shuffled so that the compiler knows the warp index (and everything derived from it) is warp-uniform
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int NS = p.nstages;
 
   if (warp == 0 && lane == 0) {
@@ -462,9 +656,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmEnc, const __grid_constan
       mbar_init(&bars->full[s], 1);
       mbar_init(&bars->empty[s], 1);
     }
-    for (int u = 0; u < 8; ++u) mbar_init(&bars->a_ready[u], 4);
-    mbar_init(&bars->acc_full[0], 1);
-    mbar_init(&bars->acc_full[1], 1);
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&bars->abuf_ready[t], 8);
+      mbar_init(&bars->acc_full[t], 1);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&bars->tmem_base, 512);
@@ -478,131 +673,196 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmEnc, const __grid_constan
     if (lane == 0) {
       int slot = 0;
       uint32_t ph = 0;
-      for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int row0 = (int)(tile * kTileM);
-        for (int s = 0; s < kSteps; ++s) {
-          const uint32_t blob_off = c_sched.steps[s].blob_off;
-          const uint32_t bytes = c_sched.steps[s].bytes;
-          if (c_sched.steps[s].flags & F_LOADENC) {
-            mbar_wait(&bars->empty[slot], ph ^ 1);
-            mbar_expect_tx(&bars->full[slot], 2 * kKbBytes);
-            tma_load_2d(ring + (size_t)slot * kSlotBytes, &tmEnc, &bars->full[slot], 0, row0);
-            tma_load_2d(ring + (size_t)slot * kSlotBytes + kKbBytes, &tmEnc, &bars->full[slot], 64, row0);
-            if (++slot == NS) slot = 0, ph ^= 1;
+      const uint8_t* wblob = p.wblob + (size_t)(blockIdx.x % p.replicas) * p.blob_stride;
+      for (long long pair = blockIdx.x; pair < p.num_pairs; pair += gridDim.x) {
+        for (int o = 0; o < kOps; ++o) {
+          const int s0 = c_prog[P].ops[o].s0, s1 = c_prog[P].ops[o].s1;
+          if (s1 == s0) continue;
+          for (int t = 0; t < 2; ++t) {
+            long long tile = pair * 2 + t;
+            if (tile >= p.num_tiles) tile = p.num_tiles - 1;  // phantom tile of an odd tail: recompute the last one
+            const int row0 = (int)(tile * kTileM);
+            for (int s = s0; s < s1; ++s) {
+              const uint32_t blob_off = c_prog[P].steps[s].blob_off;  // (relative to this CTA's copy of the blob)
+              const uint32_t bytes = c_prog[P].steps[s].bytes;
+              if (c_prog[P].steps[s].flags & F_LOADENC) {
+                mbar_wait(&bars->empty[slot], ph ^ 1);
+                mbar_expect_tx(&bars->full[slot], 2 * kKbBytes);
+                tma_load_2d(ring + (size_t)slot * kSlotBytes, &tmEnc, &bars->full[slot], 0, row0);
+                tma_load_2d(ring + (size_t)slot * kSlotBytes + kKbBytes, &tmEnc, &bars->full[slot], 64, row0);
+                if (++slot == NS) slot = 0, ph ^= 1;
+              }
+              mbar_wait(&bars->empty[slot], ph ^ 1);
+              if (p.debug & 1) {  // experiment: no weight traffic (the MMAs read whatever the slot holds)
+                mbar_arrive(&bars->full[slot]);
+              } else {
+                mbar_expect_tx(&bars->full[slot], bytes);
+                bulk_load_1d(ring + (size_t)slot * kSlotBytes, wblob + blob_off, bytes, &bars->full[slot]);
+              }
+              if (++slot == NS) slot = 0, ph ^= 1;
+            }
           }
-          mbar_wait(&bars->empty[slot], ph ^ 1);
-          if (p.debug & 1) {  // experiment: no weight traffic (the MMAs read whatever the slot holds)
-            mbar_arrive(&bars->full[slot]);
-          } else {
-            mbar_expect_tx(&bars->full[slot], bytes);
-            bulk_load_1d(ring + (size_t)slot * kSlotBytes, p.wblob + blob_off, bytes, &bars->full[slot]);
-          }
-          if (++slot == NS) slot = 0, ph ^= 1;
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     // ================================ MMA issuer ================================================================
-    // One thread runs the schedule, fully unrolled at compile time (mma_step<S>): descriptor offsets, instruction
-    // descriptors, accumulate flags and barrier indices are immediates; only the ring position is dynamic.
+    // One thread runs the schedule, fully unrolled at compile time (mma_step<P,S>): descriptor offsets, instruction
+    // descriptors, accumulate flags and barrier indices are immediates; only the ring position and the tile are
+    // dynamic.
     if (lane == 0) {
       MmaCtx mc;
-      mc.bars = bars, mc.slot = 0, mc.enc_slot = 0, mc.ph = 0, mc.unit_ph = 0, mc.ns = NS;
+      mc.bars = bars, mc.slot = 0, mc.enc_slot = 0, mc.ph = 0, mc.ab_ph = 0, mc.ns = NS;
       mc.abuf16 = smem_u32(abuf) >> 4, mc.ring16 = smem_u32(ring) >> 4, mc.tmem_base = tmem_base;
-      for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x)
-        mma_program(mc, std::make_integer_sequence<int, kSteps>{});
+      mc.prof = p.prof != nullptr, mc.t_ab = 0, mc.t_full = 0;
+      const long long t_start = clock64();
+      for (long long pair = blockIdx.x; pair < p.num_pairs; pair += gridDim.x)
+        mma_program<P>(mc, std::make_integer_sequence<int, kOps>{});
+      if (p.prof != nullptr) {
+        p.prof[blockIdx.x * 8 + 0] = (unsigned long long)(clock64() - t_start);
+        p.prof[blockIdx.x * 8 + 1] = (unsigned long long)mc.t_ab;
+        p.prof[blockIdx.x * 8 + 2] = (unsigned long long)mc.t_full;
+      }
     }
     __syncwarp();
   } else {
     // ================================ epilogue warps ============================================================
     EpiCtx c;
-    c.abuf = abuf, c.masks = masks, c.bars = bars, c.tmActs = &tmActs;
+    c.tmActs = &tmActs;
     c.q = warp & 3;            // TMEM lane quadrant (hardware rule: warp id % 4)
-    c.hf = (warp - 2) >> 2;    // which of the two warps of the quadrant: even / odd 32-column units
-    c.lane = lane, c.row = c.q * 32 + lane, c.save = p.save, c.skip = (p.debug & 2) != 0;
+    c.hf = (warp - 2) >> 2;    // which of the two warps of the quadrant
+    c.lane = lane, c.row = c.q * 32 + lane, c.save = p.save != 0, c.skip = (p.debug & 2) != 0;
     const uint32_t tlane = tmem_base + ((uint32_t)(c.q * 32) << 16);
+    if (lane == 0) {           // both activation buffers / accumulators start out free
+      mbar_arrive(&bars->abuf_ready[0]);
+      mbar_arrive(&bars->abuf_ready[1]);
+    }
     uint32_t acc_ph = 0;
-    for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const long long m = tile * kTileM + c.row;
-      const bool row_ok = m < p.M;
-      const long long m_safe = row_ok ? m : p.M - 1;
-      c.tile_row0 = (int)(tile * kTileM);
-      for (int e = 0; e < kEpis; ++e) {
-        const Epi ep = c_sched.epis[e];
-        mbar_wait(&bars->acc_full[ep.bar], (acc_ph >> ep.bar) & 1u);
-        acc_ph ^= 1u << ep.bar;
-        tc_fence_after();
-        const uint32_t tacc = tlane + ep.acc_col;
-        switch (ep.type) {
-          case E_RELU:
-            rewrite_abuf<M_RELU, NORMALS>(c, tacc, 8, p.bblob + ep.bias_off, nullptr, ep.mask_idx, ep.save_idx);
-            break;
-          case E_HEADS:
-            if (c.hf == 0) {  // density head (Y[0:16]) before anything else
-              float v[16];
-              tmem_ld16(tlane + kAccY, v);
-              if (row_ok) {
+    long long t_wait = 0;
+    const long long t_epi0 = clock64();
+    for (long long pair = blockIdx.x; pair < p.num_pairs; pair += gridDim.x) {
+      for (int e = 0; e < kOps; ++e) {
+        const Op op = c_prog[P].ops[e];
+        for (int t = 0; t < 2; ++t) {
+          const long long tile = pair * 2 + t;
+          const bool tile_ok = tile < p.num_tiles;
+          c.m = tile * kTileM + c.row;
+          c.row_ok = tile_ok && c.m < p.M;
+          const long long m_safe = c.row_ok ? c.m : p.M - 1;
+          c.tile_row0 = (int)(tile * kTileM);
+          c.save = p.save != 0 && tile_ok;
+          c.abuf = abuf + t * kAbufBytes;
+          c.tacc = tlane + (uint32_t)t * 256u;
+          c.acc_full = &bars->acc_full[t], c.abuf_ready = &bars->abuf_ready[t];
+          c.acc_parity = (acc_ph >> t) & 1u;
+          if (op.has_mma) acc_ph ^= 1u << t;
+          if (p.prof != nullptr && op.has_mma) {  // (the real wait inside the epilogue then returns at once)
+            const long long t0 = clock64();
+            mbar_wait(c.acc_full, c.acc_parity);
+            t_wait += clock64() - t0;
+          }
+          c.mask = p.masks == nullptr
+                       ? nullptr
+                       : p.masks + (size_t)(p.masks_per_tile ? tile : (long long)blockIdx.x * 2 + t) * kMaskWordsPerTile;
+          constexpr bool kFwd = P == P_FWD || P == P_FWDJ;
+          constexpr bool kChain = P == P_FWDJ || P == P_BWD;
+          const int epi = op.epi;
+          if (kFwd && epi == E_RELU) {
+            rewrite_abuf<M_BIAS_RELU>(c, p, op, nullptr, op.bias_off);
+          } else if (kFwd && epi == E_EXTRA) {
+            rewrite_abuf<M_BIAS>(c, p, op, nullptr, op.bias_off);
+          } else if (kFwd && epi == E_VIEW) {
+            rewrite_abuf<M_ROWBIAS_RELU>(c, p, op, p.row_bias + (m_safe / p.S) * kCondW, 0);
+          } else if (P != P_FWD && epi == E_MASK) {
+            rewrite_abuf<M_MASK>(c, p, op, nullptr, 0);
+          } else if (P == P_BWD && epi == E_LIN) {
+            rewrite_abuf<M_LIN>(c, p, op, nullptr, 0);
+          } else if (P == P_BWD && epi == E_BSEED) {
+            rewrite_abuf<M_BSEED>(c, p, op, nullptr, 0);
+          } else if (P == P_BWD && epi == E_BDZ7) {
+            rewrite_abuf<M_BDZ7>(c, p, op, nullptr, 0);
+          } else if (kFwd) switch (epi) {
+            case E_DEN:
+              epi_wait(c);
+              if (c.hf == 0) {
+                float v[16];
+                tmem_ld16(c.tacc + op.acc_col, v);
+                if (c.row_ok) {
 #pragma unroll
-                for (int ch = 0; ch < 16; ++ch)
-                  if (ch < p.C) p.raw_den[m * p.C + ch] = v[ch] + __ldg(p.bblob + kBiasHD + ch);
+                  for (int ch = 0; ch < 16; ++ch)
+                    if (ch < p.C) p.raw_den[c.m * p.C + ch] = v[ch] + __ldg(p.bblob + kBiasHD + ch);
+                }
               }
-            }
-            rewrite_abuf<M_LINEAR, NORMALS>(c, tacc, 8, p.bblob + ep.bias_off, nullptr, 0, ep.save_idx);
-            break;
-          case E_VIEW:
-            rewrite_abuf<M_VIEW, NORMALS>(c, tacc, 4, nullptr, p.row_bias + (m_safe / p.S) * kCondW, 0, ep.save_idx);
-            break;
-          case E_COLOR:
-            if (c.hf == 0) {
-              float v[16];
-              tmem_ld16(tacc, v);
-              if (row_ok) {
+              epi_done(c);
+              break;
+            case E_COLOR:
+              if (P == P_FWDJ) {
+                // raw_rgb first (the accumulator is complete once acc_full fires), then the seed of the Jacobian
+                // sweep a_7 = relu'(h_7) * w_sigma replaces the view activations
+                epi_wait(c);
+                if (c.hf == 0) {
+                  float v[16];
+                  tmem_ld16(c.tacc + op.acc_col, v);
+                  if (c.row_ok) {
 #pragma unroll
-                for (int ch = 0; ch < 3; ++ch) p.raw_rgb[m * 3 + ch] = v[ch] + __ldg(p.bblob + kBiasC + ch);
+                    for (int ch = 0; ch < 3; ++ch) p.raw_rgb[c.m * 3 + ch] = v[ch] + __ldg(p.bblob + kBiasC + ch);
+                  }
+                }
+                Op o2 = op;
+                o2.has_mma = 0;
+                rewrite_abuf<M_SEED>(c, p, o2, nullptr, kWDen);
+              } else {
+                epi_wait(c);
+                if (c.hf == 0) {
+                  float v[16];
+                  tmem_ld16(c.tacc + op.acc_col, v);
+                  if (c.row_ok) {
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) p.raw_rgb[c.m * 3 + ch] = v[ch] + __ldg(p.bblob + kBiasC + ch);
+                  }
+                }
+                epi_done(c);
               }
-            }
-            if (NORMALS)  // seed of the Jacobian sweep: a_7 = relu'(h_7) * w_sigma
-              rewrite_abuf<M_SEED, NORMALS>(c, tacc, 8, p.bblob + kWSigma, nullptr, ep.mask_idx, ep.save_idx);
-            else
-              tc_fence_before();
-            break;
-          case E_JAC5:
-          case E_G0:
-            if (c.hf == 0) {  // d sigma / d enc: skip-connection part first (stored), layer-0 part added at the end
+              break;
+            default:
+              break;
+          }
+          if (kChain && (epi == E_GSKIP || epi == E_G0)) {
+            {  // gradient w.r.t. the encoding, 96 fp32 columns: chunks 0,1 -> hf 0, chunk 2 -> hf 1
+              epi_wait(c);
+              if (p.g_enc != nullptr) {
 #pragma unroll 1
-              for (int c0 = 0; c0 < kEncDim; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld32u(tlane + kAccY + c0, r);
-                tmem_wait_ld();
-                if (row_ok) {
-                  float4* dst = reinterpret_cast<float4*>(p.g_enc + m * kEncDim + c0);
+                for (int ch = c.hf * 2; ch < (c.hf == 0 ? 2 : 3); ++ch) {
+                  uint32_t r[32];
+                  tmem_ld32u(c.tacc + op.acc_col + ch * 32, r);
+                  tmem_wait_ld();
+                  if (c.row_ok) {
+                    float4* dst = reinterpret_cast<float4*>(p.g_enc + c.m * kEncDim + ch * 32);
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) {
-                    float4 o = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
-                                           __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
-                    if (ep.type == E_G0) {
-                      float4 prev = dst[i];
-                      o.x += prev.x, o.y += prev.y, o.z += prev.z, o.w += prev.w;
+                    for (int i = 0; i < 8; ++i) {
+                      float4 o = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                             __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+                      if (op.epi == E_G0) {
+                        float4 prev = dst[i];
+                        o.x += prev.x, o.y += prev.y, o.z += prev.z, o.w += prev.w;
+                      }
+                      dst[i] = o;
                     }
-                    dst[i] = o;
                   }
                 }
               }
+              epi_done(c);
             }
-            if (ep.type == E_G0) {
-              tc_fence_before();
-              break;
-            }
-            rewrite_abuf<M_JAC, NORMALS>(c, tacc, 8, nullptr, nullptr, ep.mask_idx, ep.save_idx);
-            break;
-          default:  // E_JAC
-            rewrite_abuf<M_JAC, NORMALS>(c, tacc, 8, nullptr, nullptr, ep.mask_idx, ep.save_idx);
-            break;
+          }
         }
       }
     }
     if (lane == 0) bulk_wait_all();
+    if (p.prof != nullptr && lane == 0 && warp == 2) {
+      p.prof[blockIdx.x * 8 + 3] = (unsigned long long)(clock64() - t_epi0);
+      p.prof[blockIdx.x * 8 + 4] = (unsigned long long)t_wait;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -636,15 +896,75 @@ static bool make_map_acts(CUtensorMap* out, const void* base, unsigned long long
   return true;
 }
 
+// copies are 4 KB-aligned plus an odd number of 256-byte lines apart, so that equal tile offsets land on different slices
+static long long blob_stride() { return ((long long)kSched.blob_bytes + 4095) / 4096 * 4096 + 256 * 37; }
+
+template <int P>
+static int launch(const CUtensorMap& tmEnc, const CUtensorMap& tmActs, FusedParams& p, cudaStream_t st,
+                  const char* what) {
+  const size_t fixed = 1024 + 2 * kAbufBytes + sizeof(FBarriers);
+  int ns = (int)(((size_t)kSmemLimit - fixed) / kSlotBytes);
+  if (ns > kFMaxStages) ns = kFMaxStages;
+  PNB_REQUIRE(ns >= 3, "mlp_fused: shared memory budget too small");
+  p.nstages = ns;
+  const size_t smem_bytes = fixed + (size_t)ns * kSlotBytes;
+  if (const char* dbg = getenv("PNB_FUSED_DEBUG")) p.debug = atoi(dbg);  // timing experiments only (wrong results)
+  p.replicas = kReplicas, p.blob_stride = blob_stride();
+  if (const char* r = getenv("PNB_FUSED_REPLICAS")) {  // timing experiments only
+    p.replicas = atoi(r);
+    if (p.replicas < 1 || p.replicas > kReplicas) p.replicas = kReplicas;
+  }
+  const long long gx = p.num_pairs < kNumSMs ? p.num_pairs : kNumSMs;
+  static unsigned long long* prof_buf = nullptr;
+  const bool prof = getenv("PNB_FUSED_PROF") != nullptr;
+  if (prof) {
+    if (prof_buf == nullptr) cudaMalloc(&prof_buf, sizeof(unsigned long long) * 8 * kNumSMs);
+    cudaMemsetAsync(prof_buf, 0, sizeof(unsigned long long) * 8 * kNumSMs, st);
+    p.prof = prof_buf;
+  }
+  cudaError_t e = cudaFuncSetAttribute(mlp_fused_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  if (e != cudaSuccess) {
+    set_error("mlp_fused(smem attr)", e);
+    return (int)e;
+  }
+  if (p.bblob != nullptr) {
+    e = cudaMemcpyToSymbolAsync(c_bblob, p.bblob, sizeof(float) * kBiasFloats, 0, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) {
+      set_error("mlp_fused(bias staging)", e);
+      return (int)e;
+    }
+  }
+  mlp_fused_kernel<P><<<(unsigned)gx, kFThreads, smem_bytes, st>>>(tmEnc, tmActs, p);
+  if (prof) {  // timing experiments only: per-CTA cycle counters, averaged
+    unsigned long long h[8 * kNumSMs];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, prof_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    double a[5] = {0, 0, 0, 0, 0};
+    for (long long b = 0; b < gx; ++b)
+      for (int i = 0; i < 5; ++i) a[i] += (double)h[b * 8 + i] / (double)gx;
+    fprintf(stderr, "[%s] cycles/CTA: mma total %.0f (wait abuf %.0f, wait ring %.0f) | epilogue warp total %.0f (wait acc %.0f)\n",
+            what, a[0], a[1], a[2], a[3], a[4]);
+  }
+  return finish(what);
+}
+
 }  // namespace fused
 }  // namespace pnb
 
 using namespace pnb;
 using namespace pnb::fused;
 
-extern "C" long long pnb_mlp_fused_wblob_bytes(void) { return (long long)kSched.blob_bytes; }
+extern "C" long long pnb_mlp_fused_wblob_bytes(void) { return blob_stride() * kReplicas; }
 extern "C" long long pnb_mlp_fused_bblob_floats(void) { return kBiasFloats; }
 extern "C" int pnb_mlp_fused_act_planes(void) { return kActPlanes; }
+extern "C" int pnb_mlp_fused_bwd_planes(void) { return kBwdPlanes; }
+extern "C" int pnb_mlp_fused_adj_planes(void) { return kAdjPlanes; }
+
+extern "C" long long pnb_mlp_fused_mask_words(long long M, int per_tile) {
+  const long long tiles = (M + kTileM - 1) / kTileM;
+  const long long slots = per_tile ? (tiles + 1) / 2 * 2 : 2ll * kNumSMs;
+  return slots * kMaskWordsPerTile;
+}
 
 extern "C" int pnb_mlp_fused_pack(const void* const* params_host, int C, void* wblob, float* bblob, void* stream) {
   PNB_REQUIRE(params_host != nullptr && wblob != nullptr && bblob != nullptr, "mlp_fused_pack: null argument");
@@ -660,22 +980,17 @@ extern "C" int pnb_mlp_fused_pack(const void* const* params_host, int C, void* w
   }
   a.C = C;
   a.n_tiles = s.n_pack;
-  for (int i = 0; i < s.n_pack; ++i) a.tiles[i] = s.pack[i];
-  for (int i = 0; i < s.n_pack; ++i) {  // density / colour heads have C / 3 valid rows
-    if (a.tiles[i].param == 8) a.tiles[i].vr = (int16_t)C;
-    if (a.tiles[i].param == 11) a.tiles[i].vr = 3;
-  }
   cudaStream_t st = as_stream(stream);
-  pack_tiles_kernel<<<s.n_pack, 256, 0, st>>>(a, reinterpret_cast<uint8_t*>(wblob));
+  pack_tiles_kernel<<<dim3(s.n_pack, kReplicas), 256, 0, st>>>(a, reinterpret_cast<uint8_t*>(wblob), blob_stride());
   int rc = finish("mlp_fused_pack(tiles)");
   if (rc) return rc;
-  pack_bias_kernel<<<4, 256, 0, st>>>(a, bblob);
+  pack_bias_kernel<<<8, 256, 0, st>>>(a, bblob);
   return finish("mlp_fused_pack(bias)");
 }
 
 extern "C" int pnb_mlp_fused_fwd(long long M, int S, int C, const void* enc, int ld_enc, const void* wblob,
                                  const float* bblob, const float* row_bias, float* raw_den, float* raw_rgb,
-                                 void* acts, float* g_enc, void* stream) {
+                                 void* acts, float* g_enc, void* masks, int masks_per_tile, void* stream) {
   PNB_REQUIRE(M >= 0 && S >= 1 && C >= 1 && C <= 16, "mlp_fused_fwd: bad sizes");
   PNB_REQUIRE(enc && wblob && bblob && row_bias && raw_den && raw_rgb, "mlp_fused_fwd: null argument");
   PNB_REQUIRE(ld_enc % 8 == 0 && ld_enc >= kEncDim && ((uintptr_t)enc % 16 == 0) && ((uintptr_t)wblob % 16 == 0) &&
@@ -683,21 +998,15 @@ extern "C" int pnb_mlp_fused_fwd(long long M, int S, int C, const void* enc, int
               "mlp_fused_fwd: enc / blobs / row_bias must be 16-byte aligned, ld_enc % 8 == 0");
   PNB_REQUIRE(g_enc == nullptr || (uintptr_t)g_enc % 16 == 0, "mlp_fused_fwd: g_enc must be 16-byte aligned");
   PNB_REQUIRE(acts == nullptr || (uintptr_t)acts % 128 == 0, "mlp_fused_fwd: acts must be 128-byte aligned");
-  PNB_REQUIRE(M < (1ll << 31) - kTileM, "mlp_fused_fwd: M too large for 32-bit TMA coordinates");
+  PNB_REQUIRE(g_enc == nullptr || masks != nullptr, "mlp_fused_fwd: the Jacobian sweep needs the sign-bit buffer");
+  PNB_REQUIRE(M < (1ll << 31) - 2 * kTileM, "mlp_fused_fwd: M too large for 32-bit TMA coordinates");
   if (M == 0) return 0;
-  const bool normals = g_enc != nullptr;
   FusedParams p{};
-  p.M = M, p.num_tiles = (M + kTileM - 1) / kTileM;
+  p.M = M, p.num_tiles = (M + kTileM - 1) / kTileM, p.num_pairs = (p.num_tiles + 1) / 2;
   p.S = S, p.C = C, p.save = acts != nullptr;
-  if (const char* dbg = getenv("PNB_FUSED_DEBUG")) p.debug = atoi(dbg);  // timing experiments only (wrong results)
   p.wblob = reinterpret_cast<const uint8_t*>(wblob), p.bblob = bblob, p.row_bias = row_bias;
   p.raw_den = raw_den, p.raw_rgb = raw_rgb, p.g_enc = g_enc;
-  const size_t fixed = 1024 + kAbufBytes + (normals ? kMaskBytes : 0) + sizeof(FBarriers);
-  int ns = (int)(((size_t)kSmemLimit - fixed) / kSlotBytes);
-  if (ns > kFMaxStages) ns = kFMaxStages;
-  PNB_REQUIRE(ns >= 3, "mlp_fused_fwd: shared memory budget too small");
-  p.nstages = ns;
-  const size_t smem_bytes = fixed + (size_t)ns * kSlotBytes;
+  p.masks = reinterpret_cast<uint32_t*>(masks), p.masks_per_tile = masks_per_tile;
   CUtensorMap tmEnc, tmActs;
   if (!make_map_enc(&tmEnc, enc, (unsigned long long)M, (unsigned long long)ld_enc)) return PNB_ERR_ARG;
   if (p.save) {
@@ -705,19 +1014,47 @@ extern "C" int pnb_mlp_fused_fwd(long long M, int S, int C, const void* enc, int
   } else {
     tmActs = tmEnc;
   }
-  const long long gx = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
   cudaStream_t st = as_stream(stream);
-  cudaError_t e;
-  if (normals) {
-    e = cudaFuncSetAttribute(mlp_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    if (e == cudaSuccess) mlp_fused_kernel<true><<<(unsigned)gx, kFThreads, smem_bytes, st>>>(tmEnc, tmActs, p);
-  } else {
-    e = cudaFuncSetAttribute(mlp_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    if (e == cudaSuccess) mlp_fused_kernel<false><<<(unsigned)gx, kFThreads, smem_bytes, st>>>(tmEnc, tmActs, p);
-  }
-  if (e != cudaSuccess) {
-    set_error("mlp_fused_fwd(smem attr)", e);
-    return (int)e;
-  }
-  return finish("mlp_fused_fwd");
+  if (g_enc != nullptr) return launch<P_FWDJ>(tmEnc, tmActs, p, st, "mlp_fused_fwd(jac)");
+  return launch<P_FWD>(tmEnc, tmActs, p, st, "mlp_fused_fwd");
+}
+
+extern "C" int pnb_mlp_fused_bwd(long long M, int C, const void* wblob, const float* bblob, const float* d_rgb,
+                                 const float* d_den, const void* masks, void* dz_planes, float* d_enc, void* stream) {
+  PNB_REQUIRE(M >= 0 && C >= 1 && C <= 16, "mlp_fused_bwd: bad sizes");
+  PNB_REQUIRE(wblob && bblob && d_rgb && d_den && masks && dz_planes, "mlp_fused_bwd: null argument");
+  PNB_REQUIRE(((uintptr_t)wblob % 16 == 0) && ((uintptr_t)bblob % 16 == 0) && ((uintptr_t)dz_planes % 128 == 0) &&
+                  (d_enc == nullptr || (uintptr_t)d_enc % 16 == 0),
+              "mlp_fused_bwd: misaligned argument");
+  PNB_REQUIRE(M < (1ll << 31) - 2 * kTileM, "mlp_fused_bwd: M too large for 32-bit TMA coordinates");
+  if (M == 0) return 0;
+  FusedParams p{};
+  p.M = M, p.num_tiles = (M + kTileM - 1) / kTileM, p.num_pairs = (p.num_tiles + 1) / 2;
+  p.S = 1, p.C = C, p.save = 1;
+  p.wblob = reinterpret_cast<const uint8_t*>(wblob), p.bblob = bblob;
+  p.g_enc = d_enc, p.d_rgb = d_rgb, p.d_den = d_den;
+  p.masks = reinterpret_cast<uint32_t*>(const_cast<void*>(masks)), p.masks_per_tile = 1;
+  CUtensorMap tmActs;
+  if (!make_map_acts(&tmActs, dz_planes, kBwdPlanes, (unsigned long long)M)) return PNB_ERR_ARG;
+  return launch<P_BWD>(tmActs, tmActs, p, as_stream(stream), "mlp_fused_bwd");
+}
+
+extern "C" int pnb_mlp_fused_jadj(long long M, const void* u, int ld_u, const void* wblob, const void* masks,
+                                  void* q_planes, void* stream) {
+  PNB_REQUIRE(M >= 0, "mlp_fused_jadj: bad sizes");
+  PNB_REQUIRE(u && wblob && masks && q_planes, "mlp_fused_jadj: null argument");
+  PNB_REQUIRE(ld_u % 8 == 0 && ld_u >= kEncDim && ((uintptr_t)u % 16 == 0) && ((uintptr_t)wblob % 16 == 0) &&
+                  ((uintptr_t)q_planes % 128 == 0),
+              "mlp_fused_jadj: misaligned argument");
+  PNB_REQUIRE(M < (1ll << 31) - 2 * kTileM, "mlp_fused_jadj: M too large for 32-bit TMA coordinates");
+  if (M == 0) return 0;
+  FusedParams p{};
+  p.M = M, p.num_tiles = (M + kTileM - 1) / kTileM, p.num_pairs = (p.num_tiles + 1) / 2;
+  p.S = 1, p.C = 1, p.save = 1;
+  p.wblob = reinterpret_cast<const uint8_t*>(wblob);
+  p.masks = reinterpret_cast<uint32_t*>(const_cast<void*>(masks)), p.masks_per_tile = 1;
+  CUtensorMap tmEnc, tmActs;
+  if (!make_map_enc(&tmEnc, u, (unsigned long long)M, (unsigned long long)ld_u)) return PNB_ERR_ARG;
+  if (!make_map_acts(&tmActs, q_planes, kAdjPlanes, (unsigned long long)M)) return PNB_ERR_ARG;
+  return launch<P_JADJ>(tmEnc, tmActs, p, as_stream(stream), "mlp_fused_jadj");
 }

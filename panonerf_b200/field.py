@@ -337,20 +337,65 @@ def fused_pack(names: List[str], params) -> dict:
     return slot
 
 
-def fused_forward(enc, vb, S, C, pack, acts, g_enc):
+_mask_scratch: Dict[str, torch.Tensor] = {}
+
+
+def fused_masks(M: int, dev, per_tile: bool) -> torch.Tensor:
+    """Sign bit-plane buffer of the fused kernels: one record per 128-sample tile when the backward kernels will
+    read it, otherwise a per-device scratch that only the in-kernel Jacobian sweep reads back."""
+    words = int(_lib.lib().pnb_mlp_fused_mask_words(M, 1 if per_tile else 0))
+    if per_tile:
+        return torch.empty(words, device=dev, dtype=torch.int32)
+    key = str(dev)
+    if key not in _mask_scratch:
+        _mask_scratch[key] = torch.empty(words, device=dev, dtype=torch.int32)
+    return _mask_scratch[key]
+
+
+def fused_forward(enc, vb, S, C, pack, acts, g_enc, masks=None, masks_per_tile=False):
     """Launch the fused kernel on bf16 IPE features `enc` [M,96]; returns (raw_den, raw_rgb)."""
     M = enc.shape[0]
     dev = enc.device
     raw_den = torch.empty(M, C, device=dev, dtype=torch.float32)
     raw_rgb = torch.empty(M, 3, device=dev, dtype=torch.float32)
+    if g_enc is not None and masks is None:
+        masks = fused_masks(M, dev, False)
     flops = M * (2 * (96 * 256 + 6 * 256 * 256 + 352 * 256 + 256 * C + 256 * 256 + 256 * 128 + 128 * 3)
                  + (2 * (6 * 256 * 256 + 2 * 96 * 256) if g_enc is not None else 0))
     nbytes = M * (192 + 4 * C + 12 + (384 if g_enc is not None else 0)
                   + (512 * (10 + (8 if g_enc is not None else 0)) if acts is not None else 0))
     with torch.cuda.device(dev), _prof("mlp_fused", nbytes, flops):
         check(_lib.lib().pnb_mlp_fused_fwd(M, S, C, _p(enc), _ld(enc), _p(pack["wblob"]), _p(pack["bblob"]), _p(vb),
-                                           _p(raw_den), _p(raw_rgb), _p(acts), _p(g_enc), _stream()), "mlp_fused_fwd")
+                                           _p(raw_den), _p(raw_rgb), _p(acts), _p(g_enc), _p(masks),
+                                           1 if masks_per_tile else 0, _stream()), "mlp_fused_fwd")
     return raw_den, raw_rgb
+
+
+def fused_backward(M, C, pack, d_rgb, d_den, masks, d_enc):
+    """dgrad chain of the backward pass in one kernel -> dz planes bf16 [10, M, 256] (include/panonerf_b200.h)."""
+    dev = d_rgb.device
+    planes = int(_lib.lib().pnb_mlp_fused_bwd_planes())
+    dz = torch.empty(planes, M, 256, device=dev, dtype=torch.bfloat16)
+    flops = M * 2 * (128 * 256 + 256 * 256 + 7 * 256 * 256 + 2 * 96 * 256)
+    nbytes = M * (12 + 4 * C + 288 + 512 * planes + (768 if d_enc is not None else 0))
+    with torch.cuda.device(dev), _prof("mlp_fused_bwd", nbytes, flops):
+        check(_lib.lib().pnb_mlp_fused_bwd(M, C, _p(pack["wblob"]), _p(pack["bblob"]), _p(d_rgb), _p(d_den), _p(masks),
+                                           _p(dz), _p(d_enc), _stream()), "mlp_fused_bwd")
+    return dz
+
+
+def fused_jadj(u, pack, masks):
+    """Adjoint (forward-mode) sweep of the density Jacobian in one kernel -> q planes bf16 [8, M, 256]."""
+    M = u.shape[0]
+    dev = u.device
+    planes = int(_lib.lib().pnb_mlp_fused_adj_planes())
+    q = torch.empty(planes, M, 256, device=dev, dtype=torch.bfloat16)
+    flops = M * 2 * (96 * 256 + 6 * 256 * 256 + 352 * 256)
+    nbytes = M * (192 + 256 + 512 * planes)
+    with torch.cuda.device(dev), _prof("mlp_fused_jadj", nbytes, flops):
+        check(_lib.lib().pnb_mlp_fused_jadj(M, _p(u), _ld(u), _p(pack["wblob"]), _p(masks), _p(q), _stream()),
+              "mlp_fused_jadj")
+    return q
 
 
 def make_backend(precision: str, params: Dict[str, torch.Tensor]):
@@ -418,7 +463,8 @@ class _Field(torch.autograd.Function):
             planes = int(_lib.lib().pnb_mlp_fused_act_planes())
             acts = torch.empty(planes, M, width, device=dev, dtype=dt) if need_bwd else None
             g_enc = torch.empty(M, xyz, device=dev, dtype=f32) if cfg["with_normals"] else None
-            raw_den, raw_rgb = fused_forward(enc, vb, S, C, pack, acts, g_enc)
+            masks = fused_masks(M, dev, True) if need_bwd else None
+            raw_den, raw_rgb = fused_forward(enc, vb, S, C, pack, acts, g_enc, masks, need_bwd)
             n_raw, jac = None, None
             if cfg["with_normals"]:
                 v = ops.ipe_vjp(means2, covs2, cfg["min_deg"], cfg["max_deg"], g_enc)
@@ -436,7 +482,7 @@ class _Field(torch.autograd.Function):
             if need_bwd:
                 ctx.bufs = dict(means=means2, covs=covs2, venc=venc, enc=enc, hs=[acts[i] for i in range(depth)],
                                 bott=acts[8], hv=acts[9][:, :wv.shape[0]], vb_rows=venc.shape[0], raw_den=raw_den,
-                                jac=jac)
+                                jac=jac, masks=masks, pack=pack, fused=not os.environ.get("PNB_NO_FUSED_BWD"))
             else:
                 ctx.bufs = None
             ctx.params = params
@@ -519,8 +565,92 @@ class _Field(torch.autograd.Function):
         return raw_rgb, raw_den, n_raw
 
     @staticmethod
+    def _backward_fused(ctx, d_raw_rgb, d_raw_den, d_n_raw):
+        """Backward of the fused forward: the dgrad chain and the adjoint Jacobian sweep each run as one fused kernel
+        (csrc/mlp_fused.cu, programs P_BWD / P_JADJ) that reads the ReLU sign bit-planes and writes the dz / q planes;
+        the weight gradients are then plain reductions over the samples (pnb_wgrad_tc)."""
+        cfg, B = ctx.cfg, ctx.bufs
+        names = cfg["names"]
+        P = dict(zip(names, ctx.params))
+        be = _TCBackend(P)
+        f32be = _F32Backend(P)
+        depth, width, xyz = cfg["depth"], cfg["width"], cfg["xyz_dim"]
+        S = cfg["samples_per_ray"]
+        enc, hs, bott, hv, raw_den = B["enc"], B["hs"], B["bott"], B["hv"], B["raw_den"]
+        means, covs, venc, masks, pack = B["means"], B["covs"], B["venc"], B["masks"], B["pack"]
+        M = means.shape[0]
+        dev, f32 = means.device, torch.float32
+        C = raw_den.shape[1]
+        sizes = [p.numel() for p in ctx.params]
+        flat = torch.zeros(sum(sizes), device=dev, dtype=f32)
+        G, off = {}, 0
+        for nme, p, sz in zip(names, ctx.params, sizes):
+            G[nme] = flat[off:off + sz].view_as(p)
+            off += sz
+        W = lambda i: f"layers.{i}.0.weight"
+        d_raw_den = torch.zeros(M, C, device=dev, dtype=f32) if d_raw_den is None else d_raw_den.contiguous().clone()
+        d_raw_rgb = torch.zeros(M, 3, device=dev, dtype=f32) if d_raw_rgb is None else d_raw_rgb.contiguous()
+
+        # ---- adjoint of the Jacobian sweep (second-order terms of the normals) -------------------------------
+        if B["jac"] is not None and d_n_raw is not None:
+            a, v = B["jac"]
+            d_n_raw = d_n_raw.contiguous()
+            d_raw0 = torch.empty(M, device=dev, dtype=f32)
+            d_v = torch.empty(M, 3, device=dev, dtype=f32)
+            with torch.cuda.device(dev):
+                check(_lib.lib().pnb_density_grad_bwd(M, C, _p(raw_den), float(cfg["density_bias"]), _p(v), _p(d_n_raw),
+                                                      _p(d_raw0), _p(d_v), _stream()), "density_grad_bwd")
+            d_raw_den[:, 0] += d_raw0
+            u = torch.empty(M, xyz, device=dev, dtype=torch.bfloat16)
+            ops.ipe_jvp_into(means, covs, cfg["min_deg"], cfg["max_deg"], d_v, u)
+            q = fused_jadj(u, pack, masks)
+            be.wgrad(a[0], u, G[W(0)])
+            for i in range(1, depth):
+                if i == 5:
+                    be.wgrad(a[i], q[i - 1], G[W(i)][:, :width])
+                    be.wgrad(a[i], u, G[W(i)][:, width:])
+                else:
+                    be.wgrad(a[i], q[i - 1], G[W(i)])
+            _colsum(q[depth - 1], G["density_layer.weight"][0])
+            del q, u
+
+        # ---- dgrad chain ------------------------------------------------------------------------------------
+        need_enc = ctx.need_means
+        d_enc = torch.empty(M, xyz, device=dev, dtype=f32) if need_enc else None
+        dz = fused_backward(M, C, pack, d_raw_rgb, d_raw_den, masks, d_enc)
+        dzv, d_bott = dz[0][:, :hv.shape[1]], dz[1]
+        dzl = lambda i: dz[9 - i]
+        # ---- weight / bias gradients ------------------------------------------------------------------------
+        _colsum(d_raw_rgb, G["color_layer.bias"])
+        be.wgrad_small(d_raw_rgb, hv, G["color_layer.weight"])
+        be.wgrad(dzv, bott, G["view_layers.0.0.weight"][:, :width])
+        dvb = _group_sum(dzv, S)
+        _colsum(dvb, G["view_layers.0.0.bias"])
+        f32be.wgrad(dvb, venc, G["view_layers.0.0.weight"][:, width:])
+        be.wgrad(d_bott, hs[depth - 1], G["extra_layer.weight"])
+        _colsum(d_bott, G["extra_layer.bias"])
+        _colsum(d_raw_den, G["density_layer.bias"])
+        be.wgrad_small(d_raw_den, hs[depth - 1], G["density_layer.weight"])
+        for i in range(depth - 1, 0, -1):
+            if i == 5:
+                be.wgrad(dzl(i), hs[i - 1], G[W(i)][:, :width])
+                be.wgrad(dzl(i), enc, G[W(i)][:, width:])
+            else:
+                be.wgrad(dzl(i), hs[i - 1], G[W(i)])
+            _colsum(dzl(i), G[f"layers.{i}.0.bias"])
+        be.wgrad(dzl(0), enc, G[W(0)])
+        _colsum(dzl(0), G["layers.0.0.bias"])
+        d_means = None
+        if need_enc:
+            d_means = ops.ipe_vjp(means, covs, cfg["min_deg"], cfg["max_deg"], d_enc).view(ctx.means_shape)
+        ctx.bufs = None
+        return (d_means, None, None, None) + tuple(G[n] for n in names)
+
+    @staticmethod
     def backward(ctx, d_raw_rgb, d_raw_den, d_n_raw):
         cfg, B = ctx.cfg, ctx.bufs
+        if B.get("fused"):
+            return _Field._backward_fused(ctx, d_raw_rgb, d_raw_den, d_n_raw)
         names = cfg["names"]
         P = dict(zip(names, ctx.params))
         be = make_backend(cfg["precision"], P)

@@ -32,14 +32,30 @@ def main():
     g_enc = torch.empty(M, 96, device=dev) if normals else None
     flops = M * (2 * (96 * 256 + 6 * 256 * 256 + 352 * 256 + 256 * C + 256 * 256 + 256 * 128 + 128 * 3)
                  + (2 * (6 * 256 * 256 + 2 * 96 * 256) if normals else 0))
+    masks = field.fused_masks(M, dev, save)
+    kernel = "mlp_fused"
+    run = lambda: field.fused_forward(enc, vb, S, C, pack, acts, g_enc, masks, save)
+    if "--bwd" in sys.argv or "--jadj" in sys.argv:
+        masks = field.fused_masks(M, dev, True)
+        field.fused_forward(enc, vb, S, C, pack, None, None, masks, True)        # real sign bits
+        if "--bwd" in sys.argv:
+            d_rgb, d_den = torch.randn(M, 3, device=dev), torch.randn(M, C, device=dev)
+            d_enc = torch.empty(M, 96, device=dev)
+            flops = M * 2 * (128 * 256 + 256 * 256 + 7 * 256 * 256 + 2 * 96 * 256)
+            kernel = "mlp_fused_bwd"
+            run = lambda: field.fused_backward(M, C, pack, d_rgb, d_den, masks, d_enc)
+        else:
+            flops = M * 2 * (96 * 256 + 6 * 256 * 256 + 352 * 256)
+            kernel = "mlp_fused_jadj"
+            run = lambda: field.fused_jadj(enc, pack, masks)
     for _ in range(3):
-        field.fused_forward(enc, vb, S, C, pack, acts, g_enc)
+        run()
     torch.cuda.synchronize()
     times = []
     for _ in range(5):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        field.fused_forward(enc, vb, S, C, pack, acts, g_enc)
+        run()
         e1.record()
         torch.cuda.synchronize()
         times.append(e0.elapsed_time(e1))
@@ -49,7 +65,7 @@ def main():
     if os.path.exists(pp):
         peaks = json.load(open(pp))
     tf = flops / ms / 1e9
-    print(json.dumps({"kernel": "mlp_fused", "samples": M, "normals": normals, "save": save, "ms": ms,
+    print(json.dumps({"kernel": kernel, "samples": M, "normals": normals, "save": save, "ms": ms,
                       "tflops": tf, "frac_of_burst_peak": tf / peaks.get("bf16_tflops", 1685.0),
                       "samples_per_s": M / ms * 1e3, "all_ms": times}))
 
