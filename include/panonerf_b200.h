@@ -186,6 +186,16 @@ int pnb_linear_tc(long long M, int Nout, int K, const void* A, int lda, const vo
 long long pnb_wgrad_tc_workspace(int Nw, int Kw);
 int pnb_wgrad_tc(long long M, int Nw, int Kw, const void* dZ, int ldz, const void* X, int ldx, float* dW, int ldw,
                  float* workspace, void* stream);
+/* All weight (and bias) gradients of one backward pass in one launch: job j computes
+ * dW_j[Nw,Kw] += Z_j^T X_j and, when want_colsum, db_j[Nw] += column sums of Z_j over the M samples.
+ * map_base: HOST array of n_maps DEVICE pointers to bf16 tensors [planes][M][ld]; map_desc: HOST int64 [n_maps][3] =
+ * {planes, ld, cols}.  jobs: HOST int64 [n_jobs][8] = {zmap, zplane, xmap, xplane, Nw, Kw, ldw, want_colsum};
+ * dW / db: HOST arrays of n_jobs DEVICE pointers (db entries may be null).  Nw in {128,256}, 16 <= Kw <= 256, Kw%16==0.
+ * workspace: pnb_wgrad_batch_workspace() bytes.  Partials are summed in a fixed order (deterministic). */
+long long pnb_wgrad_batch_workspace(void);
+int pnb_wgrad_batch(long long M, int n_maps, const void* const* map_base, const long long* map_desc, int n_jobs,
+                    const long long* jobs, const void* const* dW, const void* const* db, float* workspace,
+                    void* stream);
 /* ---- fused MLP (the whole network of models/pano_mip_nerf.py:78-114 per 128-sample tile in one kernel) ------
  * Weights are consumed from a packed blob of bf16 tiles (pre-swizzled shared-memory images, in MMA order) that
  * pnb_mlp_fused_pack builds from the 24 fp32 parameters; `params_host` is a HOST array of 24 DEVICE pointers in

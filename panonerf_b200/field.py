@@ -398,6 +398,53 @@ def fused_jadj(u, pack, masks):
     return q
 
 
+class WgradBatch:
+    """Collects the weight-gradient GEMMs (and bias column sums) of one backward pass and runs them as ONE launch
+    of pnb_wgrad_batch (csrc/wgrad_batch.cu)."""
+
+    def __init__(self, M: int, dev):
+        self.M, self.dev = M, dev
+        self.maps, self.map_ids, self.jobs, self.keep = [], {}, [], []
+
+    def _map(self, t: torch.Tensor) -> int:
+        assert t.dtype == torch.bfloat16 and t.stride(-1) == 1 and t.shape[-2] == self.M
+        key = (t.data_ptr(), tuple(t.shape), t.stride(-2))
+        if key not in self.map_ids:
+            planes = t.shape[0] if t.dim() == 3 else 1
+            if t.dim() == 3:
+                assert t.stride(0) == t.shape[1] * t.stride(1)
+            self.map_ids[key] = len(self.maps)
+            self.maps.append((t, planes, t.stride(-2), t.shape[-1]))
+        return self.map_ids[key]
+
+    def add(self, z, zplane, nw, x, xplane, kw, dW, db=None):
+        """dW[nw,kw] += z[zplane][:, :nw]^T x[xplane][:, :kw];  db[nw] += column sums of z[zplane][:, :nw]."""
+        assert dW.dtype == torch.float32 and dW.stride(1) == 1 and tuple(dW.shape) == (nw, kw)
+        self.jobs.append((self._map(z), zplane, self._map(x), xplane, nw, kw, dW.stride(0), dW, db))
+
+    def launch(self):
+        if not self.jobs:
+            return
+        lib = _lib.lib()
+        key = "wb" + str(self.dev)
+        if key not in _ws_cache:
+            _ws_cache[key] = torch.empty(int(lib.pnb_wgrad_batch_workspace()) // 4, device=self.dev,
+                                         dtype=torch.float32)
+        nm, nj = len(self.maps), len(self.jobs)
+        base = (ctypes.c_void_p * nm)(*[m[0].data_ptr() for m in self.maps])
+        desc = (ctypes.c_longlong * (3 * nm))(*[v for m in self.maps for v in (m[1], m[2], m[3])])
+        jobs = (ctypes.c_longlong * (8 * nj))(*[v for j in self.jobs
+                                                for v in (j[0], j[1], j[2], j[3], j[4], j[5], j[6],
+                                                          1 if j[8] is not None else 0)])
+        dW = (ctypes.c_void_p * nj)(*[j[7].data_ptr() for j in self.jobs])
+        db = (ctypes.c_void_p * nj)(*[(j[8].data_ptr() if j[8] is not None else None) for j in self.jobs])
+        nbytes = sum(self.M * 2 * (j[4] + j[5]) for j in self.jobs)
+        flops = sum(2 * self.M * j[4] * j[5] for j in self.jobs)
+        with torch.cuda.device(self.dev), _prof("wgrad_batch", nbytes, flops):
+            check(lib.pnb_wgrad_batch(self.M, nm, base, desc, nj, jobs, dW, db, _p(_ws_cache[key]), _stream()),
+                  "wgrad_batch")
+
+
 def make_backend(precision: str, params: Dict[str, torch.Tensor]):
     if precision == "fp32":
         return _F32Backend(params)
@@ -482,7 +529,8 @@ class _Field(torch.autograd.Function):
             if need_bwd:
                 ctx.bufs = dict(means=means2, covs=covs2, venc=venc, enc=enc, hs=[acts[i] for i in range(depth)],
                                 bott=acts[8], hv=acts[9][:, :wv.shape[0]], vb_rows=venc.shape[0], raw_den=raw_den,
-                                jac=jac, masks=masks, pack=pack, fused=not os.environ.get("PNB_NO_FUSED_BWD"))
+                                jac=jac, masks=masks, pack=pack, acts=acts,
+                                fused=not os.environ.get("PNB_NO_FUSED_BWD"))
             else:
                 ctx.bufs = None
             ctx.params = params
@@ -577,9 +625,10 @@ class _Field(torch.autograd.Function):
         depth, width, xyz = cfg["depth"], cfg["width"], cfg["xyz_dim"]
         S = cfg["samples_per_ray"]
         enc, hs, bott, hv, raw_den = B["enc"], B["hs"], B["bott"], B["hv"], B["raw_den"]
-        means, covs, venc, masks, pack = B["means"], B["covs"], B["venc"], B["masks"], B["pack"]
+        means, covs, venc, masks, pack, acts = B["means"], B["covs"], B["venc"], B["masks"], B["pack"], B["acts"]
         M = means.shape[0]
         dev, f32 = means.device, torch.float32
+        wb = WgradBatch(M, dev)
         C = raw_den.shape[1]
         sizes = [p.numel() for p in ctx.params]
         flat = torch.zeros(sum(sizes), device=dev, dtype=f32)
@@ -604,42 +653,46 @@ class _Field(torch.autograd.Function):
             u = torch.empty(M, xyz, device=dev, dtype=torch.bfloat16)
             ops.ipe_jvp_into(means, covs, cfg["min_deg"], cfg["max_deg"], d_v, u)
             q = fused_jadj(u, pack, masks)
-            be.wgrad(a[0], u, G[W(0)])
+            # dW_i += a_i^T q_{i-1}  (q_{-1} = u; layer 5 also sees u through the skip connection)
+            wb.add(acts, 10, 256, u, 0, xyz, G[W(0)])
             for i in range(1, depth):
                 if i == 5:
-                    be.wgrad(a[i], q[i - 1], G[W(i)][:, :width])
-                    be.wgrad(a[i], u, G[W(i)][:, width:])
+                    wb.add(acts, 10 + i, 256, q, i - 1, width, G[W(i)][:, :width])
+                    wb.add(acts, 10 + i, 256, u, 0, xyz, G[W(i)][:, width:])
                 else:
-                    be.wgrad(a[i], q[i - 1], G[W(i)])
-            _colsum(q[depth - 1], G["density_layer.weight"][0])
-            del q, u
+                    wb.add(acts, 10 + i, 256, q, i - 1, width, G[W(i)])
+            # d w_sigma += column sums of q_7 (a_7 = relu'(h_7) * w_sigma): rides on a minimal dummy product
+            scratch = torch.zeros(256, 16, device=dev, dtype=f32)
+            wb.add(q, depth - 1, 256, u, 0, 16, scratch, G["density_layer.weight"][0])
 
         # ---- dgrad chain ------------------------------------------------------------------------------------
         need_enc = ctx.need_means
         d_enc = torch.empty(M, xyz, device=dev, dtype=f32) if need_enc else None
         dz = fused_backward(M, C, pack, d_raw_rgb, d_raw_den, masks, d_enc)
-        dzv, d_bott = dz[0][:, :hv.shape[1]], dz[1]
-        dzl = lambda i: dz[9 - i]
-        # ---- weight / bias gradients ------------------------------------------------------------------------
+        dzv = dz[0][:, :hv.shape[1]]
+        # ---- weight / bias gradients: one batched launch -----------------------------------------------------
+        wc = hv.shape[1]
         _colsum(d_raw_rgb, G["color_layer.bias"])
-        be.wgrad_small(d_raw_rgb, hv, G["color_layer.weight"])
-        be.wgrad(dzv, bott, G["view_layers.0.0.weight"][:, :width])
-        dvb = _group_sum(dzv, S)
-        _colsum(dvb, G["view_layers.0.0.bias"])
-        f32be.wgrad(dvb, venc, G["view_layers.0.0.weight"][:, width:])
-        be.wgrad(d_bott, hs[depth - 1], G["extra_layer.weight"])
-        _colsum(d_bott, G["extra_layer.bias"])
+        pad_rgb, pad_den = be._pad64(d_raw_rgb), be._pad64(d_raw_den)
+        tmp_c = torch.zeros(wc, 64, device=dev, dtype=f32)
+        tmp_d = torch.zeros(width, 64, device=dev, dtype=f32)
+        wb.add(acts, 9, wc, pad_rgb, 0, 64, tmp_c)                      # (hv^T d_rgb): colour head, transposed
+        wb.add(dz, 0, wc, acts, 8, width, G["view_layers.0.0.weight"][:, :width], G["view_layers.0.0.bias"])
+        wb.add(dz, 1, 256, acts, 7, width, G["extra_layer.weight"], G["extra_layer.bias"])
         _colsum(d_raw_den, G["density_layer.bias"])
-        be.wgrad_small(d_raw_den, hs[depth - 1], G["density_layer.weight"])
+        wb.add(acts, 7, 256, pad_den, 0, 64, tmp_d)                     # (h7^T d_den): density head, transposed
         for i in range(depth - 1, 0, -1):
             if i == 5:
-                be.wgrad(dzl(i), hs[i - 1], G[W(i)][:, :width])
-                be.wgrad(dzl(i), enc, G[W(i)][:, width:])
+                wb.add(dz, 9 - i, 256, acts, i - 1, width, G[W(i)][:, :width], G[f"layers.{i}.0.bias"])
+                wb.add(dz, 9 - i, 256, enc, 0, xyz, G[W(i)][:, width:])
             else:
-                be.wgrad(dzl(i), hs[i - 1], G[W(i)])
-            _colsum(dzl(i), G[f"layers.{i}.0.bias"])
-        be.wgrad(dzl(0), enc, G[W(0)])
-        _colsum(dzl(0), G["layers.0.0.bias"])
+                wb.add(dz, 9 - i, 256, acts, i - 1, width, G[W(i)], G[f"layers.{i}.0.bias"])
+        wb.add(dz, 9, 256, enc, 0, xyz, G[W(0)], G["layers.0.0.bias"])
+        wb.launch()
+        G["color_layer.weight"].add_(tmp_c[:, :3].t())
+        G["density_layer.weight"].add_(tmp_d[:, :C].t())
+        dvb = _group_sum(dzv, S)
+        f32be.wgrad(dvb, venc, G["view_layers.0.0.weight"][:, width:])
         d_means = None
         if need_enc:
             d_means = ops.ipe_vjp(means, covs, cfg["min_deg"], cfg["max_deg"], d_enc).view(ctx.means_shape)
