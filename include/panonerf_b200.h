@@ -210,6 +210,9 @@ int pnb_mlp_fused_adj_planes(void);
 /* 32-bit words of the ReLU sign bit-plane buffer: per_tile = 1 -> one record per 128-sample tile of an M-sample
  * batch (what the backward kernels read), per_tile = 0 -> a per-CTA scratch (inference with normals). */
 long long pnb_mlp_fused_mask_words(long long M, int per_tile);
+/* static ring plan of program `prog` (0 fwd, 1 fwd+Jacobian, 2 bwd, 3 adjoint): out[0] = weight/IPE tile loads per
+ * pair of 128-sample tiles, out[1] = MMA steps per pair, then {slot, is_enc, tile, blob_off} per load. */
+int pnb_mlp_fused_plan(int prog, long long* out, int cap);
 int pnb_mlp_fused_pack(const void* const* params_host, int C, void* wblob, float* bblob, void* stream);
 /* enc: bf16 [M,96] IPE features (row stride ld_enc); row_bias: fp32 [ceil(M/S),128] per-ray view-direction term
  * (incl. the view-layer bias); outputs raw_den fp32 [M,C], raw_rgb fp32 [M,3].

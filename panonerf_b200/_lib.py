@@ -13,7 +13,7 @@ from typing import Dict, List, Tuple
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 HEADER = os.path.join(os.path.dirname(HERE), "include", "panonerf_b200.h")
-LIB_PATH = os.path.join(HERE, "libpanonerf_b200.so")
+LIB_PATH = os.environ.get("PNB_LIB_PATH") or os.path.join(HERE, "libpanonerf_b200.so")   # (override: A/B experiments)
 
 PNB_F32, PNB_BF16 = 0, 1
 EPI_BIAS, EPI_RELU, EPI_MASK, EPI_ACCUM = 1, 2, 4, 8

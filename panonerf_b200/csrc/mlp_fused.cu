@@ -41,7 +41,7 @@ constexpr int kSlotBytes = 32768;  // ring slot: a weight tile of up to 256 rows
 constexpr int kKbBytes = 16384;    // one k-block: 128 rows x 64 bf16, 128B-swizzled
 constexpr int kAbufBytes = 4 * kKbBytes;
 constexpr int kFThreads = 320;
-constexpr int kMaxSteps = 80, kMaxOps = 24, kMaxPack = 160, kFMaxStages = 3;
+constexpr int kMaxSteps = 80, kMaxOps = 24, kMaxPack = 160, kSlots = 3, kMaxLoads = 2 * 80 + 16;
 constexpr int kNumParams = 12;  // weights (and biases) in state-dict order: layers 0..7, density, extra, view, colour
 constexpr int kActPlanes = 18, kBwdPlanes = 10, kAdjPlanes = 8;
 constexpr int kMaskPlanes = 9;  // ReLU sign bits: trunk layers 0..7, view layer
@@ -93,10 +93,22 @@ struct Op {
   int16_t bias_off;
   int8_t mask_plane, save_plane, nunits, pad;
 };
+// Ring-slot plan of one step for one of the two tiles (static: see plan_ring below).
+struct Use {
+  int8_t w_slot, w_load, w_rel;  // weight tile: slot, wait for a fresh load first, release the slot afterwards
+  int8_t e_slot, e_load, e_rel;  // IPE tile of this (op, tile) for F_AENC steps
+  int8_t first, pad;             // first executed step of its op: the MMA overwrites the accumulator
+};
+struct LoadRec {                 // the producer's program: loads in the order the MMA warp needs them
+  uint32_t blob_off, bytes;
+  int8_t slot, is_enc, t, pad;
+};
 struct Prog {
   Step steps[kMaxSteps];
   Op ops[kMaxOps];
-  int n_steps, n_ops;
+  Use uses[2][kMaxSteps];
+  LoadRec loads[kMaxLoads];
+  int n_steps, n_ops, n_loads;
 };
 struct Sched {
   Prog prog[kNumProgs];
@@ -128,8 +140,8 @@ struct FusedParams {
 };
 
 struct FBarriers {
-  uint64_t full[kFMaxStages];
-  uint64_t empty[kFMaxStages];
+  uint64_t full[kSlots];
+  uint64_t empty[kSlots];
   uint64_t abuf_ready[2];
   uint64_t acc_full[2];
   uint32_t tmem_base;
@@ -227,6 +239,93 @@ struct Builder {
   }
 };
 
+// Static plan of the 3-slot weight ring for one pair of tiles.  Tile 0 walks the k-blocks of an op forwards, tile 1
+// backwards, so the tiles that tile 0 touched last are still resident when tile 1 starts: 5 loads instead of 8 per
+// 256x256 layer and pair.  Replacement is Belady's rule on the known future (dead tiles first, oldest first), every
+// slot is released at its last use so the producer can refill it two steps ahead, and all slots are free again at
+// the end of the pair (the plan repeats verbatim for the next pair).
+#ifndef PNB_RING_MODE
+#define PNB_RING_MODE 0  // 0: FIFO, no reuse, both tiles forwards; 1: reuse, both forwards; 2: reuse, tile 1 backwards
+#endif
+constexpr void plan_ring(Prog& g) {
+  // events in execution order
+  int ev_op[2 * kMaxSteps] = {}, ev_t[2 * kMaxSteps] = {}, ev_s[2 * kMaxSteps] = {};
+  int n_ev = 0;
+  for (int o = 0; o < g.n_ops; ++o) {
+    const int s0 = g.ops[o].s0, s1 = g.ops[o].s1;
+    for (int t = 0; t < 2; ++t)
+      for (int k = 0; k < s1 - s0; ++k) {
+        const int sidx = (t == 0 || PNB_RING_MODE < 2) ? s0 + k : s1 - 1 - k;
+        ev_op[n_ev] = o, ev_t[n_ev] = t, ev_s[n_ev] = sidx;
+        g.uses[t][sidx] = Use{};
+        g.uses[t][sidx].first = (int8_t)(k == 0);
+        ++n_ev;
+      }
+  }
+  // content ids: weights = blob offset + 1 (> 0); IPE tile of (op, t) = -(2 * op + t + 1)
+  auto wid = [&](int e) {
+    return PNB_RING_MODE == 0 ? (long long)(e + 1) * (1ll << 32) : (long long)g.steps[ev_s[e]].blob_off + 1;
+  };
+  auto eid = [&](int e) {
+    return (g.steps[ev_s[e]].flags & F_AENC) ? -(long long)(2 * ev_op[e] + ev_t[e] + 1) : 0ll;
+  };
+  long long content[kSlots] = {};
+  int last_ev[kSlots] = {}, last_kind[kSlots] = {};  // last use of the slot's content: event, 0 = weight / 1 = IPE
+  for (int k = 0; k < kSlots; ++k) last_ev[k] = -1;
+  g.n_loads = 0;
+  for (int e = 0; e < n_ev; ++e) {
+    Use& u = g.uses[ev_t[e]][ev_s[e]];
+    const long long need[2] = {eid(e), wid(e)};
+    int slot_of[2] = {-1, -1};
+    for (int n = 0; n < 2; ++n) {
+      if (need[n] == 0) continue;
+      int slot = -1;
+      for (int k = 0; k < kSlots; ++k)
+        if (content[k] == need[n]) slot = k;
+      bool load = false;
+      if (slot < 0) {
+        load = true;
+        // victim: empty slot, else a dead tile (no later use; oldest last use first), else the farthest next use
+        int best = -1;
+        long long best_key = -1;
+        for (int k = 0; k < kSlots; ++k) {
+          if (k == slot_of[0]) continue;  // never the IPE tile of this very step
+          long long key = 0;
+          if (content[k] == 0) {
+            key = (1ll << 40);
+          } else {
+            int next = -1;
+            for (int f = e; f < n_ev && next < 0; ++f)
+              if (wid(f) == content[k] || eid(f) == content[k]) next = f;
+            key = next < 0 ? (1ll << 30) - last_ev[k] : next;
+          }
+          if (key > best_key) best_key = key, best = k;
+        }
+        slot = best;
+        if (content[slot] != 0) {  // the previous tenant leaves at its last use
+          Use& pu = g.uses[ev_t[last_ev[slot]]][ev_s[last_ev[slot]]];
+          if (last_kind[slot] == 0) pu.w_rel = 1;
+          else pu.e_rel = 1;
+        }
+        content[slot] = need[n];
+        LoadRec& l = g.loads[g.n_loads++];
+        l.slot = (int8_t)slot, l.is_enc = (int8_t)(n == 0), l.t = (int8_t)ev_t[e];
+        l.blob_off = g.steps[ev_s[e]].blob_off, l.bytes = g.steps[ev_s[e]].bytes;
+      }
+      slot_of[n] = slot;
+      last_ev[slot] = e, last_kind[slot] = n == 0 ? 1 : 0;
+      if (n == 0) u.e_slot = (int8_t)slot, u.e_load = (int8_t)load;
+      else u.w_slot = (int8_t)slot, u.w_load = (int8_t)load;
+    }
+  }
+  for (int k = 0; k < kSlots; ++k)
+    if (content[k] != 0) {
+      Use& pu = g.uses[ev_t[last_ev[k]]][ev_s[last_ev[k]]];
+      if (last_kind[k] == 0) pu.w_rel = 1;
+      else pu.e_rel = 1;
+    }
+}
+
 constexpr Sched make_sched() {
   Builder b{};
   const int W_DEN = 8, W_EXTRA = 9, W_VIEW = 10, W_COL = 11;
@@ -275,12 +374,15 @@ constexpr Sched make_sched() {
     b.op(P, g0, E_G0, 0, 0, -1, -1, 0);
   }
   for (int i = 0; i < 8; ++i) b.trunk_layer(P_JADJ, i, E_MASK, i);
+  for (int P = 0; P < kNumProgs; ++P) plan_ring(b.s.prog[P]);
   return b.s;
 }
 constexpr Sched kSched = make_sched();
 static_assert(kSched.n_pack <= kMaxPack, "pack table");
 static_assert(kSched.prog[P_FWDJ].n_steps <= kMaxSteps && kSched.prog[P_FWDJ].n_ops <= kMaxOps, "schedule tables");
 static_assert(kSched.prog[P_BWD].n_steps <= kMaxSteps && kSched.prog[P_BWD].n_ops <= kMaxOps, "schedule tables");
+static_assert(kSched.prog[P_FWDJ].n_loads <= kMaxLoads, "load table");
+static_assert(1024 + 2 * kAbufBytes + kSlots * kSlotBytes + sizeof(FBarriers) <= (size_t)kSmemLimit, "shared memory budget");
 
 // Bias blob staged in the constant bank before every launch (stream-ordered device-to-device copy): the epilogue's
 // per-column addends are uniform across a warp, so they come through the constant cache / uniform datapath instead of
@@ -375,6 +477,9 @@ __device__ __forceinline__ void tmem_ld32u(uint32_t taddr, uint32_t* r) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // K-major, 128B-swizzled operand descriptor from (shared address >> 4): LBO = 16 B (unused), SBO = 1024 B, version 1
 __device__ __forceinline__ uint64_t desc_from16(uint32_t addr16) {
@@ -390,6 +495,7 @@ struct EpiCtx {
   const CUtensorMap* tmActs;
   uint32_t tacc;            // TMEM address of this tile's accumulator, lane quadrant applied
   uint32_t acc_parity;
+  uint32_t mbits[4];        // sign-bit words of this thread's units for this op (prefetched one op-tile ahead)
   long long m;              // global sample row of this thread
   int q, hf, lane, row, tile_row0;
   bool row_ok, save, skip;
@@ -417,13 +523,9 @@ __device__ __forceinline__ void rewrite_abuf_hf(const EpiCtx& c, const FusedPara
   constexpr int n_mine = (MODE == M_ROWBIAS_RELU || MODE == M_BSEED) ? 2 : 4;  // units per warp (op.nunits / 2)
   constexpr int ub = HF * n_mine;
   // sign-bit words of this thread's units: bit (31 - j) of word u <-> column 32u + j is positive.
-  // Loaded before the accumulator wait: the L2 round trip hides behind the MMAs.
   uint32_t bw[n_mine];
-  if (kAppliesMask) {
-    const uint32_t* mp = c.mask + (op.mask_plane * 8 + ub) * kTileM + c.row;
 #pragma unroll
-    for (int i = 0; i < n_mine; ++i) bw[i] = mp[i * kTileM];
-  }
+  for (int i = 0; i < n_mine; ++i) bw[i] = c.mbits[i];
   float rb[MODE == M_ROWBIAS_RELU ? n_mine : 1][32];
   if (MODE == M_ROWBIAS_RELU) {
 #pragma unroll
@@ -438,7 +540,7 @@ __device__ __forceinline__ void rewrite_abuf_hf(const EpiCtx& c, const FusedPara
   }
   float d0 = 0.f, d1 = 0.f, d2 = 0.f;
   if (MODE == M_BSEED && c.row_ok) d0 = __ldg(p.d_rgb + c.m * 3), d1 = __ldg(p.d_rgb + c.m * 3 + 1), d2 = __ldg(p.d_rgb + c.m * 3 + 2);
-  if (op.has_mma) {
+  if (op.has_mma != 2) {  // (2: the caller has already waited - Jacobian seed after the colour head)
     mbar_wait(c.acc_full, c.acc_parity);
     tc_fence_after();
   }
@@ -451,10 +553,11 @@ __device__ __forceinline__ void rewrite_abuf_hf(const EpiCtx& c, const FusedPara
   uint32_t r[2][32];
   if (kReadsAcc) tmem_ld32u(c.tacc + op.acc_col + ub * 32, r[0]);
   if (c.save) {
-    // TMA stores issued by this warp that still read this tile's buffer (the op before the other tile's) must be
-    // done; at most the other tile's two newer groups may stay pending.
-    if (c.lane == 0) bulk_wait_read<2>();
-    __syncwarp();
+    // The four warps of this half (one per TMEM lane quadrant) store whole 128-row k-blocks together; warp q = 0
+    // issues.  Its TMA stores that still read this tile's buffer (the op before the other tile's) must be done;
+    // at most the other tile's two newer groups may stay pending.
+    if (c.q == 0 && c.lane == 0) bulk_wait_read<2>();
+    named_bar_sync(1 + HF, 128);
   }
 #pragma unroll
   for (int i = 0; i < n_mine; ++i) {
@@ -476,8 +579,13 @@ __device__ __forceinline__ void rewrite_abuf_hf(const EpiCtx& c, const FusedPara
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r[i & 1][j]) + rb[i][j];
       } else if (kAddsAux) {         // + bias (per column)
+        const float4* cb = reinterpret_cast<const float4*>(c_bblob) + ((coff >> 2) + u * 8);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r[i & 1][j]) + c_bblob[coff + u * 32 + j];
+        for (int j = 0; j < 8; ++j) {
+          const float4 t = cb[j];
+          x[4 * j] = __uint_as_float(r[i & 1][4 * j]) + t.x, x[4 * j + 1] = __uint_as_float(r[i & 1][4 * j + 1]) + t.y;
+          x[4 * j + 2] = __uint_as_float(r[i & 1][4 * j + 2]) + t.z, x[4 * j + 3] = __uint_as_float(r[i & 1][4 * j + 3]) + t.w;
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r[i & 1][j]);
@@ -520,12 +628,11 @@ __device__ __forceinline__ void rewrite_abuf_hf(const EpiCtx& c, const FusedPara
     for (int j = 0; j < 4; ++j)
       sts128(dst + (((jb + j) ^ (c.row & 7)) << 4), h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
     if (c.save && (u & 1) && op.save_plane >= 0) {
-      // both halves of k-block u/2 (this warp's 32 rows) are in place: store the 32 x 64 box
+      // both halves of k-block u/2 are in place for all 128 rows: store the 128 x 64 box (16 KB)
       fence_async_smem();
-      __syncwarp();
-      if (c.lane == 0) {
-        tma_store_3d(c.tmActs, c.abuf + (u >> 1) * kKbBytes + c.q * 4096, (u >> 1) * 64, c.tile_row0 + c.q * 32,
-                     op.save_plane);
+      named_bar_sync(1 + HF, 128);
+      if (c.q == 0 && c.lane == 0) {
+        tma_store_3d(c.tmActs, c.abuf + (u >> 1) * kKbBytes, (u >> 1) * 64, c.tile_row0, op.save_plane);
         bulk_commit();
       }
     }
@@ -559,71 +666,79 @@ __device__ __forceinline__ void epi_done(const EpiCtx& c) {
 // ---------------------------------------------------------------------------------------------------------------
 struct MmaCtx {
   FBarriers* bars;
-  int slot, enc_slot, ns;
-  uint32_t ph, ab_ph;
+  uint32_t full_ph, ab_ph;  // per-slot / per-tile phase bits
   uint32_t abuf16, ring16, tmem_base;
   bool prof;
   long long t_ab, t_full;
 };
 
-template <int P, int S>
-__device__ __forceinline__ void mma_step(MmaCtx& c, int t) {
-  constexpr Step st = kSched.prog[P].steps[S];
-  if constexpr ((st.flags & F_LOADENC) != 0) {
-    mbar_wait(&c.bars->full[c.slot], c.ph);
-    c.enc_slot = c.slot;
-    if (++c.slot == c.ns) c.slot = 0, c.ph ^= 1;
-  }
+template <int SLOT>
+__device__ __forceinline__ void mma_wait_slot(MmaCtx& c) {
   if (c.prof) {
     const long long t0 = clock64();
-    mbar_wait(&c.bars->full[c.slot], c.ph);
+    mbar_wait(&c.bars->full[SLOT], (c.full_ph >> SLOT) & 1u);
     c.t_full += clock64() - t0;
   } else {
-    mbar_wait(&c.bars->full[c.slot], c.ph);
+    mbar_wait(&c.bars->full[SLOT], (c.full_ph >> SLOT) & 1u);
   }
+  c.full_ph ^= 1u << SLOT;
+}
+
+template <int P, int S, int T>
+__device__ __forceinline__ void mma_step(MmaCtx& c) {
+  constexpr Step st = kSched.prog[P].steps[S];
+  constexpr Use u = kSched.prog[P].uses[T][S];
+  if constexpr ((st.flags & F_AENC) != 0 && u.e_load != 0) mma_wait_slot<u.e_slot>(c);
+  if constexpr (u.w_load != 0) mma_wait_slot<u.w_slot>(c);
   tc_fence_after();
-  const uint32_t a16 = (((st.flags & F_AENC) != 0) ? c.ring16 + (uint32_t)c.enc_slot * (kSlotBytes >> 4)
-                                                  : c.abuf16 + (uint32_t)t * (kAbufBytes >> 4)) +
+  const uint32_t a16 = (((st.flags & F_AENC) != 0) ? c.ring16 + (uint32_t)u.e_slot * (kSlotBytes >> 4)
+                                                  : c.abuf16 + (uint32_t)T * (kAbufBytes >> 4)) +
                        st.a_off16;
-  const uint32_t b16 = c.ring16 + (uint32_t)c.slot * (kSlotBytes >> 4);
-  const uint32_t d_tmem = c.tmem_base + (uint32_t)t * 256u + st.acc_col;
+  const uint32_t b16 = c.ring16 + (uint32_t)u.w_slot * (kSlotBytes >> 4);
+  const uint32_t d_tmem = c.tmem_base + (uint32_t)T * 256u + st.acc_col;
 #pragma unroll
   for (int k = 0; k < (int)st.nk16; ++k) {
     const uint32_t ak = (uint32_t)((k >> 2) * (kKbBytes >> 4) + (k & 3) * 2);
     const uint32_t bk = (uint32_t)(k >> 2) * st.b_kb16 + (uint32_t)(k & 3) * 2;
-    umma_f16(d_tmem, desc_from16(a16 + ak), desc_from16(b16 + bk), st.idesc,
-             (k == 0 && (st.flags & F_FIRST) != 0) ? 0u : 1u);
+    umma_f16(d_tmem, desc_from16(a16 + ak), desc_from16(b16 + bk), st.idesc, (k == 0 && u.first != 0) ? 0u : 1u);
   }
-  umma_commit(&c.bars->empty[c.slot]);
-  if constexpr ((st.flags & F_RELENC) != 0) umma_commit(&c.bars->empty[c.enc_slot]);
-  if (++c.slot == c.ns) c.slot = 0, c.ph ^= 1;
+  if constexpr (u.w_rel != 0) umma_commit(&c.bars->empty[u.w_slot]);
+  if constexpr ((st.flags & F_AENC) != 0 && u.e_rel != 0) umma_commit(&c.bars->empty[u.e_slot]);
 }
 
-template <int P, int S0, int... S>
-__device__ __forceinline__ void mma_steps(MmaCtx& c, int t, std::integer_sequence<int, S...>) {
-  (mma_step<P, S0 + S>(c, t), ...);
+// tile 0 walks the steps of an op forwards, tile 1 backwards (see plan_ring)
+template <int P, int S0, int N, int T, int... K>
+__device__ __forceinline__ void mma_steps(MmaCtx& c, std::integer_sequence<int, K...>) {
+  (mma_step<P, ((T == 0 || PNB_RING_MODE < 2) ? S0 + K : S0 + N - 1 - K), T>(c), ...);
+}
+
+template <int P, int OP, int T>
+__device__ __forceinline__ void mma_op_tile(MmaCtx& c) {
+  constexpr Op op = kSched.prog[P].ops[OP];
+  // the tile's previous epilogue has drained the accumulator and rewritten the activation buffer
+  if (c.prof) {
+    const long long t0 = clock64();
+    mbar_wait(&c.bars->abuf_ready[T], (c.ab_ph >> T) & 1u);
+    c.t_ab += clock64() - t0;
+  } else {
+    mbar_wait(&c.bars->abuf_ready[T], (c.ab_ph >> T) & 1u);
+  }
+  c.ab_ph ^= 1u << T;
+  if constexpr (op.has_mma != 0) {
+    tc_fence_after();
+    mma_steps<P, op.s0, op.s1 - op.s0, T>(c, std::make_integer_sequence<int, op.s1 - op.s0>{});
+    umma_commit(&c.bars->acc_full[T]);
+  } else {
+    // Epilogue-only op: hand the tile back at once.  The epilogue still waits for this arrival, so it can never
+    // complete two phases of abuf_ready ahead of this thread (a parity wait cannot tell phase n from phase n + 2).
+    mbar_arrive(&c.bars->acc_full[T]);
+  }
 }
 
 template <int P, int OP>
 __device__ __forceinline__ void mma_op(MmaCtx& c) {
-  constexpr Op op = kSched.prog[P].ops[OP];
-#pragma unroll 1
-  for (int t = 0; t < 2; ++t) {
-    // the tile's previous epilogue has drained the accumulator and rewritten the activation buffer
-    if (c.prof) {
-      const long long t0 = clock64();
-      mbar_wait(&c.bars->abuf_ready[t], (c.ab_ph >> t) & 1u);
-      c.t_ab += clock64() - t0;
-    } else {
-      mbar_wait(&c.bars->abuf_ready[t], (c.ab_ph >> t) & 1u);
-    }
-    c.ab_ph ^= 1u << t;
-    if constexpr (op.has_mma != 0) {
-      tc_fence_after();
-      mma_steps<P, op.s0>(c, t, std::make_integer_sequence<int, op.s1 - op.s0>{});
-      umma_commit(&c.bars->acc_full[t]);
-    }
-  }
+  mma_op_tile<P, OP, 0>(c);
+  mma_op_tile<P, OP, 1>(c);
 }
 
 template <int P, int... OPS>
@@ -643,16 +758,15 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmEnc, const __grid_constan
   uint8_t* smem = align_1024(smem_raw);
   uint8_t* abuf = smem;                       // [2 tiles][4 k-blocks]
   uint8_t* ring = abuf + 2 * kAbufBytes;
-  FBarriers* bars = reinterpret_cast<FBarriers*>(ring + (size_t)p.nstages * kSlotBytes);
+  FBarriers* bars = reinterpret_cast<FBarriers*>(ring + (size_t)kSlots * kSlotBytes);
 
   // shuffled so that the compiler knows the warp index (and everything derived from it) is warp-uniform
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  const int NS = p.nstages;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmEnc);
     if (p.save) tma_prefetch_desc(&tmActs);
-    for (int s = 0; s < NS; ++s) {
+    for (int s = 0; s < kSlots; ++s) {
       mbar_init(&bars->full[s], 1);
       mbar_init(&bars->empty[s], 1);
     }
@@ -671,36 +785,27 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmEnc, const __grid_constan
   if (warp == 0) {
     // ================================ producer ==================================================================
     if (lane == 0) {
-      int slot = 0;
-      uint32_t ph = 0;
+      uint32_t eph = 0;  // per-slot phase bits of the empty barriers
       const uint8_t* wblob = p.wblob + (size_t)(blockIdx.x % p.replicas) * p.blob_stride;
+      const int n_loads = c_prog[P].n_loads;
       for (long long pair = blockIdx.x; pair < p.num_pairs; pair += gridDim.x) {
-        for (int o = 0; o < kOps; ++o) {
-          const int s0 = c_prog[P].ops[o].s0, s1 = c_prog[P].ops[o].s1;
-          if (s1 == s0) continue;
-          for (int t = 0; t < 2; ++t) {
-            long long tile = pair * 2 + t;
+        for (int l = 0; l < n_loads; ++l) {
+          const LoadRec ld = c_prog[P].loads[l];
+          const int slot = ld.slot;
+          mbar_wait(&bars->empty[slot], ((eph >> slot) & 1u) ^ 1u);
+          eph ^= 1u << slot;
+          if (ld.is_enc) {
+            long long tile = pair * 2 + ld.t;
             if (tile >= p.num_tiles) tile = p.num_tiles - 1;  // phantom tile of an odd tail: recompute the last one
             const int row0 = (int)(tile * kTileM);
-            for (int s = s0; s < s1; ++s) {
-              const uint32_t blob_off = c_prog[P].steps[s].blob_off;  // (relative to this CTA's copy of the blob)
-              const uint32_t bytes = c_prog[P].steps[s].bytes;
-              if (c_prog[P].steps[s].flags & F_LOADENC) {
-                mbar_wait(&bars->empty[slot], ph ^ 1);
-                mbar_expect_tx(&bars->full[slot], 2 * kKbBytes);
-                tma_load_2d(ring + (size_t)slot * kSlotBytes, &tmEnc, &bars->full[slot], 0, row0);
-                tma_load_2d(ring + (size_t)slot * kSlotBytes + kKbBytes, &tmEnc, &bars->full[slot], 64, row0);
-                if (++slot == NS) slot = 0, ph ^= 1;
-              }
-              mbar_wait(&bars->empty[slot], ph ^ 1);
-              if (p.debug & 1) {  // experiment: no weight traffic (the MMAs read whatever the slot holds)
-                mbar_arrive(&bars->full[slot]);
-              } else {
-                mbar_expect_tx(&bars->full[slot], bytes);
-                bulk_load_1d(ring + (size_t)slot * kSlotBytes, wblob + blob_off, bytes, &bars->full[slot]);
-              }
-              if (++slot == NS) slot = 0, ph ^= 1;
-            }
+            mbar_expect_tx(&bars->full[slot], 2 * kKbBytes);
+            tma_load_2d(ring + (size_t)slot * kSlotBytes, &tmEnc, &bars->full[slot], 0, row0);
+            tma_load_2d(ring + (size_t)slot * kSlotBytes + kKbBytes, &tmEnc, &bars->full[slot], 64, row0);
+          } else if (p.debug & 1) {  // experiment: no weight traffic (the MMAs read whatever the slot holds)
+            mbar_arrive(&bars->full[slot]);
+          } else {
+            mbar_expect_tx(&bars->full[slot], ld.bytes);
+            bulk_load_1d(ring + (size_t)slot * kSlotBytes, wblob + ld.blob_off, ld.bytes, &bars->full[slot]);
           }
         }
       }
@@ -713,7 +818,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmEnc, const __grid_constan
     // dynamic.
     if (lane == 0) {
       MmaCtx mc;
-      mc.bars = bars, mc.slot = 0, mc.enc_slot = 0, mc.ph = 0, mc.ab_ph = 0, mc.ns = NS;
+      mc.bars = bars, mc.full_ph = 0, mc.ab_ph = 0;
       mc.abuf16 = smem_u32(abuf) >> 4, mc.ring16 = smem_u32(ring) >> 4, mc.tmem_base = tmem_base;
       mc.prof = p.prof != nullptr, mc.t_ab = 0, mc.t_full = 0;
       const long long t_start = clock64();
@@ -740,6 +845,23 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmEnc, const __grid_constan
     }
     uint32_t acc_ph = 0;
     long long t_wait = 0;
+    // Sign-bit words are fetched one (op, tile) ahead of their use: the L2 round trip hides behind the previous
+    // epilogue.  (In P_FWDJ the words were written by this very thread several ops earlier.)
+    auto fetch_bits = [&](long long pair, int e, int t) -> uint4 {
+      uint4 out = make_uint4(0u, 0u, 0u, 0u);
+      if (p.masks == nullptr || pair >= p.num_pairs) return out;
+      const int epi = c_prog[P].ops[e].epi;
+      const bool applies = epi == E_MASK || epi == E_BSEED || epi == E_BDZ7 || (epi == E_COLOR && P == P_FWDJ);
+      if (!applies) return out;
+      const int n_mine = c_prog[P].ops[e].nunits >> 1;
+      const long long slot = p.masks_per_tile ? pair * 2 + t : (long long)blockIdx.x * 2 + t;
+      const uint32_t* mp = p.masks + (size_t)slot * kMaskWordsPerTile +
+                           (c_prog[P].ops[e].mask_plane * 8 + c.hf * n_mine) * kTileM + c.row;
+      out.x = mp[0], out.y = mp[kTileM];
+      if (n_mine > 2) out.z = mp[2 * kTileM], out.w = mp[3 * kTileM];
+      return out;
+    };
+    uint4 nbits = fetch_bits(blockIdx.x, 0, 0);
     const long long t_epi0 = clock64();
     for (long long pair = blockIdx.x; pair < p.num_pairs; pair += gridDim.x) {
       for (int e = 0; e < kOps; ++e) {
@@ -756,8 +878,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmEnc, const __grid_constan
           c.tacc = tlane + (uint32_t)t * 256u;
           c.acc_full = &bars->acc_full[t], c.abuf_ready = &bars->abuf_ready[t];
           c.acc_parity = (acc_ph >> t) & 1u;
-          if (op.has_mma) acc_ph ^= 1u << t;
-          if (p.prof != nullptr && op.has_mma) {  // (the real wait inside the epilogue then returns at once)
+          acc_ph ^= 1u << t;
+          if (p.prof != nullptr) {  // (the real wait inside the epilogue then returns at once)
             const long long t0 = clock64();
             mbar_wait(c.acc_full, c.acc_parity);
             t_wait += clock64() - t0;
@@ -765,6 +887,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmEnc, const __grid_constan
           c.mask = p.masks == nullptr
                        ? nullptr
                        : p.masks + (size_t)(p.masks_per_tile ? tile : (long long)blockIdx.x * 2 + t) * kMaskWordsPerTile;
+          c.mbits[0] = nbits.x, c.mbits[1] = nbits.y, c.mbits[2] = nbits.z, c.mbits[3] = nbits.w;
+          if (t == 0) nbits = fetch_bits(pair, e, 1);
+          else if (e + 1 < kOps) nbits = fetch_bits(pair, e + 1, 0);
+          else nbits = fetch_bits(pair + gridDim.x, 0, 0);
           constexpr bool kFwd = P == P_FWD || P == P_FWDJ;
           constexpr bool kChain = P == P_FWDJ || P == P_BWD;
           const int epi = op.epi;
@@ -810,7 +936,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmEnc, const __grid_constan
                   }
                 }
                 Op o2 = op;
-                o2.has_mma = 0;
+                o2.has_mma = 2;
                 rewrite_abuf<M_SEED>(c, p, o2, nullptr, kWDen);
               } else {
                 epi_wait(c);
@@ -884,7 +1010,7 @@ static bool make_map_acts(CUtensorMap* out, const void* base, unsigned long long
   }
   cuuint64_t dims[3] = {(cuuint64_t)kWidth, rows, planes};
   cuuint64_t strides[2] = {(cuuint64_t)kWidth * 2, rows * (cuuint64_t)kWidth * 2};
-  cuuint32_t box[3] = {64, 32, 1};
+  cuuint32_t box[3] = {64, (cuuint32_t)kTileM, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -903,9 +1029,7 @@ template <int P>
 static int launch(const CUtensorMap& tmEnc, const CUtensorMap& tmActs, FusedParams& p, cudaStream_t st,
                   const char* what) {
   const size_t fixed = 1024 + 2 * kAbufBytes + sizeof(FBarriers);
-  int ns = (int)(((size_t)kSmemLimit - fixed) / kSlotBytes);
-  if (ns > kFMaxStages) ns = kFMaxStages;
-  PNB_REQUIRE(ns >= 3, "mlp_fused: shared memory budget too small");
+  const int ns = kSlots;
   p.nstages = ns;
   const size_t smem_bytes = fixed + (size_t)ns * kSlotBytes;
   if (const char* dbg = getenv("PNB_FUSED_DEBUG")) p.debug = atoi(dbg);  // timing experiments only (wrong results)
@@ -1057,4 +1181,27 @@ extern "C" int pnb_mlp_fused_jadj(long long M, const void* u, int ld_u, const vo
   if (!make_map_enc(&tmEnc, u, (unsigned long long)M, (unsigned long long)ld_u)) return PNB_ERR_ARG;
   if (!make_map_acts(&tmActs, q_planes, kAdjPlanes, (unsigned long long)M)) return PNB_ERR_ARG;
   return launch<P_JADJ>(tmEnc, tmActs, p, as_stream(stream), "mlp_fused_jadj");
+}
+
+// Introspection for the tests: the static ring plan of a program.  out[0] = loads per tile pair, out[1] = MMA step
+// executions per tile pair, then per load {slot, is_enc, t, blob_off}, then per executed step (in MMA order)
+// {tile, step, blob_off, is_aenc, w_slot, w_load, w_rel, e_slot, e_load, e_rel, first, op}.
+extern "C" int pnb_mlp_fused_plan(int prog, long long* out, int cap) {
+  PNB_REQUIRE(prog >= 0 && prog < kNumProgs && out != nullptr && cap >= 2, "mlp_fused_plan: bad arguments");
+  const Prog& g = kSched.prog[prog];
+  out[0] = g.n_loads, out[1] = 2 * g.n_steps;
+  int n = 2;
+  for (int l = 0; l < g.n_loads && n + 4 <= cap; ++l) {
+    out[n++] = g.loads[l].slot, out[n++] = g.loads[l].is_enc, out[n++] = g.loads[l].t, out[n++] = g.loads[l].blob_off;
+  }
+  for (int o = 0; o < g.n_ops; ++o)
+    for (int t = 0; t < 2; ++t)
+      for (int k = 0; k < g.ops[o].s1 - g.ops[o].s0 && n + 12 <= cap; ++k) {
+        const int sidx = (t == 0 || PNB_RING_MODE < 2) ? g.ops[o].s0 + k : g.ops[o].s1 - 1 - k;
+        const Use& u = g.uses[t][sidx];
+        out[n++] = t, out[n++] = sidx, out[n++] = g.steps[sidx].blob_off, out[n++] = (g.steps[sidx].flags & F_AENC) ? 1 : 0;
+        out[n++] = u.w_slot, out[n++] = u.w_load, out[n++] = u.w_rel, out[n++] = u.e_slot, out[n++] = u.e_load;
+        out[n++] = u.e_rel, out[n++] = u.first, out[n++] = o;
+      }
+  return 0;
 }

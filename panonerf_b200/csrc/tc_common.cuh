@@ -33,6 +33,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done;
   const uint32_t addr = smem_u32(bar);
+#ifdef PNB_MBAR_WATCHDOG
+  long long spins = 0;
+#endif
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -41,6 +44,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(done)
         : "r"(addr), "r"(parity)
         : "memory");
+#ifdef PNB_MBAR_WATCHDOG
+    if (!done && ++spins > (1ll << 24)) {  // debugging aid: report the stuck barrier instead of hanging
+      printf("mbar timeout: block %d thread %d smem 0x%x parity %u\n", (int)blockIdx.x, (int)threadIdx.x, addr, parity);
+      __trap();
+    }
+#endif
   } while (!done);
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }

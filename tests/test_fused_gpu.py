@@ -96,13 +96,15 @@ def test_pack_blob_is_the_swizzled_bf16_image_of_the_weights():
 
 @pytest.mark.parametrize("S,R,normals", [(64, None, False), (64, None, True), (10, 77, True), (7, 3, False)])
 def test_fused_forward_matches_layered_path(S, R, normals):
-    """Same bf16 operands, same accumulation order: outputs agree to a few bf16 ulps (ragged tile tails included)."""
+    """Same bf16 operands, fp32 accumulation (the fused kernel may walk the k-blocks of every second tile backwards,
+    so a bf16 rounding of a hidden activation can flip): outputs agree to about one bf16 ulp of their magnitude
+    (ragged tile tails included)."""
     _tc_or_skip()
     sd, means, covs, venc = _inputs(S, R)
     a = _field(sd, means, covs, venc, S, True, normals)
     b = _field(sd, means, covs, venc, S, False, normals)
-    assert_close(a["raw_rgb"], b["raw_rgb"], 1e-3, "raw_rgb", floor=float(b["raw_rgb"].abs().mean()))
-    assert_close(a["raw_den"], b["raw_den"], 1e-3, "raw_den", floor=float(b["raw_den"].abs().mean()))
+    assert_close(a["raw_rgb"], b["raw_rgb"], 1.5e-2, "raw_rgb", floor=float(b["raw_rgb"].abs().mean()))
+    assert_close(a["raw_den"], b["raw_den"], 1.5e-2, "raw_den", floor=float(b["raw_den"].abs().mean()))
     if normals:
         na, nb = a["n_raw"].reshape(-1, 3), b["n_raw"].reshape(-1, 3)
         assert torch.isfinite(na).all()
