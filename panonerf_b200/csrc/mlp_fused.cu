@@ -245,7 +245,7 @@ struct Builder {
 // slot is released at its last use so the producer can refill it two steps ahead, and all slots are free again at
 // the end of the pair (the plan repeats verbatim for the next pair).
 #ifndef PNB_RING_MODE
-#define PNB_RING_MODE 0  // 0: FIFO, no reuse, both tiles forwards; 1: reuse, both forwards; 2: reuse, tile 1 backwards
+#define PNB_RING_MODE 2  // 0: FIFO, no reuse, both tiles forwards; 1: reuse, both forwards; 2: reuse, tile 1 backwards
 #endif
 constexpr void plan_ring(Prog& g) {
   // events in execution order

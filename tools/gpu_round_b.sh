@@ -1,10 +1,11 @@
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider > gpurun_out/tests.log 2>&1
+timeout 200 python -m pytest tests -x -q -m gpu > gpurun_out/tests.log 2>&1
 echo "pytest exit $?" | tee -a gpurun_out/tests.log
-grep -E "^E  |FAILED|passed|failed" gpurun_out/tests.log | head -40
-timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench.log 2>&1; echo "bench exit $?"; tail -1 gpurun_out/bench.log | cut -c1-2500
-python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/plain.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 30000 --csv --log-file gpurun_out/launches.csv \
+grep -E "^E  |FAILED|passed|failed" gpurun_out/tests.log | head -10
+timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench.log 2>&1; echo "bench exit $?"; tail -1 gpurun_out/bench.log | cut -c1-2500
+timeout 300 python bench.py --workload render --steps 1 --warmup 1 > gpurun_out/render1.log 2>&1; echo "render rc $?"; tail -1 gpurun_out/render1.log | cut -c1-400
+timeout 300 python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/plain.log 2>&1 && \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 30000 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu.log 2>&1
 echo "list rc $?"
-python tools/summarize_launches.py gpurun_out/launches.csv 2>/dev/null | head -40
+python tools/summarize_launches.py gpurun_out/launches.csv 2>/dev/null | head -24
