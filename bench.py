@@ -240,7 +240,7 @@ def run_render(args):
     env irradiance + surface rendering (what the reference's render_image does), rows sharded over the ranks, no
     inter-GPU communication.  `e2e` additionally copies the rendered HDR images back to pinned host memory."""
     import torch.distributed as dist
-    from panonerf_b200 import ops
+    from panonerf_b200 import field, ops
     from panonerf_b200.datasets.pano_datasets import generate_rays
     from panonerf_b200.parallel import shard_rows
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -277,21 +277,25 @@ def run_render(args):
         sampler = ClockSampler(local)
         sampler.start()
         l0 = ops.launch_count()
+        if not copy_back:
+            field.PROFILE = {}
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             render(copy_back)
         e1.record()
         barrier()
+        prof = field.PROFILE
+        field.PROFILE = None
         t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t[0]), ops.launch_count() - l0, sampler.result()
+        return float(t[0]), ops.launch_count() - l0, sampler.result(), prof
 
     for _ in range(max(args.warmup, 1)):
         render(False)
-    ms, launches, clocks = timed(False, args.steps)
-    ms_e2e, _, _ = timed(True, args.steps)
+    ms, launches, clocks, prof = timed(False, args.steps)
+    ms_e2e, _, _, _ = timed(True, args.steps)
     rays_total = H * W * args.steps
     flop_per_ray = (2 * N_SAMPLES + 100) * MLP_FLOP_PER_SAMPLE + N_SAMPLES * JAC_FLOP_PER_SAMPLE
     line = {"metric": "render_rays_per_s", "value": rays_total / (ms / 1e3), "unit": "rays/s", "n_gpus": world,
@@ -305,6 +309,7 @@ def run_render(args):
             "e2e": {"value": rays_total / (ms_e2e / 1e3), "unit": "rays/s", "h2d_bytes_per_step": 48,
                     "d2h_bytes_per_step": int(host_out.numel() * 4), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
+            "roofline": roofline_from_profile(prof, args.steps, peaks()),
             "step_tflops": H * W * flop_per_ray / (ms / args.steps / 1e3) / 1e12}
     if rank == 0:
         print(json.dumps(line), flush=True)
@@ -320,25 +325,54 @@ def step_flops():
     return RAYS_PER_GPU * (3 * (main + env) * MLP_FLOP_PER_SAMPLE + 3 * N_SAMPLES * JAC_FLOP_PER_SAMPLE)
 
 
+BOUND = {"mlp_fused": "tensor", "mlp_fused_bwd": "tensor", "mlp_fused_jadj": "tensor", "wgrad_batch": "hbm",
+         "linear_tc": "hbm", "wgrad_tc": "hbm"}
+
+
 def roofline_from_profile(prof, steps, pk):
-    """Dominant kernel = the tcgen05 linear kernel (all trunk/head/dgrad/Jacobian GEMMs).  `achieved` is its
-    ALGORITHMIC HBM bytes (read A once + write C once (+ mask read)) over its CUDA-event time
-    summed over the timed region; it is HBM-bound as an un-fused layer (128 FLOP/B < ridge ~211 FLOP/B)."""
+    """Per kernel family: ALGORITHMIC bytes / FLOPs over the CUDA-event time of its launches
+    inside the timed region (events on the launching stream).  The dominant family (most time) is the headline:
+      * wgrad_batch (all weight gradients of a level in one launch) is HBM-bound: every activation / dz plane is
+        read exactly once -> fraction of the measured copy bandwidth;
+      * the fused MLP programs (forward, forward+Jacobian, dgrad chain, adjoint sweep) are tensor-bound ->
+        fraction of the measured sustained bf16 rate (they run inside a long step).
+    `traffic` = DRAM bytes per launch from the committed ncu --set full capture of the same command
+    (profiles/r01_step_traffic.json), null if that file is absent."""
     if not prof:
         return None
-    out = {}
+    traffic = {}
+    tp = os.path.join(ROOT, "profiles", "r01_step_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp))
+    fam = {}
     for name, rec in prof.items():
         ms = sum(a.elapsed_time(b) for a, b in rec["events"])
-        out[name] = dict(ms=ms, bytes=rec["bytes"], flops=rec["flops"], launches=len(rec["events"]))
-    top = max(out, key=lambda k: out[k]["ms"])
-    r = out[top]
-    gbs = r["bytes"] / (r["ms"] / 1e3) / 1e9
-    tfs = r["flops"] / (r["ms"] / 1e3) / 1e12
-    return {"kernel": top, "bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
-            "traffic": None, "peak_source": pk["src"] + " (sustained copy bandwidth)",
-            "launches_per_step": r["launches"] / steps, "avg_launch_ms": r["ms"] / r["launches"],
-            "kernel_ms_per_step": r["ms"] / steps, "tensor_tflops": tfs, "tensor_frac_of_sustained": tfs / pk["tf_sust"],
-            "all_kernels_ms_per_step": {k: v["ms"] / steps for k, v in out.items()}}
+        n = len(rec["events"])
+        gbs = rec["bytes"] / (ms / 1e3) / 1e9
+        tfs = rec["flops"] / (ms / 1e3) / 1e12
+        bound = BOUND.get(name, "hbm")
+        peak = pk["tf_sust"] if bound == "tensor" else pk["hbm"]
+        ach = tfs if bound == "tensor" else gbs
+        fam[name] = {"kernel": name, "bound": bound, "achieved": ach, "peak": peak,
+                     "unit": "TFLOP/s" if bound == "tensor" else "GB/s", "frac": ach / peak,
+                     "traffic": traffic.get(name, {}).get("dram_bytes_per_launch"),
+                     "algorithmic_bytes_per_launch": rec["bytes"] / n, "algorithmic_flops_per_launch": rec["flops"] / n,
+                     "launches_per_step": n / steps, "avg_launch_ms": ms / n, "kernel_ms_per_step": ms / steps,
+                     "tflops": tfs, "gbps": gbs}
+    top = max(fam, key=lambda k: fam[k]["kernel_ms_per_step"])
+    out = dict(fam[top])
+    out["peak_source"] = pk["src"] + (" (sustained bf16 matmul rate)" if out["bound"] == "tensor"
+                                      else " (sustained copy bandwidth)")
+    out["other_kernels"] = {k: {kk: v[kk] for kk in ("bound", "achieved", "peak", "unit", "frac", "traffic",
+                                                      "kernel_ms_per_step", "launches_per_step")}
+                            for k, v in fam.items() if k != top}
+    mlp = [v for k, v in fam.items() if k.startswith("mlp_fused")]
+    if mlp:
+        ms = sum(v["kernel_ms_per_step"] for v in mlp)
+        fl = sum(v["algorithmic_flops_per_launch"] * v["launches_per_step"] for v in mlp)
+        out["fused_mlp_all_programs"] = {"bound": "tensor", "kernel_ms_per_step": ms, "achieved": fl / ms / 1e9,
+                                         "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": fl / ms / 1e9 / pk["tf_sust"]}
+    return out
 
 
 # ----------------------------------------------------------------------------------------------------------------

@@ -2,6 +2,8 @@
 // All kernels are HBM-bound element-wise maps; grids are sized in multiples of the 148 SMs (common.cuh).
 // The translation unit is compiled with -fmad=false so that the fp32 operation order below reproduces the
 // reference's un-fused PyTorch/NumPy arithmetic; explicit fmaf() is used only where fusing is harmless.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace pnb {
@@ -145,6 +147,38 @@ __global__ void cast_rays_kernel(long long R, int N, const float* __restrict__ t
 }
 
 // ---- IPE ------------------------------------------------------------------------------------------------------
+// sin / cos of fp32 arguments up to ~2^15 * |x| (scale 2^15 of the highest IPE degree): libdevice's sinf()/cosf()
+// fall into the Payne-Hanek slow path (local memory, ~100s of instructions) above |y| ~ 1e5, which made these
+// kernels compute-bound at 0.12 of the HBM roofline.  Here the argument is reduced in double precision
+// (y - n*pi/2 with a two-term pi/2: exact to ~1e-11 for |y| < 1e8) and the Cephes minimax polynomials are evaluated
+// in fp32 on [-pi/4, pi/4] (<= 2 ulp): the result stays within ~2.5e-7 of the correctly rounded sin/cos of the SAME
+// fp32 argument the reference hands to torch.sin (mip.py:428), far inside the 2e-6 parity bound of the tests.
+__device__ __forceinline__ void sincos_accurate(float y, float* sn, float* cs) {
+  const double yd = (double)y;
+  const double n = rint(yd * 0.63661977236758134308);
+  double r = fma(-n, 1.57079632679489655800, yd);
+  r = fma(-n, 6.12323399573676603587e-17, r);
+  const float rf = (float)r;
+  const int q = (int)n;
+  const float z = rf * rf;
+  const float ps = fmaf(rf * z, fmaf(z, fmaf(z, -1.9515295891e-4f, 8.3321608736e-3f), -1.6666654611e-1f), rf);
+  const float pc = fmaf(z, fmaf(z, fmaf(z, fmaf(z, 2.443315711809948e-5f, -1.388731625493765e-3f), 4.166664568298827e-2f), -0.5f), 1.0f);
+  const float s0 = (q & 1) ? pc : ps;
+  const float c0 = (q & 1) ? ps : pc;
+  *sn = (q & 2) ? -s0 : s0;
+  *cs = ((q + 1) & 2) ? -c0 : c0;
+}
+__device__ __forceinline__ float sin_accurate(float y) {
+  float s, c;
+  sincos_accurate(y, &s, &c);
+  return s;
+}
+__device__ __forceinline__ float cos_accurate(float y) {
+  float s, c;
+  sincos_accurate(y, &s, &c);
+  return c;
+}
+
 // One thread per (sample, l*3+c): writes the sin feature at column j and the cos feature at column 3L+j, so a
 // warp writes two contiguous runs per sample row (coalesced).  exp underflow short-circuits the sinf slow path.
 template <typename T>
@@ -163,11 +197,70 @@ __global__ void ipe_fwd_kernel(long long M, int min_deg, int L, const float* __r
     float e = expf(-0.5f * yv);
     float fs = 0.f, fc = 0.f;
     if (e != 0.f) {
-      fs = e * sinf(y);
-      fc = e * sinf(y + kHalfPiF);
+      fs = e * sin_accurate(y);
+      fc = e * sin_accurate(y + kHalfPiF);
     }
     enc[m * ld + j] = from_f32<T>(fs);
     enc[m * ld + F + j] = from_f32<T>(fc);
+  }
+}
+
+// Fast path of the forward encoding (the default): HBM-bound instead of instruction-bound.
+//   * one thread per (sample, xyz component) walks the 16 degrees: the phase of 2^l * mean modulo 2 pi is an exact
+//     left shift of the 64-bit fixed-point fraction of mean / (2 pi) (one double multiply per component instead of
+//     a range reduction per feature), sin / cos come from the SFU (MUFU, |err| < 5e-7 on [-pi, pi]);
+//   * the reference's second half is sin(fl32(y + fl32(pi/2))), NOT cos(y): the fp32 addition rounds by up to
+//     1.6e-2 rad at the highest degrees.  The rounding error is recovered exactly with a TwoSum and applied as a
+//     small-angle rotation, cos(y + eps) = cos y cos eps - sin y sin eps, so the kernel matches mip.py:428 and not
+//     the textbook formula;
+//   * features are staged in shared memory and leave as full 16-byte rows (coalesced), instead of 2-byte scatters.
+constexpr int kIpeTile = 64;  // samples per block iteration
+template <typename T, int L>
+__global__ void __launch_bounds__(3 * kIpeTile) ipe_fwd_tile_kernel(long long M, int min_deg,
+                                                                     const float* __restrict__ means,
+                                                                     const float* __restrict__ covs, T* __restrict__ enc,
+                                                                     int ld) {
+  constexpr int F = 6 * L;
+  __shared__ __align__(16) T tile[kIpeTile * F];
+  const int tid = threadIdx.x;
+  const int s = tid / 3, c = tid - 3 * s;
+  for (long long base = (long long)blockIdx.x * kIpeTile; base < M; base += (long long)gridDim.x * kIpeTile) {
+    const long long idx = base * 3 + tid;
+    if (idx < M * 3) {
+      const float mean = means[idx], cov = covs[idx];
+      double u = (double)mean * 0.15915494309189534561;  // turns
+      u -= floor(u);
+      const unsigned long long U = (unsigned long long)(u * 18446744073709551616.0);
+      const uint32_t hi = (uint32_t)(U >> 32), lo = (uint32_t)U;
+#pragma unroll 4
+      for (int l = 0; l < L; ++l) {
+        const int sh = min_deg + l;
+        const uint32_t ph = __funnelshift_l(lo, hi, sh);  // top 32 bits of U << sh: phase in 2^-32 turns
+        const float r = (float)(int)ph * 1.46291807926715968e-9f;  // 2 pi / 2^32 -> [-pi, pi)
+        const float sn = __sinf(r), cs = __cosf(r);
+        const float sc = __uint_as_float((uint32_t)(127 + sh) << 23);  // 2^sh
+        const float y = mean * sc;
+        const float e = __expf(-0.5f * (cov * (sc * sc)));
+        // fl32(y + pi/2) = y + pi/2 + eps exactly
+        const float z = y + kHalfPiF;
+        const float bb = z - y;
+        const float err = (y - (z - bb)) + (kHalfPiF - bb);
+        const float eps = 4.37113900018624283e-8f - err;
+        const float ce = fmaf(-0.5f * eps, eps, 1.0f);
+        const float se = eps * fmaf(-0.16666667f * eps, eps, 1.0f);
+        const float c2 = cs * ce - sn * se;
+        tile[s * F + l * 3 + c] = from_f32<T>(e * sn);
+        tile[s * F + 3 * L + l * 3 + c] = from_f32<T>(e * c2);
+      }
+    }
+    __syncthreads();
+    constexpr int kVecPerRow = F * (int)sizeof(T) / 16;
+    const int rows = (M - base) < kIpeTile ? (int)(M - base) : kIpeTile;
+    for (int v = tid; v < rows * kVecPerRow; v += 3 * kIpeTile) {
+      const int row = v / kVecPerRow, j = v - row * kVecPerRow;
+      reinterpret_cast<uint4*>(enc + (base + row) * ld)[j] = reinterpret_cast<const uint4*>(tile + row * F)[j];
+    }
+    __syncthreads();
   }
 }
 
@@ -190,7 +283,7 @@ __global__ void ipe_vjp_kernel(long long M, int min_deg, int L, const float* __r
       if (e == 0.f) break;  // larger l only underflow harder
       float y = mean * sc;
       float gs = to_f32<T>(g[m * ld + 3 * l + c]), gc = to_f32<T>(g[m * ld + F + 3 * l + c]);
-      acc += sc * (e * (gs * cosf(y) + gc * cosf(y + kHalfPiF)));
+      acc += sc * (e * (gs * cos_accurate(y) + gc * cos_accurate(y + kHalfPiF)));
     }
     d_means[idx] = acc;
   }
@@ -213,8 +306,8 @@ __global__ void ipe_jvp_kernel(long long M, int min_deg, int L, const float* __r
     float os = 0.f, oc = 0.f;
     if (e != 0.f) {
       float w = v[3 * m + c] * sc * e;
-      os = w * cosf(y);
-      oc = w * cosf(y + kHalfPiF);
+      os = w * cos_accurate(y);
+      oc = w * cos_accurate(y + kHalfPiF);
     }
     out[m * ld + j] = from_f32<T>(os);
     out[m * ld + F + j] = from_f32<T>(oc);
@@ -292,6 +385,20 @@ extern "C" int pnb_ipe_fwd(int M, const float* means, const float* covs, int min
   int L = max_deg - min_deg;
   PNB_REQUIRE(M >= 0 && L > 0 && ld >= 6 * L, "ipe_fwd: bad sizes");
   if (M == 0) return 0;
+  const int esz = dtype == PNB_BF16 ? 2 : 4;
+  if (L == 16 && min_deg >= 0 && min_deg + L <= 31 && ((size_t)ld * esz) % 16 == 0 && ((uintptr_t)enc % 16) == 0 &&
+      getenv("PNB_IPE_SLOW") == nullptr) {
+    long long tiles = ((long long)M + pnb::kIpeTile - 1) / pnb::kIpeTile;
+    long long cap = (long long)pnb::kNumSMs * 8;
+    int g = (int)(tiles < cap ? tiles : cap);
+    if (dtype == PNB_BF16)
+      pnb::ipe_fwd_tile_kernel<__nv_bfloat16, 16><<<g, 3 * pnb::kIpeTile, 0, as_stream(stream)>>>(
+          M, min_deg, means, covs, (__nv_bfloat16*)enc, ld);
+    else
+      pnb::ipe_fwd_tile_kernel<float, 16><<<g, 3 * pnb::kIpeTile, 0, as_stream(stream)>>>(M, min_deg, means, covs,
+                                                                                         (float*)enc, ld);
+    return finish("ipe_fwd");
+  }
   int grid = grid_for((long long)M * 3 * L, 256);
   if (dtype == PNB_BF16)
     ipe_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>(M, min_deg, L, means, covs,

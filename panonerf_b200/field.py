@@ -499,7 +499,8 @@ class _Field(torch.autograd.Function):
         fused = (be.name == "tc" and fused_enabled() and fused_supported(cfg, P)
                  and not (cfg["with_normals"] and cfg.get("jac_precision") == "fp32"))
         if fused:
-            need_bwd = any(ctx.needs_input_grad)
+            # (inside forward() grad mode is always off: radiance_field() records the caller's mode in cfg)
+            need_bwd = cfg.get("grad_enabled", True) and any(ctx.needs_input_grad)
             C = P["density_layer.weight"].shape[0]
             enc = torch.empty(M, xyz, device=dev, dtype=dt)
             ops.ipe_into(means2, covs2, cfg["min_deg"], cfg["max_deg"], enc)
@@ -840,7 +841,7 @@ def radiance_field(means, covs, venc, params: Dict[str, torch.Tensor], *, precis
     w0 = params["layers.0.0.weight"]
     cfg = dict(names=names, precision=precision, depth=depth, skip=skip, width=w0.shape[0], xyz_dim=w0.shape[1],
                samples_per_ray=samples_per_ray, min_deg=min_deg, max_deg=max_deg, density_bias=density_bias,
-               with_normals=with_normals, jac_precision=jac_precision)
+               with_normals=with_normals, jac_precision=jac_precision, grad_enabled=torch.is_grad_enabled())
     if w0.shape[1] != 6 * (max_deg - min_deg):
         raise RuntimeError("IPE width does not match the first layer")
     R = means.shape[0]

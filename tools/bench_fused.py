@@ -15,7 +15,7 @@ def main():
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     M = int(args[0]) if args else 128 * 148 * 64
     normals, save = "--normals" in sys.argv, "--save" in sys.argv
-    S, C = 64, 5
+    S, C = int(os.environ.get("BF_S", "64")), 5
     dev = torch.device("cuda", 0)
     torch.manual_seed(0)
     from oracle import panonerf_oracle as O

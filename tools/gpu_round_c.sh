@@ -1,0 +1,4 @@
+mkdir -p gpurun_out
+timeout 200 python -m pytest tests -x -q -m gpu > gpurun_out/tests.log 2>&1
+echo "pytest exit $?"; grep -E "^E  |FAILED|passed|failed" gpurun_out/tests.log | head -10
+timeout 120 python tools/bench_micro.py 2>&1 | tee gpurun_out/micro.log | cut -c1-200
