@@ -1,4 +1,5 @@
+# N-GPU weak-scaling (train) and strong-scaling (render) lines: bash tools/gpu_multi.sh N
+N=${1:-2}
 mkdir -p gpurun_out
-python bench.py --workload render --steps 1 --warmup 1 > gpurun_out/render1.log 2>&1; echo "render rc $?"; tail -1 gpurun_out/render1.log | cut -c1-700
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/train2.log 2>&1; echo "train2 rc $?"; tail -1 gpurun_out/train2.log | cut -c1-900
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --workload render --steps 1 --warmup 1 > gpurun_out/render2.log 2>&1; echo "render2 rc $?"; tail -1 gpurun_out/render2.log | cut -c1-500
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/train_n$N.log 2>&1; echo "train$N rc $?"; grep '^{' gpurun_out/train_n$N.log | tail -1 | cut -c1-330
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --workload render --steps 2 --warmup 1 > gpurun_out/render_n$N.log 2>&1; echo "render$N rc $?"; grep '^{' gpurun_out/render_n$N.log | tail -1 | cut -c1-330
