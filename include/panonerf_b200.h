@@ -237,6 +237,9 @@ int pnb_mlp_fused_jadj(long long M, const void* u, int ld_u, const void* wblob, 
                        void* stream);
 /* out[g, n] = sum of the `group` consecutive rows of x belonging to group g (fp32 out [M/group, N]) */
 int pnb_group_sum(long long M, int N, int group, const void* x, int ldx, int dtype, float* out, void* stream);
+/* head gradients as tensor-core operands: src fp32 [M,C] (C <= 16) -> dst bf16 [M,64] zero-padded; colsum (nullable)
+ * fp32 [C] += column sums of src (the head's bias gradient, color_layer / density_layer of pano_mip_nerf.py:56,76) */
+int pnb_pad_head_grad(long long M, int C, const float* src, void* dst_bf16, float* colsum, void* stream);
 /* 1 when the tcgen05 path was compiled in and the device is sm_100 */
 int pnb_tc_available(void);
 

@@ -136,6 +136,7 @@ struct FusedParams {
   uint32_t* masks;       // ReLU sign bit-planes (nullable in P_FWD without `save`)
   const float* d_rgb;    // P_BWD inputs
   const float* d_den;
+  __nv_bfloat16* planes;     // save != 0: activation planes [n][M][256] (same memory the TMA map covers)
   unsigned long long* prof;  // timing experiments: [grid][8] cycle counters (nullable)
 };
 
@@ -498,7 +499,7 @@ struct EpiCtx {
   uint32_t mbits[4];        // sign-bit words of this thread's units for this op (prefetched one op-tile ahead)
   long long m;              // global sample row of this thread
   int q, hf, lane, row, tile_row0;
-  bool row_ok, save, skip;
+  bool row_ok, save, skip, direct;
 };
 
 enum { M_BIAS_RELU = 0, M_BIAS, M_ROWBIAS_RELU, M_MASK, M_LIN, M_SEED, M_BSEED, M_BDZ7 };
@@ -552,7 +553,7 @@ __device__ __forceinline__ void rewrite_abuf_hf(const EpiCtx& c, const FusedPara
   }
   uint32_t r[2][32];
   if (kReadsAcc) tmem_ld32u(c.tacc + op.acc_col + ub * 32, r[0]);
-  if (c.save) {
+  if (c.save && !c.direct) {
     // The four warps of this half (one per TMEM lane quadrant) store whole 128-row k-blocks together; warp q = 0
     // issues.  Its TMA stores that still read this tile's buffer (the op before the other tile's) must be done;
     // at most the other tile's two newer groups may stay pending.
@@ -627,7 +628,13 @@ __device__ __forceinline__ void rewrite_abuf_hf(const EpiCtx& c, const FusedPara
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       sts128(dst + (((jb + j) ^ (c.row & 7)) << 4), h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
-    if (c.save && (u & 1) && op.save_plane >= 0) {
+    if (c.save && c.direct && op.save_plane >= 0 && c.row_ok) {
+      // straight from the registers: this thread's 32 columns are 64 contiguous bytes of its row (two full sectors)
+      uint4* gdst = reinterpret_cast<uint4*>(p.planes + ((size_t)op.save_plane * (size_t)p.M + (size_t)c.m) * kWidth + u * 32);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) __stcs(gdst + j, make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]));
+    }
+    if (c.save && !c.direct && (u & 1) && op.save_plane >= 0) {
       // both halves of k-block u/2 are in place for all 128 rows: store the 128 x 64 box (16 KB)
       fence_async_smem();
       named_bar_sync(1 + HF, 128);
@@ -838,6 +845,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmEnc, const __grid_constan
     c.q = warp & 3;            // TMEM lane quadrant (hardware rule: warp id % 4)
     c.hf = (warp - 2) >> 2;    // which of the two warps of the quadrant
     c.lane = lane, c.row = c.q * 32 + lane, c.save = p.save != 0, c.skip = (p.debug & 2) != 0;
+    c.direct = p.save == 2;
     const uint32_t tlane = tmem_base + ((uint32_t)(c.q * 32) << 16);
     if (lane == 0) {           // both activation buffers / accumulators start out free
       mbar_arrive(&bars->abuf_ready[0]);
@@ -1033,6 +1041,12 @@ static int launch(const CUtensorMap& tmEnc, const CUtensorMap& tmActs, FusedPara
   p.nstages = ns;
   const size_t smem_bytes = fixed + (size_t)ns * kSlotBytes;
   if (const char* dbg = getenv("PNB_FUSED_DEBUG")) p.debug = atoi(dbg);  // timing experiments only (wrong results)
+  if (p.save != 0) {
+    // default: 16 KB TMA stores from the activation buffer.  "direct" (st.global from the epilogue registers) was
+    // measured 25-35 % slower: 16-byte pieces at a 512-byte lane stride saturate the LSU store path.
+    const char* sm = getenv("PNB_FUSED_SAVE");
+    p.save = (sm != nullptr && sm[0] == 'd') ? 2 : 1;
+  }
   p.replicas = kReplicas, p.blob_stride = blob_stride();
   if (const char* r = getenv("PNB_FUSED_REPLICAS")) {  // timing experiments only
     p.replicas = atoi(r);
@@ -1131,6 +1145,7 @@ extern "C" int pnb_mlp_fused_fwd(long long M, int S, int C, const void* enc, int
   p.wblob = reinterpret_cast<const uint8_t*>(wblob), p.bblob = bblob, p.row_bias = row_bias;
   p.raw_den = raw_den, p.raw_rgb = raw_rgb, p.g_enc = g_enc;
   p.masks = reinterpret_cast<uint32_t*>(masks), p.masks_per_tile = masks_per_tile;
+  p.planes = reinterpret_cast<__nv_bfloat16*>(acts);
   CUtensorMap tmEnc, tmActs;
   if (!make_map_enc(&tmEnc, enc, (unsigned long long)M, (unsigned long long)ld_enc)) return PNB_ERR_ARG;
   if (p.save) {
@@ -1158,6 +1173,7 @@ extern "C" int pnb_mlp_fused_bwd(long long M, int C, const void* wblob, const fl
   p.wblob = reinterpret_cast<const uint8_t*>(wblob), p.bblob = bblob;
   p.g_enc = d_enc, p.d_rgb = d_rgb, p.d_den = d_den;
   p.masks = reinterpret_cast<uint32_t*>(const_cast<void*>(masks)), p.masks_per_tile = 1;
+  p.planes = reinterpret_cast<__nv_bfloat16*>(dz_planes);
   CUtensorMap tmActs;
   if (!make_map_acts(&tmActs, dz_planes, kBwdPlanes, (unsigned long long)M)) return PNB_ERR_ARG;
   return launch<P_BWD>(tmActs, tmActs, p, as_stream(stream), "mlp_fused_bwd");
@@ -1177,6 +1193,7 @@ extern "C" int pnb_mlp_fused_jadj(long long M, const void* u, int ld_u, const vo
   p.S = 1, p.C = 1, p.save = 1;
   p.wblob = reinterpret_cast<const uint8_t*>(wblob);
   p.masks = reinterpret_cast<uint32_t*>(const_cast<void*>(masks)), p.masks_per_tile = 1;
+  p.planes = reinterpret_cast<__nv_bfloat16*>(q_planes);
   CUtensorMap tmEnc, tmActs;
   if (!make_map_enc(&tmEnc, u, (unsigned long long)M, (unsigned long long)ld_u)) return PNB_ERR_ARG;
   if (!make_map_acts(&tmActs, q_planes, kAdjPlanes, (unsigned long long)M)) return PNB_ERR_ARG;

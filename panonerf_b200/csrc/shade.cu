@@ -663,7 +663,7 @@ extern "C" int pnb_convert(long long M, int N, const void* src, int ld_src, int 
 }
 
 namespace pnb {
-// per-ray sums over the `group` consecutive samples of a ray: one warp per (group, 32-column slab)
+// per-ray sums over the `group` consecutive samples of a ray: one thread per (group, column)  [generic path]
 template <typename T>
 __global__ void group_sum_kernel(long long G, int N, int group, const T* __restrict__ x, int ldx,
                                  float* __restrict__ out) {
@@ -678,6 +678,63 @@ __global__ void group_sum_kernel(long long G, int N, int group, const T* __restr
     out[idx] = s;
   }
 }
+// bf16 fast path: one warp per (group, 64-column slab), every lane sums one bf16x2 column pair over the rows of the
+// group: 128-byte coalesced row reads, float2 stores.
+__global__ void group_sum_bf16x2_kernel(long long G, int N, int group, const __nv_bfloat16* __restrict__ x, int ldx,
+                                        float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int slabs = N / 64;
+  const long long total = G * slabs;
+  for (long long w = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5); w < total;
+       w += (long long)gridDim.x * (blockDim.x >> 5)) {
+    const long long g = w / slabs;
+    const int col = (int)(w - g * slabs) * 64 + 2 * lane;
+    const __nv_bfloat16* base = x + g * group * (long long)ldx + col;
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll 4
+    for (int i = 0; i < group; ++i) {
+      const uint32_t v = *reinterpret_cast<const uint32_t*>(base + (long long)i * ldx);
+      s0 += __uint_as_float(v << 16);
+      s1 += __uint_as_float(v & 0xffff0000u);
+    }
+    *reinterpret_cast<float2*>(out + g * N + col) = make_float2(s0, s1);
+  }
+}
+
+// Head gradients (d raw_rgb [M,3], d raw_sigma.. [M,C]) as tensor-core operands: bf16 [M,64], zero-padded, plus their
+// column sums (= the head's bias gradient) in the same pass.  One thread per row.
+__global__ void pad_head_grad_kernel(long long M, int C, const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                     float* __restrict__ colsum) {
+  float acc[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+  for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
+    float v[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      v[c] = c < C ? src[m * C + c] : 0.f;
+      acc[c] += v[c];
+    }
+    uint4* row = reinterpret_cast<uint4*>(dst + m * 64);
+    __nv_bfloat162 h[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) h[k] = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+    row[0] = *reinterpret_cast<uint4*>(&h[0]);
+    row[1] = *reinterpret_cast<uint4*>(&h[4]);
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int j = 2; j < 8; ++j) row[j] = z;
+  }
+  if (colsum != nullptr) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      if (c < C) {
+        const float s = warp_sum(acc[c]);
+        if ((threadIdx.x & 31) == 0) atomicAdd(colsum + c, s);
+      }
+    }
+  }
+}
 }  // namespace pnb
 
 extern "C" int pnb_group_sum(long long M, int N, int group, const void* x, int ldx, int dtype, float* out,
@@ -685,9 +742,21 @@ extern "C" int pnb_group_sum(long long M, int N, int group, const void* x, int l
   PNB_REQUIRE(M >= 0 && N > 0 && group > 0 && M % group == 0, "group_sum: M must be a multiple of group");
   if (M == 0) return 0;
   long long G = M / group;
-  if (dtype == PNB_BF16)
+  if (dtype == PNB_BF16 && N % 64 == 0 && ldx % 2 == 0 && ((uintptr_t)x % 4) == 0) {
+    const long long warps = G * (N / 64);
+    const int grid = grid_for(warps * 32, 256, 8);
+    pnb::group_sum_bf16x2_kernel<<<grid, 256, 0, as_stream(stream)>>>(G, N, group, (const __nv_bfloat16*)x, ldx, out);
+  } else if (dtype == PNB_BF16)
     LAUNCH_1D(pnb::group_sum_kernel<__nv_bfloat16>, G * N, G, N, group, (const __nv_bfloat16*)x, ldx, out);
   else
     LAUNCH_1D(pnb::group_sum_kernel<float>, G * N, G, N, group, (const float*)x, ldx, out);
   return finish("group_sum");
+}
+
+extern "C" int pnb_pad_head_grad(long long M, int C, const float* src, void* dst_bf16, float* colsum, void* stream) {
+  PNB_REQUIRE(M >= 0 && C >= 1 && C <= 16 && src != nullptr && dst_bf16 != nullptr, "pad_head_grad: bad arguments");
+  PNB_REQUIRE(((uintptr_t)dst_bf16 % 16) == 0, "pad_head_grad: dst must be 16-byte aligned");
+  if (M == 0) return 0;
+  pnb::pad_head_grad_kernel<<<grid_for(M, 128, 8), 128, 0, as_stream(stream)>>>(M, C, src, (__nv_bfloat16*)dst_bf16, colsum);
+  return finish("pad_head_grad");
 }

@@ -462,6 +462,15 @@ def _mask_scale(src, w_row, out):
                                         ops.dt_code(out.dtype), _stream()), "mask_scale")
 
 
+def _pad_head_grad(x32, colsum_out):
+    """fp32 [M,C] head gradient -> bf16 [M,64] zero-padded tensor-core operand; colsum_out += its column sums."""
+    m, c = x32.shape
+    buf = torch.empty(m, 64, device=x32.device, dtype=torch.bfloat16)
+    with torch.cuda.device(x32.device):
+        check(_lib.lib().pnb_pad_head_grad(m, c, _p(x32), _p(buf), _p(colsum_out), _stream()), "pad_head_grad")
+    return buf
+
+
 def _colsum(x, out):
     m, n = x.shape
     with torch.cuda.device(x.device):
@@ -673,14 +682,13 @@ class _Field(torch.autograd.Function):
         dzv = dz[0][:, :hv.shape[1]]
         # ---- weight / bias gradients: one batched launch -----------------------------------------------------
         wc = hv.shape[1]
-        _colsum(d_raw_rgb, G["color_layer.bias"])
-        pad_rgb, pad_den = be._pad64(d_raw_rgb), be._pad64(d_raw_den)
+        pad_rgb = _pad_head_grad(d_raw_rgb, G["color_layer.bias"])
+        pad_den = _pad_head_grad(d_raw_den, G["density_layer.bias"])
         tmp_c = torch.zeros(wc, 64, device=dev, dtype=f32)
         tmp_d = torch.zeros(width, 64, device=dev, dtype=f32)
         wb.add(acts, 9, wc, pad_rgb, 0, 64, tmp_c)                      # (hv^T d_rgb): colour head, transposed
         wb.add(dz, 0, wc, acts, 8, width, G["view_layers.0.0.weight"][:, :width], G["view_layers.0.0.bias"])
         wb.add(dz, 1, 256, acts, 7, width, G["extra_layer.weight"], G["extra_layer.bias"])
-        _colsum(d_raw_den, G["density_layer.bias"])
         wb.add(acts, 7, 256, pad_den, 0, 64, tmp_d)                     # (h7^T d_den): density head, transposed
         for i in range(depth - 1, 0, -1):
             if i == 5:

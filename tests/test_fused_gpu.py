@@ -144,3 +144,78 @@ def test_fused_kernel_is_deterministic():
     b = _field(sd, means, covs, venc, 64, True, True)
     for k in ("raw_rgb", "raw_den", "n_raw"):
         assert torch.equal(a[k], b[k]), k
+
+
+def test_backward_kernel_small_batches_do_not_deadlock():
+    """Regression: the epilogue-only first op of the backward program (no MMA) used to arrive on the activation
+    barrier un-gated; with few, fast CTAs the barrier ran two phases ahead of the MMA thread (parity aliasing) and the
+    kernel hung.  Exercised at the sizes that reproduced it (16 CTAs x one tile pair, all tiles full)."""
+    _tc_or_skip()
+    from panonerf_b200 import field, ops
+    sd = golden_state_dict(load_golden("panonerf_w256.npz"))
+    names = field.param_names(8, 1)
+    params = [sd[n].to(DEV).contiguous() for n in names]
+    pack = field.fused_pack(names, params)
+    for M in (4096, 256, 21):
+        g = torch.Generator(device=DEV).manual_seed(M)
+        means = torch.rand(M, 3, device=DEV, generator=g) * 4 - 2
+        covs = torch.rand(M, 3, device=DEV, generator=g) * 1e-3
+        enc = torch.empty(M, 96, device=DEV, dtype=torch.bfloat16)
+        ops.ipe_into(means, covs, 0, 16, enc)
+        vb = torch.randn((M + 63) // 64, 128, device=DEV, generator=g)
+        masks = field.fused_masks(M, torch.device(DEV, 0), True)
+        acts = torch.empty(18, M, 256, device=DEV, dtype=torch.bfloat16)
+        field.fused_forward(enc, vb, 64, 5, pack, acts, None, masks, True)
+        d_rgb = torch.randn(M, 3, device=DEV, generator=g)
+        d_den = torch.randn(M, 5, device=DEV, generator=g)
+        for _ in range(100):
+            dz = field.fused_backward(M, 5, pack, d_rgb, d_den, masks, None)
+        torch.cuda.synchronize()
+        assert torch.isfinite(dz.float()).all()
+
+
+def test_wgrad_batch_matches_matmul():
+    """Batched weight gradients + fused bias column sums against fp32 matmuls of the same bf16 operands, including two
+    jobs that accumulate into one destination and a narrow (K=16) job."""
+    _tc_or_skip()
+    from panonerf_b200 import field
+    M = 5000
+    g = torch.Generator(device=DEV).manual_seed(1)
+    planes = (torch.randn(4, M, 256, device=DEV, generator=g)).bfloat16()
+    x96 = torch.randn(M, 96, device=DEV, generator=g).bfloat16()
+    wb = field.WgradBatch(M, torch.device(DEV, 0))
+    G0 = torch.zeros(256, 256, device=DEV)
+    G1 = torch.zeros(128, 352, device=DEV)
+    G2 = torch.zeros(256, 16, device=DEV)
+    b0, b2 = torch.zeros(256, device=DEV), torch.zeros(256, device=DEV)
+    wb.add(planes, 0, 256, planes, 1, 256, G0, b0)
+    wb.add(planes, 2, 256, planes, 3, 256, G0)                     # same destination
+    wb.add(planes, 1, 128, planes, 2, 256, G1[:, :256])
+    wb.add(planes, 1, 128, x96, 0, 96, G1[:, 256:])
+    wb.add(planes, 3, 256, x96, 0, 16, G2, b2)
+    wb.launch()
+    torch.cuda.synchronize()
+    P = planes.float()
+    ref0 = P[0].t() @ P[1] + P[2].t() @ P[3]
+    assert_close(G0, ref0, 2e-5, "dW (two jobs, one destination)")
+    assert_close(G1[:, :256], P[1][:, :128].t() @ P[2], 2e-5, "dW (Nw=128)")
+    assert_close(G1[:, 256:], P[1][:, :128].t() @ x96.float(), 2e-5, "dW (Kw=96, strided destination)")
+    assert_close(G2, P[3].t() @ x96.float()[:, :16], 2e-5, "dW (Kw=16)")
+    assert_close(b0, P[0].sum(0), 2e-5, "bias column sums")
+    assert_close(b2, P[3].sum(0), 2e-5, "bias column sums (narrow job)")
+
+
+def test_head_grad_padding_and_group_sum():
+    _tc_or_skip()
+    from panonerf_b200 import field
+    M, C, S = 6400, 5, 64
+    g = torch.Generator(device=DEV).manual_seed(2)
+    x = torch.randn(M, C, device=DEV, generator=g)
+    cs = torch.zeros(C, device=DEV)
+    pad = field._pad_head_grad(x, cs)
+    assert torch.equal(pad[:, :C].float(), x.bfloat16().float()) and float(pad[:, C:].float().abs().max()) == 0.0
+    assert_close(cs, x.sum(0), 1e-5, "head bias gradient")
+    z = torch.randn(M, 256, device=DEV, generator=g).bfloat16()
+    out = field._group_sum(z[:, :128], S)
+    ref = z[:, :128].float().view(M // S, S, 128).sum(1)
+    assert_close(out, ref, 1e-6, "group_sum (bf16x2 path)")

@@ -349,3 +349,21 @@ def test_no_cpu_fallback():
     from panonerf_b200 import ops
     with pytest.raises(RuntimeError):
         ops.pos_enc(torch.zeros(4, 3), 4)
+
+
+def test_ipe_fast_path_matches_the_exact_path(monkeypatch):
+    """The tiled forward IPE (fixed-point phase, SFU sin/cos, TwoSum-corrected second half) against the kernel that
+    range-reduces every feature in double precision, on negative / large means and tiny / huge variances."""
+    from panonerf_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    M = 10007
+    mean = (torch.rand(M, 3, generator=g) * 2 - 1) * torch.tensor([0.5, 8.0, 60.0])
+    cov = torch.rand(M, 3, generator=g) * torch.tensor([1e-9, 1e-5, 3e-2])
+    fast = torch.empty(M, 96, device=DEV)
+    ops.ipe_into(mean.to(DEV), cov.to(DEV), 0, 16, fast)
+    monkeypatch.setenv("PNB_IPE_SLOW", "1")
+    slow = torch.empty(M, 96, device=DEV)
+    ops.ipe_into(mean.to(DEV), cov.to(DEV), 0, 16, slow)
+    assert float((fast - slow).abs().max()) < 2e-6
+    ref = O.ipe(mean, cov, 0, 16)
+    assert float((fast.cpu() - ref).abs().max()) < 2e-6
