@@ -155,16 +155,33 @@ def run_ours(args):
     packed_d, gt_d = packed_h.to(dev), gt_h.to(dev)
     rays_d = unpack_rays(packed_d)
 
-    def step_resident():
+    def step_eager():
         opt.zero_grad()
         loss = system.training_step((rays_d, gt_d))
         loss.backward()
         opt.step()
         return loss
 
+    # The public API offers the step as a CUDA graph (systems.base_system.GraphedTrainStep): same kernels, one graph
+    # launch instead of ~240 kernel launches.  Eager execution remains available (--no-graph) and is what the
+    # per-kernel CUDA-event profile below uses.
+    graphed = None
+    if not args.no_graph:
+        from panonerf_b200.systems.base_system import GraphedTrainStep
+        try:
+            graphed = GraphedTrainStep(system, opt, rays_d, gt_d)
+        except Exception as e:                   # capture refused: keep the eager step (still the CUDA path)
+            sys.stderr.write(f"bench.py: CUDA-graph capture failed ({type(e).__name__}: {e}); running eagerly\n")
+            graphed = None
+
+    def step_resident():
+        return graphed() if graphed is not None else step_eager()
+
     def step_e2e():
         p = packed_h.to(dev, non_blocking=True)
         g = gt_h.to(dev, non_blocking=True)
+        if graphed is not None:
+            return float(graphed(unpack_rays(p), g))
         opt.zero_grad()
         loss = system.training_step((unpack_rays(p), g))
         loss.backward()
@@ -200,10 +217,15 @@ def run_ours(args):
 
     for _ in range(max(args.warmup, 3)):
         step_resident()
-    ms, launches, clocks, prof, last = timed(step_resident, args.steps, profile=True)
+    ms, launches, clocks, _, last = timed(step_resident, args.steps)
+    if graphed is not None:
+        launches = graphed.launches_per_step * args.steps      # replayed launches are not seen by the host counter
     for _ in range(2):
         step_e2e()
     ms_e2e, _, _, _, _ = timed(step_e2e, args.steps)
+    # per-kernel roofline: the same step, eagerly, with CUDA events around every tensor-core launch
+    step_eager()
+    ms_prof, _, _, prof, _ = timed(step_eager, args.steps, profile=True)
 
     total_rays = RAYS_PER_GPU * world * args.steps
     value = total_rays / (ms / 1e3)
@@ -218,7 +240,8 @@ def run_ours(args):
                                "env samples, surface+ort+chroma losses, fwd+bwd+allreduce+Adam",
                    "rays_per_gpu": RAYS_PER_GPU, "num_samples": N_SAMPLES, "parallelism": f"ray-dp{world}",
                    "l2": "activations per step are several GB (>> 126 MB L2): every step streams from HBM",
-                   "randomized": True},
+                   "randomized": True, "cuda_graph": graphed is not None,
+                   "eager_ms_per_step_with_profile_events": ms_prof / args.steps},
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": int(packed_h.numel() * 4 + gt_h.numel() * 4),
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
@@ -454,6 +477,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-rays", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="run the training step eagerly instead of as a CUDA graph")
     ap.add_argument("--workload", default="train", choices=["train", "render"])
     ap.add_argument("--render-hw", type=int, nargs=2, default=[512, 1024])
     ap.add_argument("--render-chunk", type=int, default=32768)

@@ -139,6 +139,10 @@ int pnb_sum(long long n, const float* x, float scale, float* out, float* ws, voi
  * g is multiplied by grad_scale first (1/world_size after the NCCL sum). step is 1-based. */
 int pnb_adam_step(long long n, float* p, const float* g, float* m, float* v, float lr, float beta1, float beta2,
                   float eps, int step, float grad_scale, void* stream);
+/* same update, step-dependent scalars from DEVICE memory: hyper = {lr, 1 - beta1^step, sqrt(1 - beta2^step)}
+ * (lets the launch sit inside a CUDA graph while the learning-rate schedule advances) */
+int pnb_adam_step_dev(long long n, float* p, const float* g, float* m, float* v, const float* hyper, float beta1,
+                      float beta2, float eps, float grad_scale, void* stream);
 
 /* ---- element-wise helpers of the MLP backward ------------------------------------------------------------- */
 /* out[m,n] = src[m,n] > 0 ? w[n]*g[m] : 0   (seed of the density-Jacobian chain; g nullable => 1) */

@@ -402,6 +402,22 @@ __global__ void adam_kernel(long long n, float* __restrict__ p, const float* __r
   }
 }
 
+// Same update with the step-dependent scalars read from device memory (hyper = {lr, 1-beta1^t, sqrt(1-beta2^t)}), so
+// that the launch can live in a CUDA graph and still follow the learning-rate schedule.
+__global__ void adam_dev_kernel(long long n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                float* __restrict__ v, const float* __restrict__ hyper, float b1, float b2, float eps,
+                                float gscale) {
+  const float lr = hyper[0], bc1 = hyper[1], bc2_sqrt = hyper[2];
+  PNB_GRID_STRIDE(i, n) {
+    float gi = g[i] * gscale;
+    float mi = m[i] * b1 + (1.f - b1) * gi;
+    float vi = v[i] * b2 + (1.f - b2) * gi * gi;
+    m[i] = mi, v[i] = vi;
+    float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = p[i] - (lr / bc1) * (mi / denom);
+  }
+}
+
 // ---- helpers of the MLP backward -----------------------------------------------------------------------------------
 template <typename TS, typename TO>
 __global__ void mask_scale_kernel(long long M, int N, const TS* __restrict__ src, int ld_src, const float* __restrict__ w,
@@ -602,6 +618,14 @@ extern "C" int pnb_adam_step(long long n, float* p, const float* g, float* m, fl
   float bc2s = sqrtf(1.f - powf(beta2, (float)step));
   LAUNCH_1D(adam_kernel, n, n, p, g, m, v, lr, beta1, beta2, eps, bc1, bc2s, grad_scale);
   return finish("adam_step");
+}
+
+extern "C" int pnb_adam_step_dev(long long n, float* p, const float* g, float* m, float* v, const float* hyper,
+                                 float beta1, float beta2, float eps, float grad_scale, void* stream) {
+  PNB_REQUIRE(n >= 0 && hyper != nullptr, "adam_step_dev: hyper (device {lr, 1-b1^t, sqrt(1-b2^t)}) required");
+  if (n == 0) return 0;
+  LAUNCH_1D(adam_dev_kernel, n, n, p, g, m, v, hyper, beta1, beta2, eps, grad_scale);
+  return finish("adam_step_dev");
 }
 
 extern "C" int pnb_mask_scale(long long M, int N, const void* src, int ld_src, const float* w, const float* g,

@@ -192,6 +192,14 @@ def adam_step(p, g, m, v, lr, step, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale
                                        float(lr), beta1, beta2, eps, int(step), float(grad_scale), _stream()), "adam")
 
 
+def adam_step_dev(p, g, m, v, hyper, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
+    """Adam update with {lr, 1-beta1^t, sqrt(1-beta2^t)} read from the device tensor `hyper` (CUDA-graph friendly)."""
+    with torch.cuda.device(p.device):
+        check(_lib.lib().pnb_adam_step_dev(p.numel(), _p(_req(p, "p")), _p(_req(g, "g")), _p(_req(m, "m")),
+                                           _p(_req(v, "v")), _p(_req(hyper, "hyper")), beta1, beta2, eps,
+                                           float(grad_scale), _stream()), "adam_dev")
+
+
 # --------------------------------------------------------------------------------------------------------------
 # autograd Functions (explicit forward / backward kernels)
 # --------------------------------------------------------------------------------------------------------------

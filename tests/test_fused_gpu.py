@@ -171,7 +171,8 @@ def test_backward_kernel_small_batches_do_not_deadlock():
         for _ in range(100):
             dz = field.fused_backward(M, 5, pack, d_rgb, d_den, masks, None)
         torch.cuda.synchronize()
-        assert torch.isfinite(dz.float()).all()
+        # (plane 0 = dz of the 128-wide view layer: its upper 128 columns are never written)
+        assert torch.isfinite(dz[1:].float()).all() and torch.isfinite(dz[0][:, :128].float()).all()
 
 
 def test_wgrad_batch_matches_matmul():

@@ -231,3 +231,52 @@ def test_optimizer_step_decreases_loss():
     # flat views stay wired: parameters changed through the fused kernel
     sd0 = golden_state_dict(g)
     assert not torch.equal(system.mip_nerf.mlp.state_dict()["layers.0.0.weight"].cpu(), sd0["layers.0.0.weight"])
+
+
+def test_cuda_graph_step_equals_eager_step():
+    """GraphedTrainStep replays the eager step: same losses and same parameters after 2 steps
+    (deterministic sampling, so both runs see identical inputs; the learning-rate schedule advances through the
+    device-side hyper-parameter tensor)."""
+    from panonerf_b200 import _lib
+    if not _lib.lib().pnb_tc_available():
+        pytest.skip("not an sm_100 device")
+    from panonerf_b200.systems.base_system import GraphedTrainStep, default_hparams
+    from panonerf_b200.systems.panonerf_system import PanoNeRFSystem
+    from panonerf_b200.datasets.pano_datasets import generate_rays, generate_lit_rays, pixel_radius
+    c2w = np.eye(4, dtype=np.float32)
+    c2w[:3, 3] = [0.1, 0.2, 0.3]
+    h, w = 16, 32
+    sd = O.synth_state_dict(seed=4, width=256, c_density=5)
+    gt = (torch.rand(h * w, 3, generator=torch.Generator().manual_seed(0)) * 2).to(DEV)
+    results = []
+    for use_graph in (False, True):
+        hp = default_hparams("panonerf", precision="bf16")
+        hp.update({"nerf.num_samples": 32, "train.randomized": False})
+        system = PanoNeRFSystem(hp).to(DEV)
+        system.mip_nerf.mlp.load_state_dict(sd)
+        rays = generate_rays(h, w, c2w, 0.0, 10.0, torch.device(DEV, 0))
+        system.env_rays = generate_lit_rays(pixel_radius(h, w, c2w, torch.device(DEV, 0)), num=10,
+                                            device=torch.device(DEV, 0))
+        opt = system.configure_optimizers()
+        losses = []
+        if use_graph:
+            step = GraphedTrainStep(system, opt, rays, gt, warmup=0)     # construction runs step 1
+            losses.append(float(step.loss))
+            losses.append(float(step(rays, gt)))
+        else:
+            hyper = torch.zeros(3, device=DEV)
+            for _ in range(2):
+                hyper.copy_(torch.tensor(opt.next_hyper(), dtype=torch.float32))
+                opt.zero_grad()
+                loss = system.training_step((rays, gt))
+                loss.backward()
+                opt.step_dev(hyper)
+                losses.append(float(loss))
+        torch.cuda.synchronize()
+        results.append((losses, opt.flat_p.clone()))
+    (l0, p0), (l1, p1) = results
+    # same kernels in the same order; the only freedom left is the order of the float atomics in the head-bias sums,
+    # so two steps agree to rounding noise (the network's second-order terms amplify it over longer runs)
+    assert l0[0] == l1[0], (l0, l1)
+    assert abs(l0[1] - l1[1]) <= 2e-5 * abs(l0[1]), (l0, l1)
+    assert float((p0 - p1).norm() / p0.norm()) < 1e-5
