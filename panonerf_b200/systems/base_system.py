@@ -85,6 +85,9 @@ class GraphedTrainStep:
     def __init__(self, system, opt, rays, gts, warmup=3):
         self.system, self.opt = system, opt
         dev = gts.device
+        # With more than one rank the gradient all-reduce (NCCL) and the update stay outside the graph: they are two
+        # launches, and capturing a collective ties the graph to the communicator's internal streams.
+        self.update_in_graph = not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
         self.rays = type(rays)(*[x.clone() for x in rays])
         self.gts = gts.clone()
         self.hyper = torch.zeros(3, device=dev, dtype=torch.float32)
@@ -94,7 +97,7 @@ class GraphedTrainStep:
         with torch.cuda.stream(side):
             for _ in range(warmup):
                 self._set_hyper()
-                self._body()
+                self._body(capturing=False)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self._set_hyper()
@@ -103,18 +106,24 @@ class GraphedTrainStep:
         with torch.cuda.graph(self.graph):
             self.loss = self._body()
         self.launches_per_step = ops.launch_count() - l0
-        self.graph.replay()                    # the captured step itself has not run yet: run it once
+        self._replay()                         # the captured step itself has not run yet: run it once
+
+    def _replay(self):
+        self.graph.replay()
+        if not self.update_in_graph:
+            self.opt.step_dev(self.hyper)
 
     def _set_hyper(self):
         # a fresh pageable tensor per step: the driver stages it before returning, so the host may run many steps
         # ahead of the device without overwriting a value that is still to be copied
         self.hyper.copy_(torch.tensor(self.opt.next_hyper(), dtype=torch.float32))
 
-    def _body(self):
+    def _body(self, capturing=True):
         self.opt.zero_grad()
         loss = self.system.training_step((self.rays, self.gts))
         loss.backward()
-        self.opt.step_dev(self.hyper)
+        if self.update_in_graph or not capturing:
+            self.opt.step_dev(self.hyper)
         return loss.detach()
 
     def __call__(self, rays=None, gts=None):
@@ -125,7 +134,7 @@ class GraphedTrainStep:
                 dst.copy_(src, non_blocking=True)
             self.gts.copy_(gts, non_blocking=True)
         self._set_hyper()
-        self.graph.replay()
+        self._replay()
         return self.loss
 
 
