@@ -32,3 +32,48 @@ def generate_lit_rays(radius, num=80, near=0, far=10.0, type=torch.float16, devi
     view = d / np.linalg.norm(d, axis=-1, keepdims=True)
     fields = (np.zeros_like(d), d, view, float(radius) * one, (4 * np.pi / num) * one, near * one, far * one, 0 * one)
     return Rays(*[torch.tensor(x).to(type).to(device) for x in fields])
+
+
+class DeviceRayFeed:
+    """Device-side training-ray feed: replaces `DataLoader` + the per-ray
+    `PanoDataset.__getitem__` (datasets/pano_datasets.py:271-281, systems/base_system.py:89-96), which hands the
+    trainer one 8-field namedtuple per ray from 28 worker processes.
+
+    The HDR image pool and the rays of every camera (kernel K1, generated once) stay on the GPU as one packed
+    [n_pixels, 14] fp32 table; a batch is `batch_size` pixel ids drawn on the device ('all_images' batching: uniform
+    over all pixels of all images) and two gathers.  Nothing touches the host per step."""
+
+    WIDTHS = (3, 3, 3, 1, 1, 1, 1, 1)          # Rays fields: 14 floats = 56 B per ray
+
+    def __init__(self, images, c2ws, near=0.0, far=10.0, device="cuda", seed=0):
+        device = torch.device(device)
+        assert len(images) == len(c2ws) and len(images) > 0
+        packed, gts = [], []
+        for img, c2w in zip(images, c2ws):
+            img = torch.as_tensor(img, dtype=torch.float32)
+            h, w = img.shape[:2]
+            rays = generate_rays(h, w, np.asarray(c2w, dtype=np.float32), near, far, device)
+            packed.append(torch.cat(list(rays), dim=1))
+            gts.append(img.reshape(h * w, -1)[:, :3].to(device))
+        self.packed = torch.cat(packed, dim=0).contiguous()
+        self.gt = torch.cat(gts, dim=0).contiguous()
+        self.n = self.packed.shape[0]
+        self.gen = torch.Generator(device=device)
+        self.gen.manual_seed(seed)
+
+    def __len__(self):
+        return self.n
+
+    def unpack(self, packed) -> Rays:
+        out, o = [], 0
+        for wd in self.WIDTHS:
+            out.append(packed[:, o:o + wd].contiguous())
+            o += wd
+        return Rays(*out)
+
+    def sample(self, batch_size, return_ids=False):
+        """-> (Rays of [batch_size, .], HDR ground truth [batch_size, 3]) on the device."""
+        ids = torch.randint(self.n, (batch_size,), device=self.packed.device, generator=self.gen)
+        rays = self.unpack(self.packed.index_select(0, ids))
+        gt = self.gt.index_select(0, ids)
+        return (rays, gt, ids) if return_ids else (rays, gt)

@@ -176,6 +176,15 @@ class BaseSystem(torch.nn.Module):
             num_env_samples=hp["nerf.num_env_samples"], precision=hp.get("precision"))
         self.env_rays = None
 
+    RENDER_CHUNK = 32768
+
+    def render_chunk(self):
+        """Rays per forward of `render_image`.  Upstream walks a panorama in `val.chunk_size` = 512-ray chunks (1024
+        sequential forwards, GPU mostly idle - SURVEY.md section 8f rank 2); chunking does not change the result
+        (rays are independent; tests/test_models_gpu.py checks bit-identity), so the knob is only a lower bound here
+        and a panorama is rendered in 32 k-ray chunks (16 forwards, ~2 GB of transient buffers)."""
+        return max(int(self.val_chunk_size), self.RENDER_CHUNK)
+
     def configure_optimizers(self):
         hp = self.hparams
         lr_fn = lambda s: mip_lr_decay(s, hp["optimizer.lr_init"], hp["optimizer.lr_final"], hp["optimizer.max_steps"],

@@ -29,7 +29,7 @@ class MipNeRFSystem(BaseSystem):
     def render_image(self, batch, chunk_size=None):
         rays, rgbs = batch[:2]
         _, height, width, _ = rgbs.shape
-        chunks, _ = rearrange_render_image(rays, chunk_size or self.val_chunk_size)
+        chunks, _ = rearrange_render_image(rays, chunk_size or self.render_chunk())
         outs = [[] for _ in range(6)]
         with torch.no_grad():
             for batch_rays in chunks:

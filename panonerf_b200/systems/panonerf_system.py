@@ -32,7 +32,7 @@ class PanoNeRFSystem(BaseSystem):
     def render_image(self, batch, chunk_size=None):
         rays, rgbs = batch[:2]
         _, height, width, _ = rgbs.shape
-        chunks, _ = rearrange_render_image(rays, chunk_size or self.val_chunk_size)
+        chunks, _ = rearrange_render_image(rays, chunk_size or self.render_chunk())
         keys = ("coarse_rgb", "fine_rgb", "coarse_dep", "fine_dep", "fine_nor", "albedo", "surface_rgb", "shading")
         acc = {k: [] for k in keys}
         with torch.no_grad():

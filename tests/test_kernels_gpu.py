@@ -367,3 +367,26 @@ def test_ipe_fast_path_matches_the_exact_path(monkeypatch):
     assert float((fast - slow).abs().max()) < 2e-6
     ref = O.ipe(mean, cov, 0, 16)
     assert float((fast.cpu() - ref).abs().max()) < 2e-6
+
+
+def test_device_ray_feed_gathers_the_rays_of_its_pixels():
+    """DeviceRayFeed: a sampled batch is exactly the K1 rays / GT colours of the drawn pixel ids,
+    over two cameras, and a training step runs on it."""
+    from panonerf_b200.datasets.pano_datasets import DeviceRayFeed, generate_rays
+    h, w = 16, 32
+    cams = []
+    for k in range(2):
+        c = np.eye(4, dtype=np.float32)
+        c[:3, 3] = [0.1 * k, 0.2, 0.3]
+        cams.append(c)
+    imgs = [torch.rand(h, w, 3, generator=torch.Generator().manual_seed(k)) * 2 for k in range(2)]
+    feed = DeviceRayFeed(imgs, cams, 0.0, 10.0, DEV, seed=3)
+    assert len(feed) == 2 * h * w
+    rays, gt, ids = feed.sample(300, return_ids=True)
+    ref = [generate_rays(h, w, c, 0.0, 10.0, DEV) for c in cams]
+    for f, name in enumerate(rays._fields):
+        full = torch.cat([getattr(r, name) for r in ref], 0)
+        assert torch.equal(getattr(rays, name), full[ids]), name
+    full_gt = torch.cat([i.reshape(-1, 3) for i in imgs], 0).to(DEV)
+    assert torch.equal(gt, full_gt[ids])
+    assert int(ids.min()) >= 0 and int(ids.max()) < len(feed) and len(torch.unique(ids)) > 200
