@@ -978,10 +978,14 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmEnc, const __grid_constan
                       float4 o = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
                                              __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
                       if (op.epi == E_G0) {
-                        float4 prev = dst[i];
-                        o.x += prev.x, o.y += prev.y, o.z += prev.z, o.w += prev.w;
+                        // += the skip-connection part this same thread stored earlier: a vector reduction at L2
+                        // instead of a load (no L2 round trip in front of the store)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(o.x), "f"(o.y),
+                                     "f"(o.z), "f"(o.w)
+                                     : "memory");
+                      } else {
+                        dst[i] = o;
                       }
-                      dst[i] = o;
                     }
                   }
                 }

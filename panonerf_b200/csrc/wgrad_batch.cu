@@ -273,8 +273,8 @@ extern "C" int pnb_wgrad_batch(long long M, int n_maps, const void* const* map_b
   PNB_REQUIRE(map_base && map_desc && jobs && dW && db && workspace, "wgrad_batch: null argument");
   PNB_REQUIRE(M < (1ll << 31) - 64, "wgrad_batch: M too large for 32-bit TMA coordinates");
   if (M == 0) return 0;
-  static WbParams p;        // (large: keep it off the stack; launches are serialised by the caller's stream use)
-  static WbReduceParams rp;
+  static thread_local WbParams p;  // large: kept off the stack; one per host thread (autograd's backward thread)
+  static thread_local WbReduceParams rp;
   for (int i = 0; i < n_maps; ++i) {
     const long long planes = map_desc[3 * i], ld = map_desc[3 * i + 1], cols = map_desc[3 * i + 2];
     PNB_REQUIRE(planes >= 1 && ld % 8 == 0 && cols >= 1 && cols <= ld && ((uintptr_t)map_base[i] % 16 == 0),

@@ -640,12 +640,23 @@ class _Field(torch.autograd.Function):
         dev, f32 = means.device, torch.float32
         wb = WgradBatch(M, dev)
         C = raw_den.shape[1]
-        sizes = [p.numel() for p in ctx.params]
-        flat = torch.zeros(sum(sizes), device=dev, dtype=f32)
-        G, off = {}, 0
-        for nme, p, sz in zip(names, ctx.params, sizes):
-            G[nme] = flat[off:off + sz].view_as(p)
-            off += sz
+        # Gradient destinations.  Parameters managed by FlatAdam carry `_pnb_direct_grad`: their .grad tensors are views
+        # of the optimiser's flat buffer and every kernel below accumulates (+=), so the gradients go straight there
+        # and autograd receives None for them - no zero-fill of a temporary, no 24 add kernels per level.  Anything
+        # else (torch.autograd.grad, plain optimisers) gets freshly computed tensors as usual.
+        direct = all(getattr(p, "_pnb_direct_grad", False) and p.grad is not None and p.grad.is_contiguous()
+                     and p.grad.dtype == f32 for p in ctx.params)
+        G = {}
+        if direct:
+            for nme, p in zip(names, ctx.params):
+                G[nme] = p.grad
+        else:
+            sizes = [p.numel() for p in ctx.params]
+            flat = torch.zeros(sum(sizes), device=dev, dtype=f32)
+            off = 0
+            for nme, p, sz in zip(names, ctx.params, sizes):
+                G[nme] = flat[off:off + sz].view_as(p)
+                off += sz
         W = lambda i: f"layers.{i}.0.weight"
         d_raw_den = torch.zeros(M, C, device=dev, dtype=f32) if d_raw_den is None else d_raw_den.contiguous().clone()
         d_raw_rgb = torch.zeros(M, 3, device=dev, dtype=f32) if d_raw_rgb is None else d_raw_rgb.contiguous()
@@ -706,6 +717,8 @@ class _Field(torch.autograd.Function):
         if need_enc:
             d_means = ops.ipe_vjp(means, covs, cfg["min_deg"], cfg["max_deg"], d_enc).view(ctx.means_shape)
         ctx.bufs = None
+        if direct:
+            return (d_means, None, None, None) + (None,) * len(names)
         return (d_means, None, None, None) + tuple(G[n] for n in names)
 
     @staticmethod

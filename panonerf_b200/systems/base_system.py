@@ -41,6 +41,7 @@ class FlatAdam:
                 self.flat_p[off:off + k].copy_(p.reshape(-1))
                 p.data = self.flat_p[off:off + k].view_as(p)
                 p.grad = self.flat_g[off:off + k].view_as(p)
+                p._pnb_direct_grad = True      # the fused backward accumulates straight into these views (field.py)
                 off += k
         self.lr_fn = lr_fn
         self.step_count = 0
