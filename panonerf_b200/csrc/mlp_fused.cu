@@ -499,7 +499,7 @@ struct EpiCtx {
   uint32_t mbits[4];        // sign-bit words of this thread's units for this op (prefetched one op-tile ahead)
   long long m;              // global sample row of this thread
   int q, hf, lane, row, tile_row0;
-  bool row_ok, save, skip, direct;
+  bool row_ok, save, skip, direct, tma;  // save: this tile stores its planes; tma / direct: how the kernel stores
 };
 
 enum { M_BIAS_RELU = 0, M_BIAS, M_ROWBIAS_RELU, M_MASK, M_LIN, M_SEED, M_BSEED, M_BDZ7 };
@@ -553,11 +553,11 @@ __device__ __forceinline__ void rewrite_abuf_hf(const EpiCtx& c, const FusedPara
   }
   uint32_t r[2][32];
   if (kReadsAcc) tmem_ld32u(c.tacc + op.acc_col + ub * 32, r[0]);
-  if (c.save && !c.direct) {
+  if (c.tma) {
     // The four warps of this half (one per TMEM lane quadrant) store whole 128-row k-blocks together; warp q = 0
-    // issues.  Its TMA stores that still read this tile's buffer (the op before the other tile's) must be done;
-    // at most the other tile's two newer groups may stay pending.
-    if (c.q == 0 && c.lane == 0) bulk_wait_read<2>();
+    // issues one bulk group per (op, tile).  Its group that still reads this tile's buffer (the op before the other
+    // tile's) must be done; only the other tile's newer group may stay pending.
+    if (c.q == 0 && c.lane == 0) bulk_wait_read<1>();
     named_bar_sync(1 + HF, 128);
   }
 #pragma unroll
@@ -634,17 +634,22 @@ __device__ __forceinline__ void rewrite_abuf_hf(const EpiCtx& c, const FusedPara
 #pragma unroll
       for (int j = 0; j < 4; ++j) __stcs(gdst + j, make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]));
     }
-    if (c.save && !c.direct && (u & 1) && op.save_plane >= 0) {
-      // both halves of k-block u/2 are in place for all 128 rows: store the 128 x 64 box (16 KB)
-      fence_async_smem();
-      named_bar_sync(1 + HF, 128);
-      if (c.q == 0 && c.lane == 0) {
-        tma_store_3d(c.tmActs, c.abuf + (u >> 1) * kKbBytes, (u >> 1) * 64, c.tile_row0, op.save_plane);
-        bulk_commit();
-      }
-    }
   }
   fence_async_smem();
+  if (c.tma) {
+    // this half's k-blocks are in place for all 128 rows: one rendezvous, then the 128 x 64 boxes (16 KB each) leave
+    // as one bulk group.  (Always committed - also for ops without a plane and for the phantom tile of an odd tail -
+    // so that the one-group-per-(op, tile) count the wait above relies on stays exact.)
+    named_bar_sync(1 + HF, 128);
+    if (c.q == 0 && c.lane == 0) {
+      if (c.save && op.save_plane >= 0) {
+#pragma unroll
+        for (int kb = ub / 2; kb < (ub + n_mine) / 2; ++kb)
+          tma_store_3d(c.tmActs, c.abuf + kb * kKbBytes, kb * 64, c.tile_row0, op.save_plane);
+      }
+      bulk_commit();
+    }
+  }
   tc_fence_before();
   __syncwarp();
   if (c.lane == 0) mbar_arrive(c.abuf_ready);
@@ -845,7 +850,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmEnc, const __grid_constan
     c.q = warp & 3;            // TMEM lane quadrant (hardware rule: warp id % 4)
     c.hf = (warp - 2) >> 2;    // which of the two warps of the quadrant
     c.lane = lane, c.row = c.q * 32 + lane, c.save = p.save != 0, c.skip = (p.debug & 2) != 0;
-    c.direct = p.save == 2;
+    c.direct = p.save == 2, c.tma = p.save == 1;
     const uint32_t tlane = tmem_base + ((uint32_t)(c.q * 32) << 16);
     if (lane == 0) {           // both activation buffers / accumulators start out free
       mbar_arrive(&bars->abuf_ready[0]);
