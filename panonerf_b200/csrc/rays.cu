@@ -179,6 +179,43 @@ __device__ __forceinline__ float cos_accurate(float y) {
   return c;
 }
 
+// Exact-phase variants for the gradient kernels: the phase of y = mean * 2^sh modulo 2 pi is a left shift of the 64-bit
+// fixed-point fraction of mean / (2 pi) (one double multiply per mean instead of a double-precision reduction per
+// feature); sin / cos of the reduced argument come from the same Cephes polynomials as sincos_accurate, so the
+// accuracy is unchanged (~1 ulp), unlike the SFU path of the forward kernel.
+__device__ __forceinline__ void phase_fixed(float mean, uint32_t* hi, uint32_t* lo) {
+  double u = (double)mean * 0.15915494309189534561;  // turns
+  u -= floor(u);
+  const unsigned long long U = (unsigned long long)(u * 18446744073709551616.0);
+  *hi = (uint32_t)(U >> 32), *lo = (uint32_t)U;
+}
+__device__ __forceinline__ void sincos_phase(uint32_t ph, float* sn, float* cs) {
+  const uint32_t q = (ph + 0x20000000u) >> 30;       // nearest quarter turn
+  const int f = (int)(ph - (q << 30));               // remainder in [-2^29, 2^29) units of 2^-32 turn
+  const float rf = (float)f * 1.46291807926715968e-9f;  // * 2 pi / 2^32  -> [-pi/4, pi/4]
+  const float z = rf * rf;
+  const float ps = fmaf(rf * z, fmaf(z, fmaf(z, -1.9515295891e-4f, 8.3321608736e-3f), -1.6666654611e-1f), rf);
+  const float pc = fmaf(z, fmaf(z, fmaf(z, fmaf(z, 2.443315711809948e-5f, -1.388731625493765e-3f), 4.166664568298827e-2f), -0.5f), 1.0f);
+  const float s0 = (q & 1) ? pc : ps;
+  const float c0 = (q & 1) ? ps : pc;
+  *sn = (q & 2) ? -s0 : s0;
+  *cs = ((q + 1) & 2) ? -c0 : c0;
+}
+// cos(y) and cos(fl32(y + fl32(pi/2))) for y = mean * 2^sh with phase `ph` (the second argument is what the reference
+// differentiates, mip.py:428): fl32(y + pi/2) = y + pi/2 + eps with eps recovered exactly by a TwoSum.
+__device__ __forceinline__ void cos_pair_phase(float y, uint32_t ph, float* cy, float* cz) {
+  float sn, cs;
+  sincos_phase(ph, &sn, &cs);
+  const float z = y + kHalfPiF;
+  const float bb = z - y;
+  const float err = (y - (z - bb)) + (kHalfPiF - bb);
+  const float eps = 4.37113900018624283e-8f - err;
+  const float ce = fmaf(-0.5f * eps, eps, 1.0f);
+  const float se = eps * fmaf(-0.16666667f * eps, eps, 1.0f);
+  *cy = cs;
+  *cz = -(sn * ce + cs * se);
+}
+
 // One thread per (sample, l*3+c): writes the sin feature at column j and the cos feature at column 3L+j, so a
 // warp writes two contiguous runs per sample row (coalesced).  exp underflow short-circuits the sinf slow path.
 template <typename T>
@@ -277,13 +314,19 @@ __global__ void ipe_vjp_kernel(long long M, int min_deg, int L, const float* __r
     int c = (int)(idx - m * 3);
     float mean = means[idx], cov = covs[idx];
     float acc = 0.f;
+    const bool fast = min_deg >= 0 && min_deg + L <= 31;
+    uint32_t hi = 0, lo = 0;
+    if (fast) phase_fixed(mean, &hi, &lo);
     for (int l = 0; l < L; ++l) {
       float sc = exp2f((float)(min_deg + l));
       float e = expf(-0.5f * (cov * (sc * sc)));
       if (e == 0.f) break;  // larger l only underflow harder
       float y = mean * sc;
       float gs = to_f32<T>(g[m * ld + 3 * l + c]), gc = to_f32<T>(g[m * ld + F + 3 * l + c]);
-      acc += sc * (e * (gs * cos_accurate(y) + gc * cos_accurate(y + kHalfPiF)));
+      float cy, cz;
+      if (fast) cos_pair_phase(y, __funnelshift_l(lo, hi, min_deg + l), &cy, &cz);
+      else cy = cos_accurate(y), cz = cos_accurate(y + kHalfPiF);
+      acc += sc * (e * (gs * cy + gc * cz));
     }
     d_means[idx] = acc;
   }
@@ -306,8 +349,16 @@ __global__ void ipe_jvp_kernel(long long M, int min_deg, int L, const float* __r
     float os = 0.f, oc = 0.f;
     if (e != 0.f) {
       float w = v[3 * m + c] * sc * e;
-      os = w * cos_accurate(y);
-      oc = w * cos_accurate(y + kHalfPiF);
+      float cy, cz;
+      if (min_deg >= 0 && min_deg + L <= 31) {
+        uint32_t hi, lo;
+        phase_fixed(means[3 * m + c], &hi, &lo);
+        cos_pair_phase(y, __funnelshift_l(lo, hi, min_deg + l), &cy, &cz);
+      } else {
+        cy = cos_accurate(y), cz = cos_accurate(y + kHalfPiF);
+      }
+      os = w * cy;
+      oc = w * cz;
     }
     out[m * ld + j] = from_f32<T>(os);
     out[m * ld + F + j] = from_f32<T>(oc);

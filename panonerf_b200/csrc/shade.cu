@@ -726,36 +726,35 @@ __global__ void group_sum_bf16x2_kernel(long long G, int N, int group, const __n
 }
 
 // Head gradients (d raw_rgb [M,3], d raw_sigma.. [M,C]) as tensor-core operands: bf16 [M,64], zero-padded, plus their
-// column sums (= the head's bias gradient) in the same pass.  One thread per row.
+// column sums (= the head's bias gradient) in the same pass.  Eight consecutive lanes own one 128-byte output row
+// (16 bytes each), so a warp stores 512 contiguous bytes per instruction.
 __global__ void pad_head_grad_kernel(long long M, int C, const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
                                      float* __restrict__ colsum) {
-  float acc[16];
+  const int chunk = threadIdx.x & 7;  // columns [8*chunk, 8*chunk + 8)
+  float acc[8];
 #pragma unroll
-  for (int c = 0; c < 16; ++c) acc[c] = 0.f;
-  for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
-    float v[16];
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  const long long rows_per_pass = (long long)gridDim.x * (blockDim.x >> 3);
+  for (long long m = blockIdx.x * (long long)(blockDim.x >> 3) + (threadIdx.x >> 3); m < M; m += rows_per_pass) {
+    float v[8];
 #pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      v[c] = c < C ? src[m * C + c] : 0.f;
-      acc[c] += v[c];
+    for (int k = 0; k < 8; ++k) {
+      const int c = chunk * 8 + k;
+      v[k] = c < C ? src[m * C + c] : 0.f;
+      acc[k] += v[k];
     }
-    uint4* row = reinterpret_cast<uint4*>(dst + m * 64);
-    __nv_bfloat162 h[8];
+    __nv_bfloat162 h[4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) h[k] = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
-    row[0] = *reinterpret_cast<uint4*>(&h[0]);
-    row[1] = *reinterpret_cast<uint4*>(&h[4]);
-    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-    for (int j = 2; j < 8; ++j) row[j] = z;
+    for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+    reinterpret_cast<uint4*>(dst + m * 64)[chunk] = *reinterpret_cast<uint4*>(h);
   }
-  if (colsum != nullptr) {
+  if (colsum != nullptr) {  // lanes l, l+8, l+16, l+24 share a chunk; all lanes take part in the shuffles
 #pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      if (c < C) {
-        const float s = warp_sum(acc[c]);
-        if ((threadIdx.x & 31) == 0) atomicAdd(colsum + c, s);
-      }
+    for (int k = 0; k < 8; ++k) {
+      float s = acc[k];
+      s += __shfl_xor_sync(0xffffffffu, s, 8);
+      s += __shfl_xor_sync(0xffffffffu, s, 16);
+      if ((threadIdx.x & 31) < 8 && chunk * 8 + k < C) atomicAdd(colsum + chunk * 8 + k, s);
     }
   }
 }
@@ -781,6 +780,6 @@ extern "C" int pnb_pad_head_grad(long long M, int C, const float* src, void* dst
   PNB_REQUIRE(M >= 0 && C >= 1 && C <= 16 && src != nullptr && dst_bf16 != nullptr, "pad_head_grad: bad arguments");
   PNB_REQUIRE(((uintptr_t)dst_bf16 % 16) == 0, "pad_head_grad: dst must be 16-byte aligned");
   if (M == 0) return 0;
-  pnb::pad_head_grad_kernel<<<grid_for(M, 128, 8), 128, 0, as_stream(stream)>>>(M, C, src, (__nv_bfloat16*)dst_bf16, colsum);
+  pnb::pad_head_grad_kernel<<<grid_for(M * 8, 256, 8), 256, 0, as_stream(stream)>>>(M, C, src, (__nv_bfloat16*)dst_bf16, colsum);
   return finish("pad_head_grad");
 }
