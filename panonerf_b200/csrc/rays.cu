@@ -93,33 +93,37 @@ __device__ __forceinline__ float strat_t(int i, int N, float nr, float fr, const
   return lower + (upper - lower) * rnd[i];
 }
 
-__global__ void sample_cast_kernel(long long R, int N, const float* __restrict__ origins, int o_div,
-                                   const float* __restrict__ dirs, const float* __restrict__ radii,
-                                   const float* __restrict__ near_v, const float* __restrict__ far_v, int d_mod,
-                                   const float* __restrict__ s_lin, const float* __restrict__ t_rand, int rand_ld,
-                                   int disparity, float* __restrict__ t_out, float* __restrict__ means,
-                                   float* __restrict__ covs) {
-  const long long total = R * (N + 1);
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    long long r = idx / (N + 1);
-    int i = (int)(idx - r * (N + 1));
-    long long rd = d_mod ? r % d_mod : r, ro = r / o_div;
-    float nr = near_v[rd], fr = far_v[rd];
+// One warp per ray: the per-ray constants are loaded once, the lanes walk the fence-posts, and there is no 64-bit
+// index division per sample (the flat-index version spent most of its instructions there).
+__global__ void __launch_bounds__(256)
+sample_cast_kernel(long long R, int N, const float* __restrict__ origins, int o_div,
+                   const float* __restrict__ dirs, const float* __restrict__ radii,
+                   const float* __restrict__ near_v, const float* __restrict__ far_v, int d_mod,
+                   const float* __restrict__ s_lin, const float* __restrict__ t_rand, int rand_ld,
+                   int disparity, float* __restrict__ t_out, float* __restrict__ means,
+                   float* __restrict__ covs) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  for (long long r = warp0; r < R; r += (long long)gridDim.x * (blockDim.x >> 5)) {
+    const long long rd = d_mod ? r % d_mod : r, ro = r / o_div;
+    const float nr = near_v[rd], fr = far_v[rd], rad = radii[rd];
+    const float o[3] = {origins[3 * ro], origins[3 * ro + 1], origins[3 * ro + 2]};
+    const float d[3] = {dirs[3 * rd], dirs[3 * rd + 1], dirs[3 * rd + 2]};
     const float* rnd = t_rand ? t_rand + (long long)rand_ld * r : nullptr;
-    float t0 = strat_t(i, N, nr, fr, s_lin, rnd, disparity);
-    t_out[idx] = t0;
-    if (i < N) {
-      float t1 = strat_t(i + 1, N, nr, fr, s_lin, rnd, disparity);
-      float o[3] = {origins[3 * ro], origins[3 * ro + 1], origins[3 * ro + 2]};
-      float d[3] = {dirs[3 * rd], dirs[3 * rd + 1], dirs[3 * rd + 2]};
-      float m[3], c[3];
-      frustum_gaussian(t0, t1, radii[rd], o, d, m, c);
-      long long s = r * N + i;
+    float* trow = t_out + r * (N + 1);
+    for (int i = lane; i <= N; i += 32) {
+      const float t0 = strat_t(i, N, nr, fr, s_lin, rnd, disparity);
+      trow[i] = t0;
+      if (i < N) {
+        const float t1 = strat_t(i + 1, N, nr, fr, s_lin, rnd, disparity);
+        float m[3], c[3];
+        frustum_gaussian(t0, t1, rad, o, d, m, c);
+        const long long sidx = r * N + i;
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        means[3 * s + k] = m[k];
-        covs[3 * s + k] = c[k];
+        for (int k = 0; k < 3; ++k) {
+          means[3 * sidx + k] = m[k];
+          covs[3 * sidx + k] = c[k];
+        }
       }
     }
   }
@@ -415,7 +419,7 @@ extern "C" int pnb_sample_cast(int R, int N, const float* origins, int o_div, co
                                float* means, float* covs, void* stream) {
   PNB_REQUIRE(R >= 0 && N > 0 && o_div >= 1 && d_mod >= 0, "sample_cast: bad sizes");
   if (R == 0) return 0;
-  sample_cast_kernel<<<grid_for((long long)R * (N + 1), 256), 256, 0, as_stream(stream)>>>(
+  sample_cast_kernel<<<grid_for((long long)R * 32, 256, 8), 256, 0, as_stream(stream)>>>(
       R, N, origins, o_div, directions, radii, near_v, far_v, d_mod, s_lin, t_rand, rand_ld, disparity, t_out, means,
       covs);
   return finish("sample_cast");

@@ -29,6 +29,46 @@ composite_fwd_kernel(long long R, int N, const float* __restrict__ rgb, const fl
     const float* tr = t + r * (N + 1);
     double carry = 0.0;
     float c0 = 0.f, c1 = 0.f, c2 = 0.f, a = 0.f, s = 0.f;
+    if (N <= 64) {
+      // both halves of the ray at once: all loads are issued up front and the two fp64 scans are independent chains
+      // (same values, same order of additions as the generic loop below - bit-identical results)
+      const int i0 = lane, i1 = lane + 32;
+      const bool ok0 = i0 < N, ok1 = i1 < N;
+      const float t00 = ok0 ? tr[i0] : 0.f, t01 = ok0 ? tr[i0 + 1] : 0.f;
+      const float t10 = ok1 ? tr[i1] : 0.f, t11 = ok1 ? tr[i1 + 1] : 0.f;
+      const float den0 = ok0 ? density[r * N + i0] : 0.f, den1 = ok1 ? density[r * N + i1] : 0.f;
+      float ca[3] = {0.f, 0.f, 0.f}, cb[3] = {0.f, 0.f, 0.f};
+      if (ok0) {
+        const float* c = rgb + 3 * (r * N + i0);
+        ca[0] = c[0], ca[1] = c[1], ca[2] = c[2];
+      }
+      if (ok1) {
+        const float* c = rgb + 3 * (r * N + i1);
+        cb[0] = c[0], cb[1] = c[1], cb[2] = c[2];
+      }
+      const float sd0 = ok0 ? den0 * ((t01 - t00) * dnorm) : 0.f;
+      const float sd1 = ok1 ? den1 * ((t11 - t10) * dnorm) : 0.f;
+      const double incl0 = warp_scan_incl((double)sd0, lane);
+      const double incl1 = warp_scan_incl((double)sd1, lane);
+      const double prev0 = __shfl_up_sync(0xffffffffu, incl0, 1), prev1 = __shfl_up_sync(0xffffffffu, incl1, 1);
+      const double tot0 = __shfl_sync(0xffffffffu, incl0, 31);
+      const double excl0 = 0.0 + (lane == 0 ? 0.0 : prev0);
+      const double excl1 = (0.0 + tot0) + (lane == 0 ? 0.0 : prev1);
+      const float w0 = (1.f - expf(-sd0)) * expf(-(float)excl0);
+      const float w1 = (1.f - expf(-sd1)) * expf(-(float)excl1);
+      if (ok0) {
+        weights[r * N + i0] = w0;
+        c0 += w0 * ca[0], c1 += w0 * ca[1], c2 += w0 * ca[2];
+        a += w0;
+        s += w0 * (0.5f * (t00 + t01));
+      }
+      if (ok1) {
+        weights[r * N + i1] = w1;
+        c0 += w1 * cb[0], c1 += w1 * cb[1], c2 += w1 * cb[2];
+        a += w1;
+        s += w1 * (0.5f * (t10 + t11));
+      }
+    } else
     for (int base = 0; base < N; base += 32) {
       int i = base + lane;
       bool ok = i < N;
