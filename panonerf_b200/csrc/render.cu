@@ -200,6 +200,7 @@ resample_kernel(long long R, int N, const float* __restrict__ t, const float* __
     for (int k = 0; k < 8; ++k) {
       int i = lane + 32 * k;
       blur[k] = 0.f;
+      if (32 * k >= N) continue;  // (warp-uniform: N = 64 touches two of the eight register slots)
       if (i < N) {
         float wl = sw[i > 0 ? i - 1 : 0], wc = sw[i], wr = sw[i + 1 < N ? i + 1 : N - 1];
         blur[k] = blur_pool ? 0.5f * (fmaxf(wl, wc) + fmaxf(wc, wr)) + padding : wc;
@@ -214,6 +215,7 @@ resample_kernel(long long R, int N, const float* __restrict__ t, const float* __
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       int i = lane + 32 * k;
+      if (32 * k >= N) continue;
       if (i < N) sw[i] = (blur[k] + add) / wsum;
     }
     __syncwarp();
