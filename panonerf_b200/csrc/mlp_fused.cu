@@ -6,9 +6,10 @@
 // Why: layer-by-layer GEMMs (gemm_tc.cu) stream every [M,256] activation through HBM and are bound by it at
 // ~0.3 of the tensor roofline.  Here a CTA owns TWO 128-sample tiles at a time and ping-pongs between them:
 //
-//   warp 0      producer : streams the pre-swizzled bf16 weight tiles (cp.async.bulk, L2 -> SMEM ring of 32 KB slots)
-//                          and the IPE k-blocks of each tile (TMA tensor load) in exactly the order the MMA warp
-//                          consumes them;
+//   warp 0      producer : streams the pre-swizzled bf16 weight tiles (cp.async.bulk, L2 -> SMEM ring of three 32 KB
+//                          slots) and the IPE k-blocks of each tile (TMA tensor load) following a static plan of the
+//                          ring (plan_ring): tile 1 walks the k-blocks of an op backwards so that it re-uses the
+//                          slots tile 0 touched last (5 loads instead of 8 per layer and tile pair);
 //   warp 1      MMA      : one thread issues tcgen05.mma (M=128, N<=256, K=16, bf16 -> fp32 TMEM).  A comes from the
 //                          tile's activation buffer in SMEM (128B-swizzled K-major, 4 k-blocks of 64 columns), B from
 //                          the ring, D is the tile's own 256-column TMEM accumulator.  The program alternates
@@ -55,6 +56,9 @@ constexpr int kReplicas = 1;
 constexpr int kBiasHE = 2048, kBiasHD = 2304, kBiasC = 2320, kWDen = 2336, kWCol = kWDen + 16 * 256,
               kBiasFloats = kWCol + 4 * 128;
 
+// Step flags.  The kernel consumes F_AENC only (A operand = the IPE tile in the ring instead of the activation buffer);
+// the other three annotate the forward walk of a step list - which step needs / releases the IPE tile, which one starts
+// the accumulation - and are re-derived per tile by plan_ring (tile 1 walks every op backwards).
 enum : uint32_t { F_AENC = 1, F_LOADENC = 2, F_RELENC = 4, F_FIRST = 8 };
 enum { P_FWD = 0, P_FWDJ = 1, P_BWD = 2, P_JADJ = 3, kNumProgs = 4 };
 
