@@ -458,16 +458,31 @@ __global__ void pack_bias_kernel(const PackArgs a, float* __restrict__ bblob) {
 // ---------------------------------------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
+// L2 policies: the 2.2 MB weight blob is re-streamed by every CTA for every tile pair and must stay in L2
+// (evict_last), while the saved activation planes are written once and read milliseconds later by the weight-gradient
+// kernel (evict_first) - without the hints GBs of planes flush the weights out of L2 in the training variants.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
 }
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2,
+                                             uint64_t pol) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4}], [%1], %5;" ::"l"(
                    reinterpret_cast<uint64_t>(map)),
-               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "l"(pol)
                : "memory");
 }
 __device__ __forceinline__ void tmem_ld32u(uint32_t taddr, uint32_t* r) {
@@ -503,6 +518,7 @@ struct EpiCtx {
   uint32_t mbits[4];        // sign-bit words of this thread's units for this op (prefetched one op-tile ahead)
   long long m;              // global sample row of this thread
   int q, hf, lane, row, tile_row0;
+  uint64_t store_policy;    // L2 evict_first for the saved planes
   bool row_ok, save, skip, direct, tma;  // save: this tile stores its planes; tma / direct: how the kernel stores
 };
 
@@ -649,7 +665,7 @@ __device__ __forceinline__ void rewrite_abuf_hf(const EpiCtx& c, const FusedPara
       if (c.save && op.save_plane >= 0) {
 #pragma unroll
         for (int kb = ub / 2; kb < (ub + n_mine) / 2; ++kb)
-          tma_store_3d(c.tmActs, c.abuf + kb * kKbBytes, kb * 64, c.tile_row0, op.save_plane);
+          tma_store_3d(c.tmActs, c.abuf + kb * kKbBytes, kb * 64, c.tile_row0, op.save_plane, c.store_policy);
       }
       bulk_commit();
     }
@@ -803,6 +819,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmEnc, const __grid_constan
     if (lane == 0) {
       uint32_t eph = 0;  // per-slot phase bits of the empty barriers
       const uint8_t* wblob = p.wblob + (size_t)(blockIdx.x % p.replicas) * p.blob_stride;
+      const uint64_t wpol = l2_policy_evict_last();
       const int n_loads = c_prog[P].n_loads;
       for (long long pair = blockIdx.x; pair < p.num_pairs; pair += gridDim.x) {
         for (int l = 0; l < n_loads; ++l) {
@@ -821,7 +838,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmEnc, const __grid_constan
             mbar_arrive(&bars->full[slot]);
           } else {
             mbar_expect_tx(&bars->full[slot], ld.bytes);
-            bulk_load_1d(ring + (size_t)slot * kSlotBytes, wblob + ld.blob_off, ld.bytes, &bars->full[slot]);
+            bulk_load_1d(ring + (size_t)slot * kSlotBytes, wblob + ld.blob_off, ld.bytes, &bars->full[slot], wpol);
           }
         }
       }
@@ -855,6 +872,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmEnc, const __grid_constan
     c.hf = (warp - 2) >> 2;    // which of the two warps of the quadrant
     c.lane = lane, c.row = c.q * 32 + lane, c.save = p.save != 0, c.skip = (p.debug & 2) != 0;
     c.direct = p.save == 2, c.tma = p.save == 1;
+    c.store_policy = l2_policy_evict_first();
     const uint32_t tlane = tmem_base + ((uint32_t)(c.q * 32) << 16);
     if (lane == 0) {           // both activation buffers / accumulators start out free
       mbar_arrive(&bars->abuf_ready[0]);
