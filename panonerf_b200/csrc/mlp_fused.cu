@@ -478,6 +478,14 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
       "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_hint(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                                 uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], "
+      "[%2], %5;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(pol)
+      : "memory");
+}
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2,
                                              uint64_t pol) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4}], [%1], %5;" ::"l"(
@@ -628,7 +636,10 @@ __device__ __forceinline__ void rewrite_abuf_hf(const EpiCtx& c, const FusedPara
 #pragma unroll
           for (int g = 0; g < 4; ++g) sg[g] = __funnelshift_l(__float_as_uint(x[8 * g + j]), sg[g], 1);
         }
-        c.mask[(op.mask_plane * 8 + u) * kTileM + c.row] = ~((sg[0] << 24) | (sg[1] << 16) | (sg[2] << 8) | sg[3]);
+        const uint32_t word = ~((sg[0] << 24) | (sg[1] << 16) | (sg[2] << 8) | sg[3]);
+        uint32_t* mdst = c.mask + (op.mask_plane * 8 + u) * kTileM + c.row;
+        if (p.masks_per_tile) __stcs(mdst, word);  // training: next read by the backward kernels, stream past L2
+        else *mdst = word;                         // inference: read back by this kernel's Jacobian sweep
       }
     }
     if (kAppliesMask) {
@@ -820,6 +831,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmEnc, const __grid_constan
       uint32_t eph = 0;  // per-slot phase bits of the empty barriers
       const uint8_t* wblob = p.wblob + (size_t)(blockIdx.x % p.replicas) * p.blob_stride;
       const uint64_t wpol = l2_policy_evict_last();
+      const uint64_t epol = l2_policy_evict_first();  // IPE tiles are read once per use
       const int n_loads = c_prog[P].n_loads;
       for (long long pair = blockIdx.x; pair < p.num_pairs; pair += gridDim.x) {
         for (int l = 0; l < n_loads; ++l) {
@@ -832,8 +844,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmEnc, const __grid_constan
             if (tile >= p.num_tiles) tile = p.num_tiles - 1;  // phantom tile of an odd tail: recompute the last one
             const int row0 = (int)(tile * kTileM);
             mbar_expect_tx(&bars->full[slot], 2 * kKbBytes);
-            tma_load_2d(ring + (size_t)slot * kSlotBytes, &tmEnc, &bars->full[slot], 0, row0);
-            tma_load_2d(ring + (size_t)slot * kSlotBytes + kKbBytes, &tmEnc, &bars->full[slot], 64, row0);
+            tma_load_2d_hint(ring + (size_t)slot * kSlotBytes, &tmEnc, &bars->full[slot], 0, row0, epol);
+            tma_load_2d_hint(ring + (size_t)slot * kSlotBytes + kKbBytes, &tmEnc, &bars->full[slot], 64, row0, epol);
           } else if (p.debug & 1) {  // experiment: no weight traffic (the MMAs read whatever the slot holds)
             mbar_arrive(&bars->full[slot]);
           } else {
