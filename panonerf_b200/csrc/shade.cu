@@ -748,13 +748,23 @@ __global__ void pad_head_grad_kernel(long long M, int C, const float* __restrict
     for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
     reinterpret_cast<uint4*>(dst + m * 64)[chunk] = *reinterpret_cast<uint4*>(h);
   }
-  if (colsum != nullptr) {  // lanes l, l+8, l+16, l+24 share a chunk; all lanes take part in the shuffles
+  if (colsum != nullptr) {
+    // lanes l, l+8, l+16, l+24 share a chunk (all lanes take part in the shuffles); then one shared-memory pass over
+    // the block's warps, so that only 16 atomics per BLOCK reach the few hot global addresses
+    __shared__ float part[8][16];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       float s = acc[k];
       s += __shfl_xor_sync(0xffffffffu, s, 8);
       s += __shfl_xor_sync(0xffffffffu, s, 16);
-      if ((threadIdx.x & 31) < 8 && chunk * 8 + k < C) atomicAdd(colsum + chunk * 8 + k, s);
+      if (lane < 2) part[warp][lane * 8 + k] = s;   // lane 0: columns 0..7, lane 1: columns 8..15
+    }
+    __syncthreads();
+    if (threadIdx.x < 16 && (int)threadIdx.x < C) {
+      float s = 0.f;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += part[w][threadIdx.x];
+      atomicAdd(colsum + threadIdx.x, s);
     }
   }
 }
