@@ -104,3 +104,45 @@ def test_bench_reference_arm_runs_on_cpu():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "train_rays_per_s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_adam_hyper_parameters_for_the_graph_step():
+    """FlatAdam.next_hyper feeds the device-side update of GraphedTrainStep: lr from the MipLRDecay schedule and the
+    two Adam bias corrections exactly as pnb_adam_step forms them on the host (1 - b1^t, sqrt(1 - b2^t))."""
+    import math
+    from panonerf_b200.systems.base_system import FlatAdam, mip_lr_decay
+
+    opt = FlatAdam.__new__(FlatAdam)                       # no parameters needed for the schedule bookkeeping
+    opt.step_count = 0
+    opt.lr_fn = lambda s: mip_lr_decay(s, 2e-4, 2e-5, 44000, 120, 0.01)
+    for t in range(1, 6):
+        lr, bc1, bc2s = opt.next_hyper()
+        assert opt.step_count == t
+        assert lr == mip_lr_decay(t - 1, 2e-4, 2e-5, 44000, 120, 0.01)
+        assert abs(bc1 - (1 - 0.9 ** t)) < 1e-15 and abs(bc2s - math.sqrt(1 - 0.999 ** t)) < 1e-15
+
+
+def test_bench_roofline_report_schema():
+    """bench.py's roofline object from a (fake) per-kernel profile: dominant family first, the contract's keys present,
+    tensor-bound families measured in TFLOP/s against the sustained peak, HBM-bound ones in GB/s."""
+    import bench
+
+    class Ev:
+        def __init__(self, ms):
+            self.ms = ms
+
+        def elapsed_time(self, other):
+            return other.ms
+
+    prof = {"wgrad_batch": dict(events=[(Ev(0), Ev(2.0))], bytes=10e9, flops=1e12),
+            "mlp_fused": dict(events=[(Ev(0), Ev(1.0))], bytes=1e9, flops=1.2e12),
+            "mlp_fused_bwd": dict(events=[(Ev(0), Ev(0.5))], bytes=1e9, flops=0.3e12)}
+    r = bench.roofline_from_profile(prof, 1, dict(hbm=6500.0, tf_burst=1685.0, tf_sust=1382.0, src="measured"))
+    assert r["kernel"] == "wgrad_batch" and r["bound"] == "hbm" and r["unit"] == "GB/s"
+    assert abs(r["achieved"] - 5000.0) < 1e-6 and abs(r["frac"] - 5000.0 / 6500.0) < 1e-9
+    for k in ("peak", "traffic", "launches_per_step", "avg_launch_ms", "kernel_ms_per_step", "other_kernels"):
+        assert k in r
+    o = r["other_kernels"]["mlp_fused"]
+    assert o["bound"] == "tensor" and o["unit"] == "TFLOP/s" and abs(o["achieved"] - 1200.0) < 1e-6
+    allp = r["fused_mlp_all_programs"]
+    assert abs(allp["kernel_ms_per_step"] - 1.5) < 1e-9 and abs(allp["achieved"] - 1000.0) < 1e-6
