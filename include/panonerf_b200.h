@@ -101,6 +101,12 @@ int pnb_composite_bwd(int R, int N, const float* rgb, const float* density, cons
  * blur_pool=0 skips the blur-pool/padding step (plain sorted_piecewise_constant_pdf on the given weights). */
 int pnb_resample(int R, int N, const float* t, const float* weights, float padding, int blur_pool, const float* u,
                  int u_ld, float* new_t, long long* inds, void* stream);
+/* Same, followed by cast_rays on the new fence-posts in the same kernel (models/mip.py:351 -> :67-89): the whole of
+ * resample_along_rays in one launch.  means/covs [R,N,3] (both nullable together: then identical to pnb_resample);
+ * origins/directions [R,3], radii [R]. */
+int pnb_resample_cast(int R, int N, const float* t, const float* weights, float padding, int blur_pool,
+                      const float* u, int u_ld, float* new_t, long long* inds, const float* origins,
+                      const float* directions, const float* radii, float* means, float* covs, void* stream);
 
 /* ---- normals / orientation loss / albedo compositing: models/pano_mip_nerf.py:296-317 ---------------------- */
 int pnb_normals_fwd(int R, int N, const float* n_raw, const float* weights, const float* dirs,

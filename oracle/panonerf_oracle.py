@@ -241,6 +241,22 @@ def resample_along_rays(origins, directions, radii, t, weights, randomized, padd
     return new_t, cast_cone(new_t, origins, directions, radii)
 
 
+def resample_case(n: int, rays: int = 4096):
+    """Seeded config-size inputs of the resampling tests / golden vectors (tests/golden/make_golden.py): peaky
+    weights incl. an all-zero ray and a single spike, sorted fence-posts, random ray geometry."""
+    gen = torch.Generator().manual_seed(1000 + n)
+    w = torch.rand(rays, n, generator=gen) ** 4
+    w[0] = 0.0
+    w[1] = 0.0
+    w[1, n // 2] = 1.0
+    w[2] = 1e-9                                   # weight_sum below eps: the padding branch of mip.py:253-257
+    t = torch.sort(torch.rand(rays, n + 1, generator=gen) * 10, dim=-1).values
+    o = torch.rand(rays, 3, generator=gen) - 0.5
+    d = torch.nn.functional.normalize(torch.randn(rays, 3, generator=gen), dim=-1)
+    rad = torch.full((rays, 1), 0.0035)
+    return t, w, o, d, rad
+
+
 # ----------------------------------------------------------------------------------------------------------
 # surface branch / tone mapping
 # ----------------------------------------------------------------------------------------------------------

@@ -3,6 +3,7 @@
 // HBM.  HBM-bound: composite fwd moves 24 B/sample + 36 B/ray, bwd 40 B/sample + 32 B/ray, resample
 // 12 B/sample + 8 B/ray.
 #include "common.cuh"
+#include "geom.cuh"
 
 namespace pnb {
 
@@ -178,75 +179,158 @@ composite_bwd_kernel(long long R, int N, const float* __restrict__ rgb, const fl
   }
 }
 
-// models/mip.py:324-329 (blur-pool) + 253-300 (pad, pdf, cdf, searchsorted(right=True), gather, lerp)
+// models/mip.py:324-329 (blur-pool) + 253-300 (pad, pdf, cdf, searchsorted(right=True), gather, lerp), optionally
+// followed by cast_rays on the new fence-posts (mip.py:351) in the same kernel.  One warp per ray, KMAX = ceil(N/32)
+// samples per lane.  Bit-exactness notes (the indices must equal torch's on the CPU reference path):
+//   * torch.sum over the contiguous sample axis is NOT a plain left-to-right sum: ATen's CPU kernel (SumKernel.cpp,
+//     vectorized_inner_sum / row_sum) keeps 4 interleaved accumulators of 8-lane vectors, i.e. element e of a row
+//     goes to accumulator (e / 8) % 4, lane e % 8; then acc0 + acc1 + acc2 + acc3, then the scalar tail (N % 8) and
+//     the 8 lanes are added left to right.  Lane L of the warp plays accumulator L / 8, vector lane L % 8, so the
+//     strided layout i = L + 32 k reproduces that order exactly (checked against torch.sum on the host for every N
+//     the tests use; N < 8 takes ATen's scalar path: 4 interleaved scalar accumulators);
+//   * torch.cumsum on the CPU accumulates in double and rounds every prefix to fp32: the scan runs in fp64.
+template <int KMAX>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 resample_kernel(long long R, int N, const float* __restrict__ t, const float* __restrict__ weights, float padding,
-                int blur_pool, const float* __restrict__ u, int u_ld, float* __restrict__ new_t, long long* __restrict__ inds_out) {
+                int blur_pool, const float* __restrict__ u, int u_ld, float* __restrict__ new_t,
+                long long* __restrict__ inds_out, const float* __restrict__ origins, const float* __restrict__ dirs,
+                const float* __restrict__ radii, float* __restrict__ means, float* __restrict__ covs) {
   extern __shared__ float smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  float* sw = smem + (size_t)wib * (3 * N + 2);  // raw weights, then pdf
-  float* sc = sw + N;                            // cdf, N+1 entries
-  float* sb = sc + N + 1;                        // bins (t), N+1 entries
+  const int stride = 3 * N + 4;
+  float* sa = smem + (size_t)wib * stride;  // raw weights, later the cdf (N+1 entries)
+  float* sp = sa + N + 1;                   // blurred weights, then the pdf, then the new fence-posts (N+1)
+  float* sb = sp + N + 1;                   // bins (t), N+1 entries
+  const int K = (N + 31) >> 5;              // samples per lane
+  const int vec = N >> 3, ilp = vec >> 2;   // ATen: 8-float vectors, 4 interleaved accumulators
+  const bool ragged = (N & 31) != 0;
   const long long warp0 = blockIdx.x * (long long)kWarpsPerBlock + wib;
   for (long long r = warp0; r < R; r += (long long)gridDim.x * kWarpsPerBlock) {
-    for (int i = lane; i < N; i += 32) sw[i] = weights[r * N + i];
-    for (int i = lane; i <= N; i += 32) sb[i] = t[r * (N + 1) + i];
-    __syncwarp();
-    // blur-pool: wm[k] = max(w[max(k-1,0)], w[min(k,N-1)]), blur[i] = .5 (wm[i] + wm[i+1]) + padding.
-    // N <= 256 (checked by the launcher) so each lane owns at most 8 strided samples, kept in registers.
-    float local = 0.f;
-    float blur[8];
+    const float* wr = weights + r * N;
+    const float* tr = t + r * (N + 1);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      int i = lane + 32 * k;
-      blur[k] = 0.f;
-      if (32 * k >= N) continue;  // (warp-uniform: N = 64 touches two of the eight register slots)
-      if (i < N) {
-        float wl = sw[i > 0 ? i - 1 : 0], wc = sw[i], wr = sw[i + 1 < N ? i + 1 : N - 1];
-        blur[k] = blur_pool ? 0.5f * (fmaxf(wl, wc) + fmaxf(wc, wr)) + padding : wc;
-        local += blur[k];
-      }
+    for (int k = 0; k < KMAX; ++k) {
+      const int i = lane + 32 * k;
+      if (i < N) sa[i] = wr[i];
+      if (i <= N) sb[i] = tr[i];
     }
-    float wsum = warp_sum(local);
-    __syncwarp();  // every lane has read its neighbours: sw can be overwritten with the pdf
-    float pad = fmaxf(0.f, 1e-5f - wsum);  // mip.py:253-257
-    float add = pad / (float)N;
+    if (lane == 0 && 32 * KMAX <= N) sb[N] = tr[N];  // (N == 32 * KMAX: the last fence-post)
+    __syncwarp();
+    // blur-pool: wm[k] = max(w[max(k-1,0)], w[min(k,N-1)]), blur[i] = .5 (wm[i] + wm[i+1]) + padding
+    float blur[KMAX];
+    float local = 0.f;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      const int i = lane + 32 * k;
+      blur[k] = 0.f;
+      if (i < N) {
+        const float wc = sa[i];
+        if (blur_pool) {
+          const float wl = sa[i > 0 ? i - 1 : 0], wrt = sa[i + 1 < N ? i + 1 : N - 1];
+          blur[k] = 0.5f * (fmaxf(wl, wc) + fmaxf(wc, wrt)) + padding;
+        } else {
+          blur[k] = wc;
+        }
+        if (ragged || N < 8) sp[i] = blur[k];
+      }
+      if (k < ilp) local += blur[k];  // accumulator lane/8, vector lane%8: elements i4*32 + lane, i4 ascending
+    }
+    float wsum;
+    if (N < 8) {  // ATen scalar path: 4 interleaved scalar accumulators, leftovers into accumulator 0
+      __syncwarp();
+      float p4[4] = {0.f, 0.f, 0.f, 0.f};
+      const int q4 = N >> 2;
+      for (int i = 0; i < q4; ++i)
+        for (int k = 0; k < 4; ++k) p4[k] += sp[i * 4 + k];
+      for (int i = q4 * 4; i < N; ++i) p4[0] += sp[i];
+      wsum = ((p4[0] + p4[1]) + p4[2]) + p4[3];
+    } else {
+      if (ragged) {  // vectors beyond the last full group of 4 go to accumulator 0, then the scalar tail
+        __syncwarp();
+        if (lane < 8)
+          for (int j = ilp * 4; j < vec; ++j) local += sp[j * 8 + lane];
+      }
+      float p = local + __shfl_down_sync(0xffffffffu, local, 8);
+      p += __shfl_down_sync(0xffffffffu, local, 16);
+      p += __shfl_down_sync(0xffffffffu, local, 24);
+      float acc = 0.f;
+      if (ragged)
+        for (int e = vec * 8; e < N; ++e) acc += sp[e];
+#pragma unroll
+      for (int l = 0; l < 8; ++l) acc += __shfl_sync(0xffffffffu, p, l);
+      wsum = acc;
+    }
+    __syncwarp();  // every lane is done with the raw / blurred values in shared memory
+    const float pad = fmaxf(0.f, 1e-5f - wsum);  // mip.py:253-257
+    const float add = pad / (float)N;
     wsum += pad;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      int i = lane + 32 * k;
-      if (32 * k >= N) continue;
-      if (i < N) sw[i] = (blur[k] + add) / wsum;
+    for (int k = 0; k < KMAX; ++k) {
+      const int i = lane + 32 * k;
+      if (i < N) sp[i] = (blur[k] + add) / wsum;
     }
     __syncwarp();
-    // cdf[k] = min(1, float(sum_{j<k} double(pdf_j))) : torch's CPU cumsum accumulates in double
-    double carry = 0.0;
-    for (int base = 0; base < N; base += 32) {
-      int i = base + lane;
-      double p = i < N ? (double)sw[i] : 0.0;
-      double incl = warp_scan_incl(p, lane);
-      double prev = __shfl_up_sync(0xffffffffu, incl, 1);
-      double excl = carry + (lane == 0 ? 0.0 : prev);
-      carry += __shfl_sync(0xffffffffu, incl, 31);
-      if (i < N) sc[i] = i == 0 ? 0.f : fminf(1.f, (float)excl);
+    // cdf[i] = min(1, float(sum_{j<i} double(pdf_j))), lane-blocked: lane owns samples [lane*K, lane*K + K)
+    {
+      double e[KMAX];
+      double run = 0.0;
+#pragma unroll
+      for (int j = 0; j < KMAX; ++j) {
+        const int i = lane * K + j;
+        e[j] = run;
+        if (j < K && i < N) run += (double)sp[i];
+      }
+      const double incl = warp_scan_incl(run, lane);
+      const double base = incl - run;
+#pragma unroll
+      for (int j = 0; j < KMAX; ++j) {
+        const int i = lane * K + j;
+        if (j < K && i < N) sa[i] = i == 0 ? 0.f : fminf(1.f, (float)(base + e[j]));
+      }
+      if (lane == 0) sa[N] = 1.f;
     }
-    if (lane == 0) sc[N] = 1.f;
     __syncwarp();
-    for (int j = lane; j <= N; j += 32) {
-      float uj = u[(long long)u_ld * r + j];
+    const float* ur = u + (long long)u_ld * r;
+#pragma unroll
+    for (int k = 0; k < KMAX + 1; ++k) {
+      const int j = lane + 32 * k;
+      if (j > N || (k == KMAX && 32 * KMAX != N)) continue;
+      const float uj = ur[j];
       int lo = 0, hi = N + 1;  // first index with cdf > u
       while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        if (sc[mid] <= uj) lo = mid + 1; else hi = mid;
+        const int mid = (lo + hi) >> 1;
+        if (sa[mid] <= uj) lo = mid + 1; else hi = mid;
       }
-      int below = lo - 1 > 0 ? lo - 1 : 0, above = lo < N ? lo : N;
-      float c0 = sc[below], c1 = sc[above];
+      const int below = lo - 1 > 0 ? lo - 1 : 0, above = lo < N ? lo : N;
+      const float c0 = sa[below], c1 = sa[above];
       float den = c1 - c0;
       if (den < 1e-5f) den = 1.f;
-      float frac = (uj - c0) / den;
-      float b0 = sb[below], b1 = sb[above];
-      new_t[r * (N + 1) + j] = b0 + frac * (b1 - b0);
+      const float frac = (uj - c0) / den;
+      const float b0 = sb[below], b1 = sb[above];
+      const float nt = b0 + frac * (b1 - b0);
+      new_t[r * (N + 1) + j] = nt;
+      sp[j] = nt;
       if (inds_out) inds_out[r * (N + 1) + j] = lo;
+    }
+    __syncwarp();
+    if (means != nullptr) {  // cast_rays on the new fence-posts (models/mip.py:351, 67-89)
+      const float o[3] = {origins[3 * r], origins[3 * r + 1], origins[3 * r + 2]};
+      const float d[3] = {dirs[3 * r], dirs[3 * r + 1], dirs[3 * r + 2]};
+      const float rad = radii[r];
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        const int i = lane + 32 * k;
+        if (i < N) {
+          float m[3], c[3];
+          frustum_gaussian(sp[i], sp[i + 1], rad, o, d, m, c);
+          const long long sidx = r * N + i;
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            means[3 * sidx + q] = m[q];
+            covs[3 * sidx + q] = c[q];
+          }
+        }
+      }
     }
     __syncwarp();
   }
@@ -284,13 +368,39 @@ extern "C" int pnb_composite_bwd(int R, int N, const float* rgb, const float* de
   return finish("composite_bwd");
 }
 
+template <int KMAX>
+static int launch_resample(int R, int N, const float* t, const float* weights, float padding, int blur_pool,
+                           const float* u, int u_ld, float* new_t, long long* inds, const float* origins,
+                           const float* dirs, const float* radii, float* means, float* covs, cudaStream_t st) {
+  const size_t smem = (size_t)kWarpsPerBlock * (3 * N + 4) * sizeof(float);
+  const int grid = grid_for((long long)R * 32, kWarpsPerBlock * 32, 4);
+  resample_kernel<KMAX><<<grid, kWarpsPerBlock * 32, smem, st>>>(R, N, t, weights, padding, blur_pool, u, u_ld, new_t,
+                                                                inds, origins, dirs, radii, means, covs);
+  return finish("resample");
+}
+
+extern "C" int pnb_resample_cast(int R, int N, const float* t, const float* weights, float padding, int blur_pool,
+                                 const float* u, int u_ld, float* new_t, long long* inds, const float* origins,
+                                 const float* directions, const float* radii, float* means, float* covs,
+                                 void* stream) {
+  PNB_REQUIRE(R >= 0 && N > 0 && N <= 256 && (u_ld == 0 || u_ld >= N + 1), "resample: need 0 < N <= 256");
+  PNB_REQUIRE(t && weights && u && new_t, "resample: null argument");
+  PNB_REQUIRE((means == nullptr) == (covs == nullptr), "resample: means and covs go together");
+  PNB_REQUIRE(means == nullptr || (origins && directions && radii), "resample: the fused cast needs the rays");
+  if (R == 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  if (N <= 64)
+    return launch_resample<2>(R, N, t, weights, padding, blur_pool, u, u_ld, new_t, inds, origins, directions, radii,
+                              means, covs, st);
+  if (N <= 128)
+    return launch_resample<4>(R, N, t, weights, padding, blur_pool, u, u_ld, new_t, inds, origins, directions, radii,
+                              means, covs, st);
+  return launch_resample<8>(R, N, t, weights, padding, blur_pool, u, u_ld, new_t, inds, origins, directions, radii,
+                            means, covs, st);
+}
+
 extern "C" int pnb_resample(int R, int N, const float* t, const float* weights, float padding, int blur_pool,
                             const float* u, int u_ld, float* new_t, long long* inds, void* stream) {
-  PNB_REQUIRE(R >= 0 && N > 0 && N <= 256 && (u_ld == 0 || u_ld >= N + 1), "resample: need 0 < N <= 256");
-  if (R == 0) return 0;
-  size_t smem = (size_t)kWarpsPerBlock * (3 * N + 2) * sizeof(float);
-  int grid = grid_for((long long)R * 32, kWarpsPerBlock * 32, 4);
-  resample_kernel<<<grid, kWarpsPerBlock * 32, smem, as_stream(stream)>>>(R, N, t, weights, padding, blur_pool, u, u_ld,
-                                                                         new_t, inds);
-  return finish("resample");
+  return pnb_resample_cast(R, N, t, weights, padding, blur_pool, u, u_ld, new_t, inds, nullptr, nullptr, nullptr,
+                           nullptr, nullptr, stream);
 }

@@ -67,11 +67,12 @@ def resample_along_rays(origins, directions, radii, t_samples, weights, randomiz
     t_samples, weights = f(t_samples), f(weights)
     if randomized and u is None:
         u = stratified_u(weights.shape[0], t_samples.shape[-1], weights.device)
-    res = ops.resample(t_samples, weights, resample_padding, u=u if randomized else None, return_inds=return_inds)
-    new_t, inds = res if return_inds else (res, None)
-    means, covs = ops.cast_rays_t(new_t, f(origins), f(directions), f(radii))
+    res = ops.resample(t_samples, weights, resample_padding, u=u if randomized else None, return_inds=return_inds,
+                       cast=(f(origins), f(directions), f(radii)))
     if return_inds:
+        new_t, inds, means, covs = res
         return new_t, (means, covs), inds
+    new_t, means, covs = res
     return new_t, (means, covs)
 
 

@@ -151,8 +151,10 @@ def pos_enc(x, deg: int):
     return out
 
 
-def resample(t, weights, padding: float, u=None, return_inds=False, blur_pool=True):
-    """models/mip.py:304-352 (stop_grad branch): new fence-posts [R,N+1] (+ searchsorted indices for tests)."""
+def resample(t, weights, padding: float, u=None, return_inds=False, blur_pool=True, cast=None):
+    """models/mip.py:304-352 (stop_grad branch): new fence-posts [R,N+1] (+ searchsorted indices for tests).
+    `cast=(origins, directions, radii)` also runs cast_rays on the new fence-posts in the same kernel and appends
+    (means, covs) to the result."""
     r, n = weights.shape
     dev = t.device
     if u is None:
@@ -161,11 +163,17 @@ def resample(t, weights, padding: float, u=None, return_inds=False, blur_pool=Tr
         u, u_ld = _req(u, "u"), n + 1
     new_t = torch.empty(r, n + 1, device=dev, dtype=torch.float32)
     inds = torch.empty(r, n + 1, device=dev, dtype=torch.int64) if return_inds else None
+    o = d = rad = means = covs = None
+    if cast is not None:
+        o, d, rad = (_req(x, nm) for x, nm in zip(cast, ("origins", "directions", "radii")))
+        means = torch.empty(r, n, 3, device=dev, dtype=torch.float32)
+        covs = torch.empty(r, n, 3, device=dev, dtype=torch.float32)
     with torch.cuda.device(dev):
-        check(_lib.lib().pnb_resample(r, n, _p(_req(t, "t")), _p(_req(weights, "weights")), float(padding), int(blur_pool), _p(u),
-                                      u_ld,
-                                      _p(new_t), _p(inds), _stream()), "resample")
-    return (new_t, inds) if return_inds else new_t
+        check(_lib.lib().pnb_resample_cast(r, n, _p(_req(t, "t")), _p(_req(weights, "weights")), float(padding),
+                                           int(blur_pool), _p(u), u_ld, _p(new_t), _p(inds), _p(o), _p(d), _p(rad),
+                                           _p(means), _p(covs), _stream()), "resample")
+    out = (new_t,) + ((inds,) if return_inds else ()) + ((means, covs) if cast is not None else ())
+    return out if len(out) > 1 else new_t
 
 
 def hdr_to_ldr(x, quantize=False):
@@ -388,7 +396,8 @@ def shade(env_rgb, albedo, normal, light_dirs, solid_angle):
 
 
 class _TonemapMSE(torch.autograd.Function):
-    """sum(mask * (hdr_to_ldr(pred) - gt)^2) / sum(mask)   (systems/panonerf_system.py:44-50)."""
+    """sum(mask * (hdr_to_ldr(pred) - gt)^2) / sum(mask)   (systems/panonerf_system.py:44-50).
+    `inv_mask_sum` is a python float or a 0-dim device tensor (1 / mask.sum() computed on the device)."""
 
     @staticmethod
     def forward(ctx, pred, gt_ldr, mask, inv_mask_sum):
@@ -399,6 +408,8 @@ class _TonemapMSE(torch.autograd.Function):
                                                 _p(partial), _stream()), "tonemap_se_fwd")
         ctx.save_for_backward(pred, gt_ldr, mask)
         ctx.inv = inv_mask_sum
+        if isinstance(inv_mask_sum, torch.Tensor):
+            return dsum(partial) * inv_mask_sum
         return dsum(partial, inv_mask_sum)
 
     @staticmethod
@@ -412,7 +423,7 @@ class _TonemapMSE(torch.autograd.Function):
         return d_pred, None, None, None
 
 
-def tonemap_mse(pred, gt_ldr, mask, inv_mask_sum: float):
+def tonemap_mse(pred, gt_ldr, mask, inv_mask_sum):
     return _TonemapMSE.apply(pred, gt_ldr, mask, inv_mask_sum)
 
 

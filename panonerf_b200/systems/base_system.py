@@ -48,7 +48,23 @@ class FlatAdam:
         field.invalidate_packs()
 
     def zero_grad(self):
+        self._rebind_grads(fold=False)
         self.flat_g.zero_()
+
+    def _rebind_grads(self, fold=True):
+        """Every p.grad must stay a view of `flat_g` (the fused backward accumulates straight into it, field.py).
+        `module.zero_grad()` / `set_to_none=True` or an external autograd call can replace it: stray gradients are
+        folded into the flat buffer (so the update never runs on a silently empty buffer) and the views re-installed."""
+        off = 0
+        for p in self.params:
+            k = p.numel()
+            view = self.flat_g[off:off + k].view_as(p)
+            g = p.grad
+            if g is None or g.data_ptr() != view.data_ptr() or g.shape != view.shape:
+                if fold and g is not None:
+                    view.add_(g.to(view.dtype))
+                p.grad = view
+            off += k
 
     def all_reduce_grads(self):
         """Sum over ranks (mean taken inside the Adam kernel via grad_scale = 1/world)."""
@@ -56,6 +72,7 @@ class FlatAdam:
         return all_reduce_flat_(self.flat_g)
 
     def step(self):
+        self._rebind_grads()
         scale = self.all_reduce_grads()
         self.step_count += 1
         lr = self.lr_fn(self.step_count - 1)
@@ -71,6 +88,8 @@ class FlatAdam:
         return self.lr_fn(t - 1), 1.0 - beta1 ** t, math.sqrt(1.0 - beta2 ** t)
 
     def step_dev(self, hyper):
+        if not torch.cuda.is_current_stream_capturing():
+            self._rebind_grads()
         scale = self.all_reduce_grads()
         ops.adam_step_dev(self.flat_p, self.flat_g, self.m, self.v, hyper, grad_scale=scale)
         field.invalidate_packs()
@@ -81,38 +100,70 @@ class GraphedTrainStep:
     replayed: ~240 kernel launches become one graph launch, which removes the host-side launch cost (it matters most
     with 8 ranks sharing the host cores).  Inputs are copied into static buffers, the learning rate and the Adam bias
     corrections reach the update kernel through a 3-float device tensor, so the schedule still advances.  Results are
-    those of the eager step (same kernels, same order); `torch.rand` streams are graph-safe Philox streams."""
+    those of the eager step (same kernels, same order); `torch.rand` streams are graph-safe Philox streams.
+
+    With more than one rank the NCCL all-reduce of the flat gradient buffer and the update kernel are captured too
+    (NCCL supports stream capture), so a step is a single graph launch on every rank; `PNB_GRAPH_NCCL=0` keeps them
+    outside the graph.
+
+    Step-dependent Python branches of `training_step` (`train.surface_start_step`) are frozen into a captured graph,
+    so the step key (`system.graph_key()`) is re-evaluated before every replay and the graph is re-captured when it
+    flips; `system.global_step` advances once per step like Lightning's."""
 
     def __init__(self, system, opt, rays, gts, warmup=3):
         self.system, self.opt = system, opt
         dev = gts.device
-        # With more than one rank the gradient all-reduce (NCCL) and the update stay outside the graph: they are two
-        # launches, and capturing a collective ties the graph to the communicator's internal streams.
-        self.update_in_graph = not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
+        self.dev = dev
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        import os
+        self.update_in_graph = (not multi) or os.environ.get("PNB_GRAPH_NCCL", "1") != "0"
         self.rays = type(rays)(*[x.clone() for x in rays])
         self.gts = gts.clone()
         self.hyper = torch.zeros(3, device=dev, dtype=torch.float32)
         self.launches_per_step = 0
+        self.captures = 0
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(warmup):
                 self._set_hyper()
                 self._body(capturing=False)
+                system.global_step += 1
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self._set_hyper()
+        try:
+            self._capture()
+        except Exception:                      # noqa: BLE001 - e.g. a communicator that refuses stream capture
+            if not (multi and self.update_in_graph):
+                raise
+            self.update_in_graph = False       # keep the collective and the update outside the graph
+            torch.cuda.synchronize(dev)
+            self._capture()
+        self._replay()                         # the captured step itself has not run yet: run it once
+        system.global_step += 1
+
+    def _key(self):
+        fn = getattr(self.system, "graph_key", None)
+        return fn() if fn is not None else None
+
+    def _capture(self):
+        torch.cuda.synchronize(self.dev)
+        self.key = self._key()
         l0 = ops.launch_count()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.loss = self._body()
         self.launches_per_step = ops.launch_count() - l0
-        self._replay()                         # the captured step itself has not run yet: run it once
+        self.captures += 1
 
     def _replay(self):
         self.graph.replay()
         if not self.update_in_graph:
             self.opt.step_dev(self.hyper)
+        # the replayed update changed the parameters behind torch's back: cached bf16 weight packs are stale for any
+        # eager forward that follows (e.g. a validation render); inside the graph the re-pack kernels are captured
+        field.invalidate_packs()
 
     def _set_hyper(self):
         # a fresh pageable tensor per step: the driver stages it before returning, so the host may run many steps
@@ -134,8 +185,11 @@ class GraphedTrainStep:
             for dst, src in zip(self.rays, rays):
                 dst.copy_(src, non_blocking=True)
             self.gts.copy_(gts, non_blocking=True)
+        if self._key() != self.key:            # a step-dependent branch flipped: the captured graph is out of date
+            self._capture()
         self._set_hyper()
         self._replay()
+        self.system.global_step += 1
         return self.loss
 
 
@@ -191,6 +245,18 @@ class BaseSystem(torch.nn.Module):
         lr_fn = lambda s: mip_lr_decay(s, hp["optimizer.lr_init"], hp["optimizer.lr_final"], hp["optimizer.max_steps"],
                                        hp["optimizer.lr_delay_steps"], hp["optimizer.lr_delay_mult"])
         return FlatAdam(self.mip_nerf.mlp.parameters(), lr_fn)
+
+    def graph_key(self):
+        """Everything `training_step` branches on in Python (a captured CUDA graph is only valid while it is fixed)."""
+        hp = self.hparams
+        return (bool(self.global_step >= hp.get("train.surface_start_step", 0) and hp.get("train.surface", False)),
+                bool(hp.get("loss.ort_loss", 0) > 0), bool(hp.get("loss.chrom_loss", 0) > 0), self.train_randomized)
+
+    @staticmethod
+    def _inv_mask_sum(mask):
+        """1 / mask.sum() as a device scalar (systems/panonerf_system.py:44-50 divide by `mask.sum()`): a fixed-order
+        device reduction, no host synchronisation, so the step stays CUDA-graph capturable."""
+        return torch.reciprocal(ops.dsum(mask))
 
     # ---- losses shared by both systems ---------------------------------------------------------------------------
     @staticmethod

@@ -17,7 +17,7 @@ class MipNeRFSystem(BaseSystem):
         outputs = self.mip_nerf(rays=rays, randomized=self.train_randomized, white_bkgd=self.white_bkgd,
                                 use_ort_loss=use_ort_loss)
         mask = ops._f32c(rays.lossmult).reshape(-1)
-        inv = 1.0 / float(mask.numel()) if self.hparams.get("assume_unit_mask", True) else 1.0 / float(mask.sum())
+        inv = self._inv_mask_sum(mask)
         (vol_c, *_), (vol_f, _, ort_loss, _) = outputs
         vol_coarse = self._masked_mse(vol_c, ldr_rgb_gt, mask, inv)
         vol_fine = self._masked_mse(vol_f, ldr_rgb_gt, mask, inv)

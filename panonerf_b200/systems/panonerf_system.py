@@ -16,7 +16,7 @@ class PanoNeRFSystem(BaseSystem):
         outputs = self.mip_nerf(rays=rays, env_rays=self.env_rays, randomized=self.train_randomized,
                                 white_bkgd=self.white_bkgd, enable_surf=surf_on, use_ort_loss=use_ort_loss)
         mask = ops._f32c(rays.lossmult).reshape(-1)
-        inv = 1.0 / float(mask.numel()) if hp.get("assume_unit_mask", True) else 1.0 / float(mask.sum())
+        inv = self._inv_mask_sum(mask)
         (rgb_c, *_), (rgb_f, _, ort_loss, _, alb, _, sf_rgb, _, _) = outputs
         vol_coarse = self._masked_mse(rgb_c, ldr_rgb_gt, mask, inv)
         vol_fine = self._masked_mse(rgb_f, ldr_rgb_gt, mask, inv)

@@ -119,7 +119,7 @@ def ops_fixture(ns):
     print("ops.npz", len(out), "arrays")
 
 
-def model_fixture(ns, name, pano, width, b, n, h, w, sd_from_seed=None, store_grads=True):
+def model_fixture(ns, name, pano, width, b, n, h, w, sd_from_seed=None, store_grads=True, gslice=64):
     out = {}
     c2w = camera(rot_seed=1)
     ds, rays = ref_rays(ns, h, w, c2w)
@@ -172,20 +172,70 @@ def model_fixture(ns, name, pano, width, b, n, h, w, sd_from_seed=None, store_gr
         if store_grads:
             out["grad/" + k] = npy(g)
         else:
-            out["gslice/" + k] = npy(g.reshape(-1)[:: max(1, g.numel() // 64)][:64])
+            out["gslice/" + k] = npy(g.reshape(-1)[:: max(1, g.numel() // gslice)][:gslice])
+    if not pano and not store_grads:
+        # first-order variant (configs/mipnerf.yaml: ort_loss 0 -> no normals, no second-order terms): the gradient is a
+        # plain sum over samples, so the fp32 parity path can be held to a 1e-5-class bound
+        model.mlp.zero_grad()
+        res = model(rays=r, randomized=False, white_bkgd=False, use_ort_loss=False)
+        loss0 = O.mipnerf_loss(res, r, gt, ort_mult=0.0)
+        out["noort/loss"] = npy(loss0)
+        loss0.backward()
+        for k, p in model.mlp.named_parameters():
+            g = p.grad
+            out["noort/gnorm/" + k] = np.array(float(g.norm()))
+            out["noort/gslice/" + k] = npy(g.reshape(-1)[:: max(1, g.numel() // gslice)][:gslice])
     np.savez_compressed(os.path.join(HERE, name), **out)
     print(name, "loss", float(loss), "arrays", len(out))
+
+
+def resample_fixture(ns):
+    """Config-size resampling vectors (4096 rays x N = 64 / 128 / 256) from the reference's resample_along_rays:
+    searchsorted indices in full (bit-exact contract), the new fence-posts as a SHA-256 of their bytes plus every
+    16th row.  Inputs are regenerated from the seed by the tests (torch's CPU generator is host-independent)."""
+    import hashlib
+    mip = ns.mip
+    out = {}
+    for n in (64, 128, 256):
+        t, w, o, d, rad = O.resample_case(n)
+        new_t, (rm, rc) = mip.resample_along_rays(o, d, rad, t, w.clone(), False, "cone", True, 0.01)
+        wb = O.blur_weights(w, 0.01)
+        new_t2, inds, cdf = O.pdf_sample(t, wb.clone(), n + 1, False, return_aux=True)
+        assert torch.equal(new_t2, new_t), "oracle restatement differs from the reference"
+        assert torch.equal(mip.sorted_piecewise_constant_pdf(t, wb.clone(), n + 1, False), new_t)
+        assert int(inds.max()) <= n and int(inds.min()) >= 1
+        out[f"inds/{n}"] = inds.numpy().astype(np.uint16 if n > 255 else np.uint8)
+        out[f"new_t_sha256/{n}"] = np.frombuffer(hashlib.sha256(new_t.numpy().tobytes()).digest(), dtype=np.uint8)
+        out[f"new_t_rows16/{n}"] = npy(new_t[::16])
+        out[f"mean_rows64/{n}"] = npy(rm[::64])
+        out[f"cov_rows64/{n}"] = npy(rc[::64])
+        out[f"cdf_sha256/{n}"] = np.frombuffer(hashlib.sha256(cdf.numpy().tobytes()).digest(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(HERE, "resample_large.npz"), **out)
+    print("resample_large.npz", len(out), "arrays")
 
 
 def main():
     assert rh.available(), "reference tree not found"
     torch.set_num_threads(8)
     ns = rh.load()
-    ops_fixture(ns)
-    model_fixture(ns, "mipnerf_w64.npz", False, 64, 24, 16, 8, 16)
-    model_fixture(ns, "panonerf_w64.npz", True, 64, 24, 16, 8, 16)
-    model_fixture(ns, "mipnerf_w256.npz", False, 256, 16, 64, 16, 32, sd_from_seed=4, store_grads=False)
-    model_fixture(ns, "panonerf_w256.npz", True, 256, 16, 64, 16, 32, sd_from_seed=4, store_grads=False)
+    which = set(sys.argv[1:]) or {"ops", "small", "resample", "c1", "c2s"}
+    if "ops" in which:
+        ops_fixture(ns)
+    if "small" in which:
+        model_fixture(ns, "mipnerf_w64.npz", False, 64, 24, 16, 8, 16)
+        model_fixture(ns, "panonerf_w64.npz", True, 64, 24, 16, 8, 16)
+        model_fixture(ns, "mipnerf_w256.npz", False, 256, 16, 64, 16, 32, sd_from_seed=4, store_grads=False)
+        model_fixture(ns, "panonerf_w256.npz", True, 256, 16, 64, 16, 32, sd_from_seed=4, store_grads=False)
+    if "resample" in which:
+        resample_fixture(ns)
+    # BASELINE.json config sizes (SURVEY.md section 8d): C1 = MipNeRF, 4096 rays of a 64 x 128 grid, 128 + 128 samples;
+    # C2 subset = PanoMipNeRF, 2048 of the 8192 rays of a 256 x 512 grid, 64 + 64 samples, surface + ort + chroma on.
+    if "c1" in which:
+        model_fixture(ns, "mipnerf_c1.npz", False, 256, 4096, 128, 64, 128, sd_from_seed=4, store_grads=False,
+                      gslice=2048)
+    if "c2s" in which:
+        model_fixture(ns, "panonerf_c2s.npz", True, 256, 2048, 64, 256, 512, sd_from_seed=4, store_grads=False,
+                      gslice=2048)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,120 @@
+"""Root-cause hunt for the intermittent 1e-4 IPE outliers of round 1 (tests/test_kernels_gpu.py::test_ipe_and_posenc).
+
+For many seeds: the CPU fp32 oracle (torch.sin / torch.exp on the host), the GPU kernel (fast SFU path and the
+double-precision exact path) and a float64 evaluation of the SAME fp32 arguments (the correctly rounded value any
+fp32 sin approximates) are compared.  Whoever is more than 2e-6 away from the float64 value is the culprit; the
+offending arguments, their 16-wide vector neighbours and the host CPU / ATen capability are dumped.
+
+    python tools/ipe_repro.py [--seeds 60] [--no-gpu]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import panonerf_oracle as O  # noqa: E402
+
+
+def host_info():
+    info = {"torch_cpu_capability": torch.backends.cpu.get_cpu_capability(), "threads": torch.get_num_threads(),
+            "cpu_count": os.cpu_count()}
+    try:
+        out = subprocess.run("lscpu", shell=True, capture_output=True, text=True).stdout
+        for line in out.splitlines():
+            if line.startswith(("Model name", "Flags")):
+                k, v = line.split(":", 1)
+                v = v.strip()
+                info[k.strip()] = v if k.startswith("Model") else " ".join(f for f in v.split() if f.startswith("avx"))
+    except Exception as e:       # noqa: BLE001
+        info["lscpu"] = repr(e)
+    return info
+
+
+def case(seed, m=4096):
+    gen = torch.Generator().manual_seed(seed)
+    mean = torch.rand(m, 3, generator=gen) * 10 - 5
+    cov = torch.rand(m, 3, generator=gen) * torch.tensor([1e-6, 1e-4, 1e-2])
+    return mean, cov
+
+
+def truth64(mean, cov):
+    """exp(-0.5 yv) * sin(arg) in float64 on the fp32 arguments the reference builds (models/mip.py:415-428)."""
+    scales = torch.tensor([2.0 ** i for i in range(16)])
+    y = (mean[..., None, :] * scales[:, None]).flatten(-2)
+    yv = (cov[..., None, :] * scales[:, None] ** 2).flatten(-2)
+    arg = torch.cat([y, y + 0.5 * torch.tensor(np.pi)], -1)          # fp32, like upstream
+    e = torch.exp(-0.5 * torch.cat([yv, yv], -1))                    # fp32 exp argument, fp32 exp
+    return (e.double() * torch.sin(arg.double())), arg, e
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seeds", type=int, default=60)
+    ap.add_argument("--no-gpu", action="store_true")
+    ap.add_argument("--threads", type=int, nargs="*", default=[0])
+    args = ap.parse_args()
+    print(json.dumps({"host": host_info()}), flush=True)
+    gpu = torch.cuda.is_available() and not args.no_gpu
+    if gpu:
+        from panonerf_b200 import ops
+    worst = {"cpu": 0.0, "gpu_fast": 0.0, "gpu_exact": 0.0}
+    culprits = []
+    for nt in args.threads:
+        if nt:
+            torch.set_num_threads(nt)
+        for seed in range(args.seeds):
+            mean, cov = case(seed)
+            t64, arg, e = truth64(mean, cov)
+            cpu = O.ipe(mean, cov, 0, 16)
+            cpu_again = O.ipe(mean, cov, 0, 16)
+            d_cpu = (cpu.double() - t64).abs()
+            worst["cpu"] = max(worst["cpu"], float(d_cpu.max()))
+            rec = {"seed": seed, "threads": torch.get_num_threads(), "cpu_max": float(d_cpu.max()),
+                   "cpu_repeatable": bool(torch.equal(cpu, cpu_again))}
+            if float(d_cpu.max()) >= 2e-6 or not rec["cpu_repeatable"]:
+                idx = int(d_cpu.argmax())
+                flat = arg.flatten()
+                lo = idx // 16 * 16
+                rec["cpu_outlier"] = {"flat_index": idx, "arg": float(flat[idx]), "exp": float(e.flatten()[idx]),
+                                      "cpu": float(cpu.flatten()[idx]), "truth": float(t64.flatten()[idx]),
+                                      "sin_scalar": float(torch.sin(flat[idx:idx + 1])),
+                                      "sin_in_vector16": float(torch.sin(flat[lo:lo + 16].clone())[idx - lo]),
+                                      "vector16_args": [float(v) for v in flat[lo:lo + 16]],
+                                      "n_outliers": int((d_cpu >= 2e-6).sum())}
+                culprits.append(rec)
+            if gpu:
+                md, cd = mean.cuda(), cov.cuda()
+                outs = {}
+                for name, env in (("gpu_fast", None), ("gpu_exact", "1")):
+                    if env:
+                        os.environ["PNB_IPE_SLOW"] = env
+                    try:
+                        o = torch.empty(mean.shape[0], 96, device="cuda")
+                        ops.ipe_into(md, cd, 0, 16, o)
+                        o2 = torch.empty(mean.shape[0], 96, device="cuda")
+                        ops.ipe_into(md, cd, 0, 16, o2)
+                    finally:
+                        os.environ.pop("PNB_IPE_SLOW", None)
+                    d = (o.cpu().double() - t64).abs()
+                    worst[name] = max(worst[name], float(d.max()))
+                    rec[name + "_max"] = float(d.max())
+                    rec[name + "_repeatable"] = bool(torch.equal(o, o2))
+                    outs[name] = o
+                rec["gpu_vs_cpu_max"] = float((outs["gpu_fast"].cpu() - cpu).abs().max())
+                if rec["gpu_fast_max"] >= 2e-6 or rec["gpu_exact_max"] >= 2e-6 or not rec["gpu_fast_repeatable"]:
+                    culprits.append(rec)
+            if seed < 3 or "cpu_outlier" in rec:
+                print(json.dumps(rec), flush=True)
+    print(json.dumps({"worst_abs_err_vs_float64": worst, "culprit_records": len(culprits)}), flush=True)
+    for c in culprits[:20]:
+        print(json.dumps(c), flush=True)
+
+
+if __name__ == "__main__":
+    main()
