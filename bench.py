@@ -217,6 +217,16 @@ def run_ours(args):
 
     for _ in range(max(args.warmup, 3)):
         step_resident()
+    # Pre-heat: keep stepping (untimed) until the GPU has been busy for `--preheat` seconds, so that the timed steps
+    # run at the clocks a long training run settles to (the sustained roofline denominator then applies even when
+    # the timed region itself is short).
+    preheat_steps = 0
+    t_pre = time.perf_counter()
+    while time.perf_counter() - t_pre < args.preheat:
+        for _ in range(10):
+            step_resident()
+        torch.cuda.synchronize()
+        preheat_steps += 10
     ms, launches, clocks, _, last = timed(step_resident, args.steps)
     if graphed is not None:
         launches = graphed.launches_per_step * args.steps      # replayed launches are not seen by the host counter
@@ -231,7 +241,8 @@ def run_ours(args):
     value = total_rays / (ms / 1e3)
     e2e = total_rays / (ms_e2e / 1e3)
     pk = peaks()
-    roof = roofline_from_profile(prof, args.steps, pk)
+    roof = roofline_from_profile(prof, args.steps, pk, step_ms=ms / args.steps, step_flop=step_flops(),
+                                 ideal_bytes_per_step=ideal_train_bytes(RAYS_PER_GPU))
     line = {
         "metric": "train_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -241,6 +252,8 @@ def run_ours(args):
                    "rays_per_gpu": RAYS_PER_GPU, "num_samples": N_SAMPLES, "parallelism": f"ray-dp{world}",
                    "l2": "activations per step are several GB (>> 126 MB L2): every step streams from HBM",
                    "randomized": True, "cuda_graph": graphed is not None,
+                   "preheat_s": args.preheat, "preheat_steps": preheat_steps,
+                   "update_in_graph": bool(graphed is not None and graphed.update_in_graph),
                    "eager_ms_per_step_with_profile_events": ms_prof / args.steps},
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": int(packed_h.numel() * 4 + gt_h.numel() * 4),
@@ -250,6 +263,21 @@ def run_ours(args):
         "final_loss": float(last),
         "step_tflops": step_flops() * world / (ms / args.steps / 1e3) / 1e12,
     }
+    if not args.no_extras:
+        # the other BASELINE.json configurations, as extra keys of the same line (every rank takes part)
+        try:
+            line["c4"] = measure_c4(system, opt, dev, world, rank, args.c4_steps)
+        except Exception as e:                   # noqa: BLE001
+            import traceback
+            line["c4"] = {"error": f"{type(e).__name__}: {e}", "traceback": traceback.format_exc()[-3000:]}
+        graphed = None
+        torch.cuda.empty_cache()
+        try:
+            r = measure_render(system, dev, world, rank, local, 512, 1024, args.render_chunk, args.render_steps, 1)
+            line["render"] = {k: r[k] for k in ("metric", "value", "unit", "ms_per_step", "scaling", "config", "e2e",
+                                                "gpu_launches", "roofline", "step_tflops", "steps")}
+        except Exception as e:                   # noqa: BLE001
+            line["render"] = {"error": f"{type(e).__name__}: {e}"}
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.cpu_rays)
@@ -258,7 +286,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def run_render(args):
+def measure_render(system, dev, world, rank, local, H, W, chunk, steps, warmup):
     """configs[2]: full-panorama inference render (1024x512 equirect = 524 288 rays), PanoMipNeRF with normals +
     env irradiance + surface rendering (what the reference's render_image does), rows sharded over the ranks, no
     inter-GPU communication.  `e2e` additionally copies the rendered HDR images back to pinned host memory."""
@@ -266,27 +294,20 @@ def run_render(args):
     from panonerf_b200 import field, ops
     from panonerf_b200.datasets.pano_datasets import generate_rays
     from panonerf_b200.parallel import shard_rows
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    system = make_system(dev)
-    H, W = args.render_hw
     row0, nrows = shard_rows(H, rank, world)
-    chunk = args.render_chunk
-    host_out = torch.empty(nrows * W, 3 * 4 + 2, pin_memory=True)
+    host_out = torch.empty(3 * 4 + 2, nrows * W, pin_memory=True)
 
     def render(copy_back):
         rays = generate_rays(H, W, camera(), 0.0, 10.0, dev, row0=row0, nrows=nrows)
         rays = type(rays)(*[x.view(1, nrows, W, -1) for x in rays])
-        outs = system.render_image((rays, torch.empty(1, nrows, W, 3, device=dev)), chunk_size=chunk)
+        outs = system.render_image((rays, torch.empty(1, nrows, W, 3, device=dev)), chunk_size=chunk or None)
         if copy_back:
             c_rgb, f_rgb, c_dep, f_dep, nor, alb, _, sf, sd = outs
-            flat = torch.cat([x.permute(0, 2, 3, 1).reshape(nrows * W, -1) for x in (f_rgb, nor, alb, sf, c_dep, f_dep)], 1)
-            host_out.copy_(flat, non_blocking=True)
+            k = 0
+            for x in (f_rgb, nor, alb, sf, c_dep, f_dep):          # contiguous [1,c,H,W] planes -> pinned host memory
+                c = x.shape[1]
+                host_out[k:k + c].copy_(x.view(c, nrows * W), non_blocking=True)
+                k += c
             torch.cuda.synchronize()
         return outs
 
@@ -295,7 +316,7 @@ def run_render(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(copy_back, steps):
+    def timed(copy_back, n):
         barrier()
         sampler = ClockSampler(local)
         sampler.start()
@@ -304,7 +325,7 @@ def run_render(args):
             field.PROFILE = {}
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
+        for _ in range(n):
             render(copy_back)
         e1.record()
         barrier()
@@ -315,29 +336,78 @@ def run_render(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0]), ops.launch_count() - l0, sampler.result(), prof
 
-    for _ in range(max(args.warmup, 1)):
+    for _ in range(max(warmup, 1)):
         render(False)
-    ms, launches, clocks, prof = timed(False, args.steps)
-    ms_e2e, _, _, _ = timed(True, args.steps)
-    rays_total = H * W * args.steps
+    ms, launches, clocks, prof = timed(False, steps)
+    ms_e2e, _, _, _ = timed(True, steps)
+    rays_total = H * W * steps
     flop_per_ray = (2 * N_SAMPLES + 100) * MLP_FLOP_PER_SAMPLE + N_SAMPLES * JAC_FLOP_PER_SAMPLE
-    line = {"metric": "render_rays_per_s", "value": rays_total / (ms / 1e3), "unit": "rays/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": ms / args.steps,
+    return {"metric": "render_rays_per_s", "value": rays_total / (ms / 1e3), "unit": "rays/s", "n_gpus": world,
+            "steps": steps, "warmup": max(warmup, 1), "ms_per_step": ms / steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"full-panorama PanoMipNeRF render {W}x{H}, 64+64 samples, normals + 10x10 env "
                                    f"irradiance + surface rendering, rows sharded over ranks, no collective",
-                       "chunk_rays": chunk, "parallelism": f"ray-shard{world}",
+                       "rays_per_forward": chunk or "all (one forward per panorama)", "parallelism": f"ray-shard{world}",
                        "l2": "per-chunk activations are several GB (>> 126 MB L2)"},
             "clocks": clocks,
             "e2e": {"value": rays_total / (ms_e2e / 1e3), "unit": "rays/s", "h2d_bytes_per_step": 48,
-                    "d2h_bytes_per_step": int(host_out.numel() * 4), "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": int(host_out.numel() * 4), "ms_per_step": ms_e2e / steps},
             "gpu_launches": int(launches),
-            "roofline": roofline_from_profile(prof, args.steps, peaks()),
-            "step_tflops": H * W * flop_per_ray / (ms / args.steps / 1e3) / 1e12}
+            "roofline": roofline_from_profile(prof, steps, peaks(), step_ms=ms / steps,
+                                              step_flop=H * W * flop_per_ray / world),
+            "step_tflops": H * W * flop_per_ray / (ms / steps / 1e3) / 1e12}
+
+
+def run_render(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    system = make_system(dev)
+    H, W = args.render_hw
+    line = measure_render(system, dev, world, rank, local, H, W, args.render_chunk, args.steps, args.warmup)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_c4(system, opt, dev, world, rank, steps):
+    """BASELINE.json configs[3]: 65 536 rays per GPU and step, data-parallel (one NCCL all-reduce of the flat gradient
+    per step).  The step walks the batch in 8 slices of 8192 rays (gradient accumulation, AccumulatedTrainStep) so
+    that the activation planes of a slice (~19 GB) rather than of the whole batch (~150 GB) are resident."""
+    import torch.distributed as dist
+    from panonerf_b200.systems.base_system import AccumulatedTrainStep
+    n, k = 65536, 8
+    packed_h, gt_h = host_batch(1000 + rank, n)
+    packed_d, gt_d = packed_h.to(dev), gt_h.to(dev)
+    rays_d = unpack_rays(packed_d)
+    step = AccumulatedTrainStep(system, opt, rays_d, gt_d, micro_batches=k)
+    step(rays_d, gt_d)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step(rays_d, gt_d)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0]) / steps
+    return {"workload": "configs/panonerf.yaml training step, 65536 rays/GPU (8 accumulated slices of 8192), "
+                        "one flat-gradient all-reduce + Adam per step", "rays_per_gpu": n, "micro_batches": k,
+            "steps": steps, "ms_per_step": ms, "value": n * world / (ms / 1e3), "unit": "rays/s",
+            "step_tflops": step_flops() * (n / RAYS_PER_GPU) * world / (ms / 1e3) / 1e12,
+            "peak_memory_gb": torch.cuda.max_memory_allocated(dev) / 1e9, "final_loss": float(loss)}
 
 
 def step_flops():
@@ -348,54 +418,89 @@ def step_flops():
     return RAYS_PER_GPU * (3 * (main + env) * MLP_FLOP_PER_SAMPLE + 3 * N_SAMPLES * JAC_FLOP_PER_SAMPLE)
 
 
-BOUND = {"mlp_fused": "tensor", "mlp_fused_bwd": "tensor", "mlp_fused_jadj": "tensor", "wgrad_batch": "hbm",
-         "linear_tc": "hbm", "wgrad_tc": "hbm"}
+# Kernel families of the MLP stage.  Every one of them is bounded by the TENSOR roofline (the
+# MLP - forward, data gradients, weight gradients, Jacobian sweep and its adjoint - is the one dense contraction of
+# the path); `mlp_fused_kernel<P>` is one templated kernel (programs forward / forward+Jacobian / dgrad chain /
+# adjoint sweep) and is reported as one family.  The HBM view (GB/s actually moved, ncu DRAM bytes) is kept beside
+# it as `traffic`: in training the planes the weight-gradient kernel consumes dominate it.
+FAMILY = {"mlp_fused": "mlp_fused_kernel", "mlp_fused_bwd": "mlp_fused_kernel", "mlp_fused_jadj": "mlp_fused_kernel",
+          "wgrad_batch": "wgrad_batch_kernel", "linear_tc": "linear_tc_kernel", "wgrad_tc": "wgrad_tc_kernel"}
 
 
-def roofline_from_profile(prof, steps, pk):
-    """Per kernel family: ALGORITHMIC bytes / FLOPs over the CUDA-event time of its launches
-    inside the timed region (events on the launching stream).  The dominant family (most time) is the headline:
-      * wgrad_batch (all weight gradients of a level in one launch) is HBM-bound: every activation / dz plane is
-        read exactly once -> fraction of the measured copy bandwidth;
-      * the fused MLP programs (forward, forward+Jacobian, dgrad chain, adjoint sweep) are tensor-bound ->
-        fraction of the measured sustained bf16 rate (they run inside a long step).
-    `traffic` = DRAM bytes per launch from the committed ncu --set full capture of the same command
-    (profiles/r01_step_traffic.json), null if that file is absent."""
+def roofline_from_profile(prof, steps, pk, step_ms=None, step_flop=None, ideal_bytes_per_step=None):
+    """Per kernel family: ALGORITHMIC FLOPs over the CUDA-event time of its launches inside the
+    timed region (events on the launching stream) against the measured SUSTAINED bf16 rate (the kernels run inside a
+    long step).  Headline = the family with the most device time.  Extra keys:
+      mlp_stage   all MLP families together (fused programs + weight gradients): the section-8d MLP figure;
+      whole_step  the step's algorithmic MLP FLOPs over the whole step time;
+      hbm         what the headline family moves: bytes its launches read/write by design (GB/s, fraction of the
+                  measured copy bandwidth) next to `algorithmic_bytes` = the irreducible I/O of a fully fused
+                  pipeline (encodings in, raw outputs out, gradients) - the gap is the activation stash.
+    `traffic` = DRAM bytes per launch of the headline family from the committed ncu --set full capture of the same
+    command (profiles/r0?_step_traffic.json), null if absent."""
     if not prof:
         return None
     traffic = {}
-    tp = os.path.join(ROOT, "profiles", "r01_step_traffic.json")
-    if os.path.exists(tp):
-        traffic = json.load(open(tp))
+    for name in ("r02_step_traffic.json", "r01_step_traffic.json"):
+        tp = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(tp):
+            traffic = json.load(open(tp))
+            break
     fam = {}
     for name, rec in prof.items():
+        f = fam.setdefault(FAMILY.get(name, name), {"ms": 0.0, "n": 0, "flops": 0.0, "bytes": 0.0, "traffic": 0.0,
+                                                    "traffic_known": True, "programs": {}})
         ms = sum(a.elapsed_time(b) for a, b in rec["events"])
         n = len(rec["events"])
-        gbs = rec["bytes"] / (ms / 1e3) / 1e9
-        tfs = rec["flops"] / (ms / 1e3) / 1e12
-        bound = BOUND.get(name, "hbm")
-        peak = pk["tf_sust"] if bound == "tensor" else pk["hbm"]
-        ach = tfs if bound == "tensor" else gbs
-        fam[name] = {"kernel": name, "bound": bound, "achieved": ach, "peak": peak,
-                     "unit": "TFLOP/s" if bound == "tensor" else "GB/s", "frac": ach / peak,
-                     "traffic": traffic.get(name, {}).get("dram_bytes_per_launch"),
-                     "algorithmic_bytes_per_launch": rec["bytes"] / n, "algorithmic_flops_per_launch": rec["flops"] / n,
-                     "launches_per_step": n / steps, "avg_launch_ms": ms / n, "kernel_ms_per_step": ms / steps,
-                     "tflops": tfs, "gbps": gbs}
-    top = max(fam, key=lambda k: fam[k]["kernel_ms_per_step"])
-    out = dict(fam[top])
-    out["peak_source"] = pk["src"] + (" (sustained bf16 matmul rate)" if out["bound"] == "tensor"
-                                      else " (sustained copy bandwidth)")
-    out["other_kernels"] = {k: {kk: v[kk] for kk in ("bound", "achieved", "peak", "unit", "frac", "traffic",
-                                                      "kernel_ms_per_step", "launches_per_step")}
-                            for k, v in fam.items() if k != top}
-    mlp = [v for k, v in fam.items() if k.startswith("mlp_fused")]
-    if mlp:
-        ms = sum(v["kernel_ms_per_step"] for v in mlp)
-        fl = sum(v["algorithmic_flops_per_launch"] * v["launches_per_step"] for v in mlp)
-        out["fused_mlp_all_programs"] = {"bound": "tensor", "kernel_ms_per_step": ms, "achieved": fl / ms / 1e9,
-                                         "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": fl / ms / 1e9 / pk["tf_sust"]}
+        f["ms"] += ms
+        f["n"] += n
+        f["flops"] += rec["flops"]
+        f["bytes"] += rec["bytes"]
+        t = traffic.get(name, {}).get("dram_bytes_per_launch")
+        if t is None:
+            f["traffic_known"] = False
+        else:
+            f["traffic"] += t * n
+        f["programs"][name] = {"kernel_ms_per_step": ms / steps, "launches_per_step": n / steps,
+                               "tflops": rec["flops"] / (ms / 1e3) / 1e12,
+                               "frac": rec["flops"] / (ms / 1e3) / 1e12 / pk["tf_sust"]}
+
+    def entry(k, f):
+        tfs = f["flops"] / (f["ms"] / 1e3) / 1e12
+        return {"kernel": k, "bound": "tensor", "achieved": tfs, "peak": pk["tf_sust"], "unit": "TFLOP/s",
+                "frac": tfs / pk["tf_sust"], "frac_of_burst_peak": tfs / pk["tf_burst"],
+                "traffic": (f["traffic"] / f["n"]) if f["traffic_known"] else None,
+                "algorithmic_flops_per_launch": f["flops"] / f["n"], "launches_per_step": f["n"] / steps,
+                "avg_launch_ms": f["ms"] / f["n"], "kernel_ms_per_step": f["ms"] / steps,
+                "hbm": {"designed_bytes_per_launch": f["bytes"] / f["n"],
+                        "gbps": f["bytes"] / (f["ms"] / 1e3) / 1e9,
+                        "frac_of_copy_bandwidth": f["bytes"] / (f["ms"] / 1e3) / 1e9 / pk["hbm"]},
+                "programs": f["programs"] if len(f["programs"]) > 1 else None}
+
+    top = max(fam, key=lambda k: fam[k]["ms"])
+    out = entry(top, fam[top])
+    out["peak_source"] = pk["src"] + " (MEASURED_PEAKS.json bf16_tflops_sustained: kernels timed inside a long step)"
+    out["other_kernels"] = {k: entry(k, f) for k, f in fam.items() if k != top}
+    ms_all = sum(f["ms"] for f in fam.values())
+    fl_all = sum(f["flops"] for f in fam.values())
+    out["mlp_stage"] = {"bound": "tensor", "kernel_ms_per_step": ms_all / steps, "achieved": fl_all / ms_all / 1e9,
+                        "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": fl_all / ms_all / 1e9 / pk["tf_sust"]}
+    if step_ms is not None and step_flop is not None:
+        tfs = step_flop / (step_ms / 1e3) / 1e12
+        out["whole_step"] = {"bound": "tensor", "ms_per_step": step_ms, "achieved": tfs, "peak": pk["tf_sust"],
+                             "unit": "TFLOP/s", "frac": tfs / pk["tf_sust"]}
+    if ideal_bytes_per_step is not None:
+        out["algorithmic_bytes_per_step"] = ideal_bytes_per_step
+        out["designed_bytes_per_step"] = sum(f["bytes"] for f in fam.values()) / steps
     return out
+
+
+def ideal_train_bytes(rays):
+    """Irreducible HBM I/O of a fully fused training step (SURVEY.md section 8d / VERDICT r1): per MLP evaluation the
+    Gaussians in (24 B) and the raw outputs out (32 B), the same again for their gradients in the backward pass, the
+    rays (56 B), and the 2.45 MB gradient + parameter + Adam-state buffers."""
+    samples = rays * (2 * N_SAMPLES + 100)
+    return int(samples * 2 * (24 + 32) + rays * 56 + 613768 * 4 * 5)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -472,15 +577,19 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=150)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-rays", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run the training step eagerly instead of as a CUDA graph")
     ap.add_argument("--workload", default="train", choices=["train", "render"])
+    ap.add_argument("--preheat", type=float, default=2.0, help="seconds of untimed steps before the timed region")
+    ap.add_argument("--no-extras", action="store_true", help="skip the C3 render and C4 65536-ray figures")
+    ap.add_argument("--c4-steps", type=int, default=3)
+    ap.add_argument("--render-steps", type=int, default=2)
     ap.add_argument("--render-hw", type=int, nargs=2, default=[512, 1024])
-    ap.add_argument("--render-chunk", type=int, default=32768)
+    ap.add_argument("--render-chunk", type=int, default=0, help="rays per forward (0 = the whole image in one)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

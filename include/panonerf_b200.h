@@ -235,6 +235,16 @@ int pnb_mlp_fused_pack(const void* const* params_host, int C, void* wblob, float
 int pnb_mlp_fused_fwd(long long M, int S, int C, const void* enc, int ld_enc, const void* wblob, const float* bblob,
                       const float* row_bias, float* raw_den, float* raw_rgb, void* acts, float* g_enc, void* masks,
                       int masks_per_tile, void* stream);
+/* Inference forward with the integrated positional encoding (models/mip.py:394-428) computed INSIDE the kernel:
+ * two encoder warps per CTA evaluate the 96 features of the next tile pair from means / covs [M,3] (24 B per sample)
+ * into `scratch` (pnb_mlp_fused_scratch_bytes(), per-CTA double buffer that stays in L2), the [M,96] encoding array
+ * of pnb_ipe_fwd + pnb_mlp_fused_fwd never exists.  Bit-identical to that two-kernel path.  g_enc (nullable) selects
+ * the Jacobian sweep as in pnb_mlp_fused_fwd (masks then required).  vb_mod != 0: the per-ray view-direction term is
+ * row_bias[((m / S) % vb_mod)] - env rays share their D directions (models/pano_mip_nerf.py:337-341). */
+long long pnb_mlp_fused_scratch_bytes(void);
+int pnb_mlp_fused_fwd_ipe(long long M, int S, int C, const float* means, const float* covs, int min_deg,
+                          const void* wblob, const float* bblob, const float* row_bias, int vb_mod, float* raw_den,
+                          float* raw_rgb, float* g_enc, void* masks, void* scratch, void* stream);
 /* Data-gradient chain of the backward pass (the autograd of pano_mip_nerf.py:78-114 w.r.t. activations):
  * d_rgb fp32 [M,3], d_den fp32 [M,C], masks from the forward (per tile) ->
  * dz_planes bf16 [10][M][256]: 0 dz_view (cols 0..127), 1 d_bottleneck, 2..9 dz_7..dz_0 (pre-activation gradients),
@@ -252,6 +262,23 @@ int pnb_group_sum(long long M, int N, int group, const void* x, int ldx, int dty
 int pnb_pad_head_grad(long long M, int C, const float* src, void* dst_bf16, float* colsum, void* stream);
 /* 1 when the tcgen05 path was compiled in and the device is sm_100 */
 int pnb_tc_available(void);
+
+/* ---- render driver + validation outputs ------------------------------------
+ * pnb_pack_chw: scatter n_img per-ray results src[i] = [R, channels[i]] (HOST arrays of DEVICE pointers / ints) of
+ * rays [pix0, pix0+R) into the planes of one [sum(channels), H*W] buffer - the [1,C,H,W] images that
+ * systems/panonerf_system.py:171-189 builds with cat + view + permute. */
+int pnb_pack_chw(long long R, long long HW, long long pix0, int n_img, const void* const* src_host,
+                 const int* channels_host, float* out, void* stream);
+/* (pred - gt)^2 per element, optionally times row_weights[row] (WS-PSNR solid angles): utils/metrics.py:210-237,
+ * 318-326.  Sum with pnb_sum (fixed order). */
+int pnb_image_sqerr(long long n, int W, long long HW, const float* pred, const float* gt, const float* row_weights,
+                    float* out, void* stream);
+/* Scan-line payload of an uncompressed OpenEXR file, FLOAT channels B,G,R (utils/io_exr.py:30-47) and the filtered
+ * scan lines of an 8-bit RGB PNG, (x*255) truncated (utils/vis.py:25-41); chw = [C,H,W] with C in {1,3}. */
+long long pnb_exr_payload_bytes(int H, int W);
+int pnb_exr_pack(int H, int W, int C, const float* chw, void* out, void* stream);
+long long pnb_png_payload_bytes(int H, int W);
+int pnb_png_pack(int H, int W, int C, const float* chw, void* out, void* stream);
 
 #ifdef __cplusplus
 }

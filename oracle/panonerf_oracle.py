@@ -241,6 +241,50 @@ def resample_along_rays(origins, directions, radii, t, weights, randomized, padd
     return new_t, cast_cone(new_t, origins, directions, radii)
 
 
+# ----------------------------------------------------------------------------------------------------------
+# validation outputs: metrics and image quantisation
+# ----------------------------------------------------------------------------------------------------------
+def solid_angle_refinement(h=8, w=16):
+    """utils/surface_rendering.py:294-316 (spherical, torch branch): [1, h*w, 1] fp32."""
+    d_phi, d_theta = np.pi / h, 2 * np.pi / w
+    y = (np.arange(h) + 0.5) / h
+    x = (np.arange(w) + 0.5) / w
+    _, yy = np.meshgrid(x, y)
+    return torch.Tensor((np.sin(yy * np.pi) * d_theta * d_phi).reshape(1, -1, 1))
+
+
+def calc_psnr(x, y):
+    """utils/metrics.py:210-214, 231-237."""
+    return -10.0 * torch.log10(torch.mean((x - y) ** 2))
+
+
+def calc_ws_psnr(pred, gt):
+    """utils/metrics.py:318-326."""
+    c, h, w = pred.shape
+    weights = solid_angle_refinement(h=h, w=w).reshape(1, h, w)
+    weights = weights / weights.sum()
+    return -10.0 * torch.log10(torch.sum((pred - gt) ** 2 * weights))
+
+
+def png_pixels(image_1chw):
+    """utils/vis.py:29-35: the uint8 [H,W,3] array save_results hands to PIL (single channel replicated)."""
+    img = image_1chw[0].permute(1, 2, 0).cpu().numpy()
+    if img.shape[-1] == 1:
+        img = np.concatenate([img] * 3, axis=-1)
+    return (img * 255).astype(np.uint8)
+
+
+def ipe_exact(mean, cov, min_deg: int, max_deg: int):
+    """float64 value of models/mip.py:394-428 on the fp32 ARGUMENTS upstream builds (scaled means, `y + pi/2` rounded
+    to fp32, fp32 exp argument): what a correctly rounded fp32 sin / exp would return, independent of the host libm."""
+    scales = torch.tensor([2.0 ** i for i in range(min_deg, max_deg)])
+    y = (mean[..., None, :] * scales[:, None]).flatten(-2)
+    yv = (cov[..., None, :] * scales[:, None] ** 2).flatten(-2)
+    arg = torch.cat([y, y + 0.5 * torch.tensor(np.pi)], -1)
+    ex = -0.5 * torch.cat([yv, yv], -1)
+    return torch.exp(ex.double()) * torch.sin(arg.double())
+
+
 def resample_case(n: int, rays: int = 4096):
     """Seeded config-size inputs of the resampling tests / golden vectors (tests/golden/make_golden.py): peaky
     weights incl. an all-zero ray and a single spike, sorted fence-posts, random ray geometry."""

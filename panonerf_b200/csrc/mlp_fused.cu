@@ -15,7 +15,12 @@
 //                          the ring, D is the tile's own 256-column TMEM accumulator.  The program alternates
 //                          tile 0 / tile 1 op by op, so while the epilogue warps rewrite one tile's activations the
 //                          tensor pipe is busy with the other tile;
-//   warps 2..9  epilogue : tcgen05.ld -> bias / ReLU / mask -> bf16 -> written IN PLACE into the tile's activation
+//   warps 2..3  encoder  : (inference forward only) integrated positional encoding computed in the kernel: the 96
+//                          features of the next tile pair (models/mip.py:394-428) are evaluated from the Gaussians
+//                          (24 B per sample) into a per-CTA, double-buffered scratch that lives in L2 and is
+//                          re-dirtied in place - it never reaches DRAM - from where the producer's TMA loads pick it
+//                          up as before.  The [M,96] encoding array and its kernel disappear from the render path;
+//   warps 4..11 epilogue : tcgen05.ld -> bias / ReLU / mask -> bf16 -> written IN PLACE into the tile's activation
 //                          buffer as the next op's A operand; one mbarrier hand-shake per (op, tile) in each direction.
 //
 // ReLU sign bits go to a small global (L2-resident) bit-plane buffer: the Jacobian sweep
@@ -41,7 +46,7 @@ constexpr int kWidth = 256, kEncDim = 96, kCondW = 128;
 constexpr int kSlotBytes = 32768;  // ring slot: a weight tile of up to 256 rows x 64 bf16, or the two IPE k-blocks
 constexpr int kKbBytes = 16384;    // one k-block: 128 rows x 64 bf16, 128B-swizzled
 constexpr int kAbufBytes = 4 * kKbBytes;
-constexpr int kFThreads = 320;
+constexpr int kFThreads = 384;  // producer, MMA, 2 encoder warps, 8 epilogue warps
 constexpr int kMaxSteps = 80, kMaxOps = 24, kMaxPack = 160, kSlots = 3, kMaxLoads = 2 * 80 + 16;
 constexpr int kNumParams = 12;  // weights (and biases) in state-dict order: layers 0..7, density, extra, view, colour
 constexpr int kActPlanes = 18, kBwdPlanes = 10, kAdjPlanes = 8;
@@ -141,6 +146,10 @@ struct FusedParams {
   const float* d_rgb;    // P_BWD inputs
   const float* d_den;
   __nv_bfloat16* planes;     // save != 0: activation planes [n][M][256] (same memory the TMA map covers)
+  const float* means;        // in-kernel IPE (nullable): Gaussians [M,3] x 2 and the lowest degree
+  const float* covs;
+  __nv_bfloat16* enc_scratch;  // [grid][2 buffers][2 tiles][128][96] bf16, L2-resident
+  int ipe_min_deg, vb_mod;     // vb_mod != 0: per-ray row bias of ray (m / S) % vb_mod (env rays share D directions)
   unsigned long long* prof;  // timing experiments: [grid][8] cycle counters (nullable)
 };
 
@@ -149,6 +158,8 @@ struct FBarriers {
   uint64_t empty[kSlots];
   uint64_t abuf_ready[2];
   uint64_t acc_full[2];
+  uint64_t enc_ready[2];  // in-kernel IPE: scratch buffer b holds the encodings of a tile pair
+  uint64_t enc_free[2];   //                the MMA thread is done with the pair that used buffer b
   uint32_t tmem_base;
 };
 
@@ -515,6 +526,66 @@ __device__ __forceinline__ uint64_t desc_from16(uint32_t addr16) {
   return ((uint64_t)kHi << 32) | (uint64_t)((addr16 & 0x3FFFu) | (1u << 16));
 }
 
+// Integrated positional encoding of one sample (models/mip.py:394-428, 355-361) written as 96 bf16 to `dst`
+// (12 x 16-byte stores).  Same arithmetic as ipe_fwd_tile_kernel in rays.cu - exact fixed-point phase of 2^l * mean,
+// SFU sin / cos, TwoSum-corrected second half that reproduces sin(fl32(y + fl32(pi/2))) - so the in-kernel encoding is
+// bit-identical to the stand-alone kernel's bf16 output.
+__device__ __forceinline__ void encode_row(const float* __restrict__ means, const float* __restrict__ covs, long long m,
+                                           int min_deg, __nv_bfloat16* __restrict__ dst) {
+  constexpr float kHalfPiF = 1.57079632679489661923f;
+  uint32_t hi[3], lo[3];
+  float mean[3], cov[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    mean[c] = __ldg(means + 3 * m + c), cov[c] = __ldg(covs + 3 * m + c);
+    double u = (double)mean[c] * 0.15915494309189534561;  // turns
+    u -= floor(u);
+    const unsigned long long U = (unsigned long long)(u * 18446744073709551616.0);
+    hi[c] = (uint32_t)(U >> 32), lo[c] = (uint32_t)U;
+  }
+  uint32_t w[48];  // packed bf16 pairs: features 2k, 2k+1
+  float f[6];      // sin then cos of (l, c = 0..2), flushed every two degrees
+#pragma unroll
+  for (int l = 0; l < 16; ++l) {
+    const int sh = min_deg + l;
+    const float sc = __uint_as_float((uint32_t)(127 + sh) << 23);  // 2^sh
+    float sn3[3], cs3[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const uint32_t ph = __funnelshift_l(lo[c], hi[c], sh);
+      const float r = (float)(int)ph * 1.46291807926715968e-9f;
+      const float sn = __sinf(r), cs = __cosf(r);
+      const float y = __fmul_rn(mean[c], sc);
+      const float ex = __expf(__fmul_rn(-0.5f, __fmul_rn(cov[c], __fmul_rn(sc, sc))));
+      const float z = __fadd_rn(y, kHalfPiF);
+      const float bb = __fsub_rn(z, y);
+      const float err = __fadd_rn(__fsub_rn(y, __fsub_rn(z, bb)), __fsub_rn(kHalfPiF, bb));
+      const float eps = __fsub_rn(4.37113900018624283e-8f, err);
+      const float ce = fmaf(__fmul_rn(-0.5f, eps), eps, 1.0f);
+      const float se = __fmul_rn(eps, fmaf(__fmul_rn(-0.16666667f, eps), eps, 1.0f));
+      const float c2 = __fsub_rn(__fmul_rn(cs, ce), __fmul_rn(sn, se));
+      sn3[c] = __fmul_rn(ex, sn), cs3[c] = __fmul_rn(ex, c2);
+    }
+    // feature index l*3 + c (sin) and 48 + l*3 + c (cos); two degrees = 6 features = 3 packed words each
+    if ((l & 1) == 0) {
+      f[0] = sn3[0], f[1] = sn3[1], f[2] = sn3[2];
+      f[3] = cs3[0], f[4] = cs3[1], f[5] = cs3[2];
+    } else {
+      const int k = (l >> 1) * 3;  // word index of feature (l-1)*3
+      __nv_bfloat162 t;
+      t = __floats2bfloat162_rn(f[0], f[1]); w[k] = *reinterpret_cast<uint32_t*>(&t);
+      t = __floats2bfloat162_rn(f[2], sn3[0]); w[k + 1] = *reinterpret_cast<uint32_t*>(&t);
+      t = __floats2bfloat162_rn(sn3[1], sn3[2]); w[k + 2] = *reinterpret_cast<uint32_t*>(&t);
+      t = __floats2bfloat162_rn(f[3], f[4]); w[24 + k] = *reinterpret_cast<uint32_t*>(&t);
+      t = __floats2bfloat162_rn(f[5], cs3[0]); w[24 + k + 1] = *reinterpret_cast<uint32_t*>(&t);
+      t = __floats2bfloat162_rn(cs3[1], cs3[2]); w[24 + k + 2] = *reinterpret_cast<uint32_t*>(&t);
+    }
+  }
+  uint4* o = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int k = 0; k < 12; ++k) o[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+}
+
 struct EpiCtx {
   uint8_t* abuf;            // this tile's activation buffer
   uint32_t* mask;           // this tile's sign bit-planes [plane][unit][row] (nullptr: not kept)
@@ -816,6 +887,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmEnc, const __grid_constan
     for (int t = 0; t < 2; ++t) {
       mbar_init(&bars->abuf_ready[t], 8);
       mbar_init(&bars->acc_full[t], 1);
+      mbar_init(&bars->enc_ready[t], 2);
+      mbar_init(&bars->enc_free[t], 1);
     }
     fence_barrier_init();
   }
@@ -833,7 +906,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmEnc, const __grid_constan
       const uint64_t wpol = l2_policy_evict_last();
       const uint64_t epol = l2_policy_evict_first();  // IPE tiles are read once per use
       const int n_loads = c_prog[P].n_loads;
-      for (long long pair = blockIdx.x; pair < p.num_pairs; pair += gridDim.x) {
+      const bool ipe = p.means != nullptr;
+      uint32_t it = 0;  // this CTA's pair counter: scratch buffer it & 1
+      for (long long pair = blockIdx.x; pair < p.num_pairs; pair += gridDim.x, ++it) {
+        bool enc_waited = false;
         for (int l = 0; l < n_loads; ++l) {
           const LoadRec ld = c_prog[P].loads[l];
           const int slot = ld.slot;
@@ -842,7 +918,14 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmEnc, const __grid_constan
           if (ld.is_enc) {
             long long tile = pair * 2 + ld.t;
             if (tile >= p.num_tiles) tile = p.num_tiles - 1;  // phantom tile of an odd tail: recompute the last one
-            const int row0 = (int)(tile * kTileM);
+            int row0 = (int)(tile * kTileM);
+            if (ipe) {  // the encoder warps have filled scratch buffer it & 1 with this pair's encodings
+              if (!enc_waited) {
+                mbar_wait(&bars->enc_ready[it & 1u], (it >> 1) & 1u);
+                enc_waited = true;
+              }
+              row0 = (int)((((long long)blockIdx.x * 2 + (it & 1u)) * 2 + ld.t) * kTileM);
+            }
             mbar_expect_tx(&bars->full[slot], 2 * kKbBytes);
             tma_load_2d_hint(ring + (size_t)slot * kSlotBytes, &tmEnc, &bars->full[slot], 0, row0, epol);
             tma_load_2d_hint(ring + (size_t)slot * kSlotBytes + kKbBytes, &tmEnc, &bars->full[slot], 64, row0, epol);
@@ -867,8 +950,13 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmEnc, const __grid_constan
       mc.abuf16 = smem_u32(abuf) >> 4, mc.ring16 = smem_u32(ring) >> 4, mc.tmem_base = tmem_base;
       mc.prof = p.prof != nullptr, mc.t_ab = 0, mc.t_full = 0;
       const long long t_start = clock64();
-      for (long long pair = blockIdx.x; pair < p.num_pairs; pair += gridDim.x)
+      uint32_t it = 0;
+      for (long long pair = blockIdx.x; pair < p.num_pairs; pair += gridDim.x, ++it) {
         mma_program<P>(mc, std::make_integer_sequence<int, kOps>{});
+        // every TMA load of this pair's encodings has landed (their `full` barriers were waited for above): the
+        // encoder may overwrite scratch buffer it & 1 for the pair after next
+        if (p.means != nullptr) mbar_arrive(&bars->enc_free[it & 1u]);
+      }
       if (p.prof != nullptr) {
         p.prof[blockIdx.x * 8 + 0] = (unsigned long long)(clock64() - t_start);
         p.prof[blockIdx.x * 8 + 1] = (unsigned long long)mc.t_ab;
@@ -876,12 +964,34 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmEnc, const __grid_constan
       }
     }
     __syncwarp();
+  } else if (warp < 4) {
+    // ================================ encoder warps (in-kernel IPE) ==============================================
+    if ((P == P_FWD || P == P_FWDJ) && p.means != nullptr) {
+      const int e = (warp - 2) * 32 + lane;  // 0..63: rows e, e + 64, e + 128, e + 192 of the pair's 256
+      uint32_t it = 0;
+      for (long long pair = blockIdx.x; pair < p.num_pairs; pair += gridDim.x, ++it) {
+        const uint32_t b = it & 1u;
+        if (it >= 2) mbar_wait(&bars->enc_free[b], ((it >> 1) - 1u) & 1u);
+        __nv_bfloat16* dst = p.enc_scratch + (((size_t)blockIdx.x * 2 + b) * 2 * kTileM) * kEncDim;
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+          const int row = e + 64 * j;  // tile row / 128, row % 128
+          const long long m = pair * 2 * kTileM + row;
+          if (p.debug & 4) continue;  // timing experiment: hand-shakes only (garbage encodings)
+          encode_row(p.means, p.covs, m < p.M ? m : p.M - 1, p.ipe_min_deg, dst + (size_t)row * kEncDim);
+        }
+        // generic-proxy global writes -> async-proxy (TMA) reads by the producer thread
+        asm volatile("fence.proxy.async;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->enc_ready[b]);
+      }
+    }
   } else {
     // ================================ epilogue warps ============================================================
     EpiCtx c;
     c.tmActs = &tmActs;
     c.q = warp & 3;            // TMEM lane quadrant (hardware rule: warp id % 4)
-    c.hf = (warp - 2) >> 2;    // which of the two warps of the quadrant
+    c.hf = (warp - 4) >> 2;    // which of the two warps of the quadrant
     c.lane = lane, c.row = c.q * 32 + lane, c.save = p.save != 0, c.skip = (p.debug & 2) != 0;
     c.direct = p.save == 2, c.tma = p.save == 1;
     c.store_policy = l2_policy_evict_first();
@@ -946,7 +1056,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmEnc, const __grid_constan
           } else if (kFwd && epi == E_EXTRA) {
             rewrite_abuf<M_BIAS>(c, p, op, nullptr, op.bias_off);
           } else if (kFwd && epi == E_VIEW) {
-            rewrite_abuf<M_ROWBIAS_RELU>(c, p, op, p.row_bias + (m_safe / p.S) * kCondW, 0);
+            rewrite_abuf<M_ROWBIAS_RELU>(c, p, op, p.row_bias + (p.vb_mod ? (m_safe / p.S) % p.vb_mod : m_safe / p.S) * kCondW, 0);
           } else if (P != P_FWD && epi == E_MASK) {
             rewrite_abuf<M_MASK>(c, p, op, nullptr, 0);
           } else if (P == P_BWD && epi == E_LIN) {
@@ -1036,7 +1146,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmEnc, const __grid_constan
       }
     }
     if (lane == 0) bulk_wait_all();
-    if (p.prof != nullptr && lane == 0 && warp == 2) {
+    if (p.prof != nullptr && lane == 0 && warp == 4) {
       p.prof[blockIdx.x * 8 + 3] = (unsigned long long)(clock64() - t_epi0);
       p.prof[blockIdx.x * 8 + 4] = (unsigned long long)t_wait;
     }
@@ -1199,6 +1309,42 @@ extern "C" int pnb_mlp_fused_fwd(long long M, int S, int C, const void* enc, int
   cudaStream_t st = as_stream(stream);
   if (g_enc != nullptr) return launch<P_FWDJ>(tmEnc, tmActs, p, st, "mlp_fused_fwd(jac)");
   return launch<P_FWD>(tmEnc, tmActs, p, st, "mlp_fused_fwd");
+}
+
+extern "C" long long pnb_mlp_fused_scratch_bytes(void) {
+  return (long long)kNumSMs * 2 * 2 * kTileM * kEncDim * (long long)sizeof(__nv_bfloat16);
+}
+
+// Inference forward with the integrated positional encoding computed inside the kernel (no [M,96] encoding array):
+// means / covs [M,3] fp32 in, raw outputs (and d sigma / d enc when g_enc is given) out.
+extern "C" int pnb_mlp_fused_fwd_ipe(long long M, int S, int C, const float* means, const float* covs, int min_deg,
+                                     const void* wblob, const float* bblob, const float* row_bias, int vb_mod,
+                                     float* raw_den, float* raw_rgb, float* g_enc, void* masks, void* scratch,
+                                     void* stream) {
+  PNB_REQUIRE(M >= 0 && S >= 1 && C >= 1 && C <= 16 && vb_mod >= 0, "mlp_fused_fwd_ipe: bad sizes");
+  PNB_REQUIRE(means && covs && wblob && bblob && row_bias && raw_den && raw_rgb && scratch,
+              "mlp_fused_fwd_ipe: null argument");
+  PNB_REQUIRE(min_deg >= 0 && min_deg + 16 <= 31, "mlp_fused_fwd_ipe: IPE degrees must lie in [0, 31)");
+  PNB_REQUIRE(((uintptr_t)wblob % 16 == 0) && ((uintptr_t)bblob % 16 == 0) && ((uintptr_t)row_bias % 16 == 0) &&
+                  ((uintptr_t)scratch % 128 == 0),
+              "mlp_fused_fwd_ipe: blobs / row_bias must be 16-byte, scratch 128-byte aligned");
+  PNB_REQUIRE(g_enc == nullptr || ((uintptr_t)g_enc % 16 == 0 && masks != nullptr),
+              "mlp_fused_fwd_ipe: g_enc must be 16-byte aligned and needs the sign-bit buffer");
+  PNB_REQUIRE(M < (1ll << 31) - 2 * kTileM, "mlp_fused_fwd_ipe: M too large for 32-bit TMA coordinates");
+  if (M == 0) return 0;
+  FusedParams p{};
+  p.M = M, p.num_tiles = (M + kTileM - 1) / kTileM, p.num_pairs = (p.num_tiles + 1) / 2;
+  p.S = S, p.C = C, p.save = 0, p.vb_mod = vb_mod;
+  p.wblob = reinterpret_cast<const uint8_t*>(wblob), p.bblob = bblob, p.row_bias = row_bias;
+  p.raw_den = raw_den, p.raw_rgb = raw_rgb, p.g_enc = g_enc;
+  p.masks = reinterpret_cast<uint32_t*>(masks), p.masks_per_tile = 0;
+  p.means = means, p.covs = covs, p.ipe_min_deg = min_deg;
+  p.enc_scratch = reinterpret_cast<__nv_bfloat16*>(scratch);
+  CUtensorMap tmEnc;
+  if (!make_map_enc(&tmEnc, scratch, (unsigned long long)kNumSMs * 4 * kTileM, kEncDim)) return PNB_ERR_ARG;
+  cudaStream_t st = as_stream(stream);
+  if (g_enc != nullptr) return launch<P_FWDJ>(tmEnc, tmEnc, p, st, "mlp_fused_fwd_ipe(jac)");
+  return launch<P_FWD>(tmEnc, tmEnc, p, st, "mlp_fused_fwd_ipe");
 }
 
 extern "C" int pnb_mlp_fused_bwd(long long M, int C, const void* wblob, const float* bblob, const float* d_rgb,

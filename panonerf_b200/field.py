@@ -20,7 +20,7 @@ import torch
 from . import _lib
 from ._lib import EPI_ACCUM, EPI_BIAS, EPI_MASK, EPI_RELU, PNB_BF16, PNB_F32, check
 from . import ops
-from .ops import _p, _stream
+from .ops import _p, _stream, _amp_fwd, _amp_bwd
 
 PARAM_ORDER_TRUNK = "layers.{}.0"
 
@@ -371,6 +371,30 @@ def fused_forward(enc, vb, S, C, pack, acts, g_enc, masks=None, masks_per_tile=F
     return raw_den, raw_rgb
 
 
+_enc_scratch: Dict[str, torch.Tensor] = {}
+
+
+def fused_forward_ipe(means, covs, min_deg, vb, vb_mod, S, C, pack, g_enc):
+    """Inference forward with the IPE computed inside the fused kernel (csrc/mlp_fused.cu, encoder warps): no [M,96]
+    encoding array, no pnb_ipe_fwd launch.  Returns (raw_den, raw_rgb)."""
+    M = means.shape[0]
+    dev = means.device
+    raw_den = torch.empty(M, C, device=dev, dtype=torch.float32)
+    raw_rgb = torch.empty(M, 3, device=dev, dtype=torch.float32)
+    masks = fused_masks(M, dev, False) if g_enc is not None else None
+    key = str(dev)
+    if key not in _enc_scratch:
+        _enc_scratch[key] = torch.empty(int(_lib.lib().pnb_mlp_fused_scratch_bytes()), device=dev, dtype=torch.uint8)
+    flops = M * (2 * (96 * 256 + 6 * 256 * 256 + 352 * 256 + 256 * C + 256 * 256 + 256 * 128 + 128 * 3)
+                 + (2 * (6 * 256 * 256 + 2 * 96 * 256) if g_enc is not None else 0))
+    nbytes = M * (24 + 4 * C + 12 + (384 if g_enc is not None else 0))
+    with torch.cuda.device(dev), _prof("mlp_fused", nbytes, flops):
+        check(_lib.lib().pnb_mlp_fused_fwd_ipe(M, S, C, _p(means), _p(covs), min_deg, _p(pack["wblob"]),
+                                               _p(pack["bblob"]), _p(vb), vb_mod, _p(raw_den), _p(raw_rgb), _p(g_enc),
+                                               _p(masks), _p(_enc_scratch[key]), _stream()), "mlp_fused_fwd_ipe")
+    return raw_den, raw_rgb
+
+
 def fused_backward(M, C, pack, d_rgb, d_den, masks, d_enc):
     """dgrad chain of the backward pass in one kernel -> dz planes bf16 [10, M, 256] (include/panonerf_b200.h)."""
     dev = d_rgb.device
@@ -492,6 +516,7 @@ class _Field(torch.autograd.Function):
     """(means, covs, venc, *params) -> (raw_rgb [M,3], raw_den [M,C], n_raw [M,3] | None)."""
 
     @staticmethod
+    @_amp_fwd
     def forward(ctx, means, covs, venc, cfg, *params):
         names = cfg["names"]
         P = dict(zip(names, params))
@@ -511,17 +536,27 @@ class _Field(torch.autograd.Function):
             # (inside forward() grad mode is always off: radiance_field() records the caller's mode in cfg)
             need_bwd = cfg.get("grad_enabled", True) and any(ctx.needs_input_grad)
             C = P["density_layer.weight"].shape[0]
-            enc = torch.empty(M, xyz, device=dev, dtype=dt)
-            ops.ipe_into(means2, covs2, cfg["min_deg"], cfg["max_deg"], enc)
+            vmod = cfg.get("venc_mod", 0)
             wv = P["view_layers.0.0.weight"]
+            # per-ray view-direction term of the view layer (env rays: one row per env direction, indexed modulo D)
             vb = torch.empty(venc.shape[0], wv.shape[0], device=dev, dtype=f32)
             _F32Backend(P).linear(venc, wv[:, width:], vb, bias=P["view_layers.0.0.bias"])
             pack = fused_pack(names, params)
-            planes = int(_lib.lib().pnb_mlp_fused_act_planes())
-            acts = torch.empty(planes, M, width, device=dev, dtype=dt) if need_bwd else None
             g_enc = torch.empty(M, xyz, device=dev, dtype=f32) if cfg["with_normals"] else None
-            masks = fused_masks(M, dev, True) if need_bwd else None
-            raw_den, raw_rgb = fused_forward(enc, vb, S, C, pack, acts, g_enc, masks, need_bwd)
+            in_kernel_ipe = (not need_bwd and xyz == 96 and 0 <= cfg["min_deg"] and cfg["max_deg"] <= 31
+                             and not os.environ.get("PNB_NO_FUSED_IPE"))
+            if in_kernel_ipe:
+                enc = acts = masks = None
+                raw_den, raw_rgb = fused_forward_ipe(means2, covs2, cfg["min_deg"], vb, vmod, S, C, pack, g_enc)
+            else:
+                if vmod:                         # the stand-alone launcher indexes the row bias by ray
+                    vb = vb[None].expand(M // (S * vmod), vmod, vb.shape[1]).reshape(-1, vb.shape[1]).contiguous()
+                enc = torch.empty(M, xyz, device=dev, dtype=dt)
+                ops.ipe_into(means2, covs2, cfg["min_deg"], cfg["max_deg"], enc)
+                planes = int(_lib.lib().pnb_mlp_fused_act_planes())
+                acts = torch.empty(planes, M, width, device=dev, dtype=dt) if need_bwd else None
+                masks = fused_masks(M, dev, True) if need_bwd else None
+                raw_den, raw_rgb = fused_forward(enc, vb, S, C, pack, acts, g_enc, masks, need_bwd)
             n_raw, jac = None, None
             if cfg["with_normals"]:
                 v = ops.ipe_vjp(means2, covs2, cfg["min_deg"], cfg["max_deg"], g_enc)
@@ -537,6 +572,8 @@ class _Field(torch.autograd.Function):
             ctx.need_means = means.requires_grad
             ctx.means_shape = means.shape
             if need_bwd:
+                if vmod:                         # the backward's view-direction weight gradient is per ray
+                    venc = venc[None].expand(M // (S * vmod), vmod, venc.shape[1]).reshape(-1, venc.shape[1]).contiguous()
                 ctx.bufs = dict(means=means2, covs=covs2, venc=venc, enc=enc, hs=[acts[i] for i in range(depth)],
                                 bott=acts[8], hv=acts[9][:, :wv.shape[0]], vb_rows=venc.shape[0], raw_den=raw_den,
                                 jac=jac, masks=masks, pack=pack, acts=acts,
@@ -548,6 +585,9 @@ class _Field(torch.autograd.Function):
                 return raw_rgb, raw_den, None
             return raw_rgb, raw_den, n_raw
 
+        if cfg.get("venc_mod", 0):               # layered / parity paths take one view-direction row per ray
+            vmod = cfg["venc_mod"]
+            venc = venc[None].expand(M // (S * vmod), vmod, venc.shape[1]).reshape(-1, venc.shape[1]).contiguous()
         # cat = [h_skip | enc] (the input of the layer after the skip connection); enc lives only there
         cat = torch.empty(M, width + xyz, device=dev, dtype=dt)
         enc = cat[:, width:]
@@ -722,6 +762,7 @@ class _Field(torch.autograd.Function):
         return (d_means, None, None, None) + tuple(G[n] for n in names)
 
     @staticmethod
+    @_amp_bwd
     def backward(ctx, d_raw_rgb, d_raw_den, d_n_raw):
         cfg, B = ctx.cfg, ctx.bufs
         if B.get("fused"):
@@ -855,14 +896,19 @@ class _Field(torch.autograd.Function):
 
 def radiance_field(means, covs, venc, params: Dict[str, torch.Tensor], *, precision: str, samples_per_ray: int,
                    min_deg: int, max_deg: int, density_bias: float, skip: int, with_normals: bool,
-                   jac_precision: Optional[str] = None):
-    """Evaluate the MLP on [R,S,3] Gaussians. Returns raw_rgb [R,S,3], raw_den [R,S,C], n_raw [R,S,3] | None."""
+                   jac_precision: Optional[str] = None, venc_mod: int = 0):
+    """Evaluate the MLP on [R,S,3] Gaussians. Returns raw_rgb [R,S,3], raw_den [R,S,C], n_raw [R,S,3] | None.
+    `venc` is one view encoding per ray, or - with `venc_mod` = D - one per env direction, ray r using row r % D
+    (models/pano_mip_nerf.py:337-341 broadcasts the D env directions over the surface points)."""
     names = list(params.keys())
     depth = len([n for n in names if n.startswith("layers.") and n.endswith(".weight")])
     w0 = params["layers.0.0.weight"]
     cfg = dict(names=names, precision=precision, depth=depth, skip=skip, width=w0.shape[0], xyz_dim=w0.shape[1],
                samples_per_ray=samples_per_ray, min_deg=min_deg, max_deg=max_deg, density_bias=density_bias,
-               with_normals=with_normals, jac_precision=jac_precision, grad_enabled=torch.is_grad_enabled())
+               with_normals=with_normals, jac_precision=jac_precision, grad_enabled=torch.is_grad_enabled(),
+               venc_mod=int(venc_mod))
+    if venc_mod and (venc.shape[0] != venc_mod or means.shape[0] % venc_mod):
+        raise RuntimeError("venc_mod: expected one view encoding per env direction and rays = points x directions")
     if w0.shape[1] != 6 * (max_deg - min_deg):
         raise RuntimeError("IPE width does not match the first layer")
     R = means.shape[0]

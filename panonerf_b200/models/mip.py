@@ -3,7 +3,6 @@ error behaviour).  Everything here launches kernels of libpanonerf_b200.so; tens
 import torch
 
 from .. import ops
-from ..datasets.base_datasets import Rays, Rays_keys
 
 
 def _check_shape(ray_shape):
@@ -121,13 +120,3 @@ def sample_each_points(point_origins, directions, num_samples, near, far, radii,
                                      n_rays=b * d, rand_shared=True)
     dirs = f(directions)[None].expand(b, d, 3).reshape(-1, 3)
     return t, (means, covs), dirs
-
-
-def rearrange_render_image(rays, chunk_size=4096):
-    """models/mip.py:530-547."""
-    single = [getattr(rays, key) for key in Rays_keys]
-    val_mask = single[-3]
-    single = [a.reshape(-1, a.shape[-1]) for a in single]
-    length = single[0].shape[0]
-    single = [[a[i:i + chunk_size] for i in range(0, length, chunk_size)] for a in single]
-    return [Rays(*[a[i] for a in single]) for i in range(len(single[0]))], val_mask

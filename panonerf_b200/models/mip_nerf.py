@@ -102,14 +102,14 @@ class _NerfBase(torch.nn.Module):
                            kw["mlp_num_density_channels"], kw["mlp_net_activation"], xyz, view)
 
     # -- one level of the hot path -------------------------------------------------------------------------------
-    def _field(self, means, covs, venc, samples_per_ray, with_normals):
+    def _field(self, means, covs, venc, samples_per_ray, with_normals, venc_mod=0):
         if self.disable_integration:
             covs = torch.zeros_like(covs)
         return field.radiance_field(means, covs, venc, self.mlp.named_field_params(), precision=self.precision,
                                     samples_per_ray=samples_per_ray, min_deg=self.min_deg_point,
                                     max_deg=self.max_deg_point, density_bias=self.density_bias,
                                     skip=self.mlp.skip_index, with_normals=with_normals,
-                                    jac_precision=self.jac_precision)
+                                    jac_precision=self.jac_precision, venc_mod=venc_mod)
 
     def _prep_rays(self, rays):
         f = ops._f32c

@@ -53,8 +53,7 @@ class PanoMipNeRF(_NerfBase):
                     lit_t, lit_means, lit_covs = ops.env_cast(rays.origins, rays.directions, dist_in, env.directions,
                                                              env.radii, env.near, env.far, Ne, t_rand)
                     lit_venc = ops.pos_enc(env.directions, self.deg_view)            # [D,27], one per env direction
-                    lit_venc = lit_venc[None].expand(R, D, -1).reshape(R * D, -1).contiguous()
-                    e_rgb, e_den, _ = self._field(lit_means, lit_covs, lit_venc, Ne, False)
+                    e_rgb, e_den, _ = self._field(lit_means, lit_covs, lit_venc, Ne, False, venc_mod=D)
                     e_rgb, e_den, _ = ops.activations(e_rgb.view(R * D * Ne, -1), e_den.view(R * D * Ne, C),
                                                       self.density_bias, self.rgb_padding, False)
                     env_rgb = ops.composite(e_rgb.view(R * D, Ne, 3), e_den.view(R * D, Ne), lit_t, env.directions,

@@ -14,6 +14,12 @@ from ._lib import PNB_BF16, PNB_F32, check
 
 _VP = ctypes.c_void_p
 
+# The reference trains under Lightning's `precision='16-mixed'` (train.py:86): torch.autocast(fp16) + GradScaler.  Every
+# Function below runs its kernels in the precision it was built for, so under autocast floating-point inputs are cast
+# to fp32 and autocast is switched off inside forward / backward (SURVEY.md section 8b "precision context").
+_amp_fwd = torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+_amp_bwd = torch.amp.custom_bwd(device_type="cuda")
+
 
 def _p(t: Optional[torch.Tensor]):
     return None if t is None else _VP(t.data_ptr())
@@ -215,6 +221,7 @@ class _Act(torch.autograd.Function):
     """rgb/density/albedo activations of compute_graph (models/pano_mip_nerf.py:264-278)."""
 
     @staticmethod
+    @_amp_fwd
     def forward(ctx, raw_rgb, raw_den, density_bias, rgb_padding, want_albedo):
         m, c = raw_den.shape
         dev = raw_den.device
@@ -232,6 +239,7 @@ class _Act(torch.autograd.Function):
         return rgb, den, None
 
     @staticmethod
+    @_amp_bwd
     def backward(ctx, d_rgb, d_den, d_alb):
         raw_rgb, raw_den = ctx.saved_tensors
         m, c = raw_den.shape
@@ -253,6 +261,7 @@ class _Composite(torch.autograd.Function):
     """volumetric_rendering (models/mip.py:444-483)."""
 
     @staticmethod
+    @_amp_fwd
     def forward(ctx, rgb, density, t, dirs, d_mod, white_bkgd):
         r, n = density.shape
         dev = rgb.device
@@ -269,6 +278,7 @@ class _Composite(torch.autograd.Function):
         return comp, dist, acc, w
 
     @staticmethod
+    @_amp_bwd
     def backward(ctx, g_comp, g_dist, g_acc, g_w):
         rgb, density, t, dirs = ctx.saved_tensors
         r, n = density.shape
@@ -293,6 +303,7 @@ class _Normals(torch.autograd.Function):
     (models/pano_mip_nerf.py:296-317, models/mip_nerf.py:258-277)."""
 
     @staticmethod
+    @_amp_fwd
     def forward(ctx, n_raw, weights, dirs, albedos):
         r, n = weights.shape
         dev = weights.device
@@ -307,6 +318,7 @@ class _Normals(torch.autograd.Function):
         return normal, ort, alb
 
     @staticmethod
+    @_amp_bwd
     def backward(ctx, g_normal, g_ort, g_alb):
         n_raw, weights, dirs, albedos = ctx.saved_tensors
         r, n = weights.shape
@@ -330,6 +342,7 @@ class _EnvCast(torch.autograd.Function):
     sample_each_points (models/mip.py:154-194).  Differentiable w.r.t. `distance` (detach_dist=False upstream)."""
 
     @staticmethod
+    @_amp_fwd
     def forward(ctx, origins, dirs, distance, env_dirs, env_radii, env_near, env_far, n_env, t_rand):
         r, d = origins.shape[0], env_dirs.shape[0]
         dev = origins.device
@@ -345,6 +358,7 @@ class _EnvCast(torch.autograd.Function):
         return t, means, covs
 
     @staticmethod
+    @_amp_bwd
     def backward(ctx, g_t, g_means, g_covs):
         (dirs,) = ctx.saved_tensors
         r = dirs.shape[0]
@@ -364,6 +378,7 @@ class _Shade(torch.autograd.Function):
     """Lambertian surface rendering (utils/surface_rendering.py:104-165, roughness=None branch)."""
 
     @staticmethod
+    @_amp_fwd
     def forward(ctx, env_rgb, albedo, normal, light_dirs, solid_angle):
         r, d = env_rgb.shape[0], env_rgb.shape[1]
         dev = env_rgb.device
@@ -378,6 +393,7 @@ class _Shade(torch.autograd.Function):
         return rgb, shading
 
     @staticmethod
+    @_amp_bwd
     def backward(ctx, g_rgb, g_shading):
         env_rgb, albedo, normal, light_dirs, solid_angle = ctx.saved_tensors
         r, d = env_rgb.shape[0], env_rgb.shape[1]
@@ -400,6 +416,7 @@ class _TonemapMSE(torch.autograd.Function):
     `inv_mask_sum` is a python float or a 0-dim device tensor (1 / mask.sum() computed on the device)."""
 
     @staticmethod
+    @_amp_fwd
     def forward(ctx, pred, gt_ldr, mask, inv_mask_sum):
         r = pred.shape[0]
         partial = torch.empty(r, device=pred.device, dtype=torch.float32)
@@ -413,6 +430,7 @@ class _TonemapMSE(torch.autograd.Function):
         return dsum(partial, inv_mask_sum)
 
     @staticmethod
+    @_amp_bwd
     def backward(ctx, g):
         pred, gt_ldr, mask = ctx.saved_tensors
         d_pred = torch.empty_like(pred)
@@ -431,6 +449,7 @@ class _Chroma(torch.autograd.Function):
     """mean((normalize(gt) - normalize(albedo))^2)   (systems/panonerf_system.py:58-63)."""
 
     @staticmethod
+    @_amp_fwd
     def forward(ctx, gt_ldr, albedo):
         r = albedo.shape[0]
         partial = torch.empty(r, device=albedo.device, dtype=torch.float32)
@@ -441,6 +460,7 @@ class _Chroma(torch.autograd.Function):
         return dsum(partial, 1.0 / (3 * r))
 
     @staticmethod
+    @_amp_bwd
     def backward(ctx, g):
         gt_ldr, albedo = ctx.saved_tensors
         r = albedo.shape[0]
@@ -459,15 +479,70 @@ class _Mean(torch.autograd.Function):
     """Deterministic mean of a per-ray vector (ort_loss `.mean()`, models/pano_mip_nerf.py:311)."""
 
     @staticmethod
+    @_amp_fwd
     def forward(ctx, x):
         ctx.n = x.numel()
         ctx.dev = x.device
         return dsum(x.contiguous(), 1.0 / x.numel())
 
     @staticmethod
+    @_amp_bwd
     def backward(ctx, g):
         return (g / ctx.n).expand(ctx.n)
 
 
 def dmean(x):
     return _Mean.apply(x)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# render driver / validation outputs (csrc/image.cu)
+# --------------------------------------------------------------------------------------------------------------
+def pack_chw(per_ray, out, pix0: int):
+    """Scatter per-ray results (list of [R, c_i] fp32 tensors) of rays [pix0, pix0+R) into `out` [sum(c_i), H*W]."""
+    r = per_ray[0].shape[0]
+    n = len(per_ray)
+    chans = [int(x.shape[1]) if x.dim() == 2 else 1 for x in per_ray]
+    if sum(chans) != out.shape[0]:
+        raise RuntimeError("pack_chw: channel counts do not add up to the output planes")
+    keep = [_req(x.reshape(r, c), "per-ray result") for x, c in zip(per_ray, chans)]
+    src = (ctypes.c_void_p * n)(*[x.data_ptr() for x in keep])
+    ch = (ctypes.c_int * n)(*chans)
+    with torch.cuda.device(out.device):
+        check(_lib.lib().pnb_pack_chw(r, out.shape[1], int(pix0), n, src, ch, _p(_req(out, "out")), _stream()),
+              "pack_chw")
+    return out
+
+
+def image_sqerr_sum(pred, gt, row_weights=None):
+    """sum((pred - gt)^2 [* row weight]) over a [C,H,W] image pair, fixed summation order -> 0-dim tensor."""
+    pred, gt = _req(pred, "pred"), _req(gt, "gt")
+    if pred.shape != gt.shape or pred.dim() != 3:
+        raise RuntimeError("image metrics expect two [C,H,W] tensors of the same shape")
+    c, h, w = pred.shape
+    tmp = torch.empty(pred.numel(), device=pred.device, dtype=torch.float32)
+    with torch.cuda.device(pred.device):
+        check(_lib.lib().pnb_image_sqerr(pred.numel(), w, h * w, _p(pred), _p(gt),
+                                         _p(None if row_weights is None else _req(row_weights, "row_weights")),
+                                         _p(tmp), _stream()), "image_sqerr")
+    return dsum(tmp)
+
+
+def exr_payload(chw):
+    """Scan-line blocks (uint8 device tensor) of an uncompressed float32 OpenEXR file for a [C,H,W] image."""
+    chw = _req(chw, "image")
+    c, h, w = chw.shape
+    out = torch.empty(int(_lib.lib().pnb_exr_payload_bytes(h, w)), device=chw.device, dtype=torch.uint8)
+    with torch.cuda.device(chw.device):
+        check(_lib.lib().pnb_exr_pack(h, w, c, _p(chw), _p(out), _stream()), "exr_pack")
+    return out
+
+
+def png_payload(chw):
+    """Filtered 8-bit RGB scan lines (uint8 device tensor) of a PNG for a [C,H,W] image in [0,1]."""
+    chw = _req(chw, "image")
+    c, h, w = chw.shape
+    out = torch.empty(int(_lib.lib().pnb_png_payload_bytes(h, w)), device=chw.device, dtype=torch.uint8)
+    with torch.cuda.device(chw.device):
+        check(_lib.lib().pnb_png_pack(h, w, c, _p(chw), _p(out), _stream()), "png_pack")
+    return out

@@ -193,6 +193,63 @@ class GraphedTrainStep:
         return self.loss
 
 
+class AccumulatedTrainStep:
+    """One optimiser step on a batch that is walked in `micro_batches` equal slices (gradient accumulation): the
+    graph holds forward + backward of ONE slice with the loss pre-scaled by 1/micro_batches and is replayed per slice;
+    the flat gradient buffer accumulates (field.py writes `+=`), then one all-reduce and one Adam update follow.
+    Equal slices make the accumulated gradient the gradient of the whole-batch mean loss (systems/*_system.py divide
+    by `mask.sum()` of the batch; `lossmult` is 1 for panoramas, datasets/pano_datasets.py:192).  This is how
+    BASELINE.json's 65 536 rays/GPU step (config C4) runs in a bounded activation footprint: the saved planes of a
+    65 536-ray step would be ~150 GB, those of an 8192-ray slice are ~19 GB."""
+
+    def __init__(self, system, opt, rays, gts, micro_batches, warmup=2):
+        n = gts.shape[0]
+        if n % micro_batches:
+            raise ValueError("the batch must divide into equal micro-batches")
+        self.system, self.opt, self.k, self.mb = system, opt, micro_batches, n // micro_batches
+        dev = gts.device
+        self.dev = dev
+        self.rays = type(rays)(*[x[:self.mb].clone() for x in rays])
+        self.gts = gts[:self.mb].clone()
+        self.hyper = torch.zeros(3, device=dev, dtype=torch.float32)
+        self.loss_sum = torch.zeros((), device=dev, dtype=torch.float32)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._slice_body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        opt.zero_grad()
+        # the bf16 weight packs must be rebuilt inside the graph: the parameters change between optimiser steps
+        field.invalidate_packs()
+        l0 = ops.launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._slice_body()
+        self.launches_per_slice = ops.launch_count() - l0
+        opt.zero_grad()
+
+    def _slice_body(self):
+        loss = self.system.training_step((self.rays, self.gts)) * (1.0 / self.k)
+        loss.backward()
+        self.loss_sum += loss.detach()
+
+    def __call__(self, rays, gts):
+        self.opt.zero_grad()
+        self.loss_sum.zero_()
+        for i in range(self.k):
+            sl = slice(i * self.mb, (i + 1) * self.mb)
+            for dst, src in zip(self.rays, rays):
+                dst.copy_(src[sl], non_blocking=True)
+            self.gts.copy_(gts[sl], non_blocking=True)
+            self.graph.replay()
+        self.hyper.copy_(torch.tensor(self.opt.next_hyper(), dtype=torch.float32))
+        self.opt.step_dev(self.hyper)
+        self.system.global_step += 1
+        return self.loss_sum
+
+
 class BaseSystem(torch.nn.Module):
     """systems/base_system.py:9-55 (model construction) + :81-87 (optimiser)."""
 
@@ -231,14 +288,35 @@ class BaseSystem(torch.nn.Module):
             num_env_samples=hp["nerf.num_env_samples"], precision=hp.get("precision"))
         self.env_rays = None
 
-    RENDER_CHUNK = 32768
-
-    def render_chunk(self):
+    def render_rays_per_launch(self, n_rays):
         """Rays per forward of `render_image`.  Upstream walks a panorama in `val.chunk_size` = 512-ray chunks (1024
-        sequential forwards, GPU mostly idle - SURVEY.md section 8f rank 2); chunking does not change the result
-        (rays are independent; tests/test_models_gpu.py checks bit-identity), so the knob is only a lower bound here
-        and a panorama is rendered in 32 k-ray chunks (16 forwards, ~2 GB of transient buffers)."""
-        return max(int(self.val_chunk_size), self.RENDER_CHUNK)
+        sequential forwards, GPU mostly idle - SURVEY.md section 8f rank 2).  Rays are independent, so chunking never
+        changes a pixel (tests/test_models_gpu.py checks bit-identity); here the whole image is ONE forward - a fixed,
+        small number of launches over all H*W rays - unless its transient buffers (~0.8 KB per sample: Gaussians, raw
+        outputs, the fp32 encoding gradient of the normals) would not fit in half of the free device memory, and
+        `val.chunk_size` is a no-op knob."""
+        per_ray = 768 * int(self.hparams["nerf.num_samples"]) + 8192
+        free, _ = torch.cuda.mem_get_info()
+        fit = max(1024, int(0.5 * free / per_ray) // 1024 * 1024)
+        return min(int(n_rays), fit)
+
+    def _render_into(self, rays, height, width, channels, forward, chunk_size=None):
+        """Render driver: forwards over ray ranges (normally one), per-ray results scattered straight into the
+        [sum(channels), H, W] image planes by one kernel per range (csrc/image.cu) - no list-of-chunks, no cat, no
+        permute (replaces models/mip.py:530-547 rearrange_render_image + systems/*_system.py compose())."""
+        n = height * width
+        flat = type(rays)(*[ops._f32c(x.reshape(n, x.shape[-1])) for x in rays])
+        per = int(chunk_size) if chunk_size else self.render_rays_per_launch(n)
+        out = torch.empty(sum(channels), n, device=flat[0].device, dtype=torch.float32)
+        with torch.no_grad():
+            for r0 in range(0, n, per):
+                part = type(rays)(*[x[r0:r0 + per] for x in flat])
+                ops.pack_chw(forward(part), out, r0)
+        images, c0 = [], 0
+        for c in channels:
+            images.append(out[c0:c0 + c].view(1, c, height, width))
+            c0 += c
+        return images
 
     def configure_optimizers(self):
         hp = self.hparams

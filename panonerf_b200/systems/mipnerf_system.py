@@ -2,7 +2,6 @@
 import torch
 
 from .. import ops
-from ..models.mip import rearrange_render_image
 from .base_system import BaseSystem
 
 
@@ -27,19 +26,13 @@ class MipNeRFSystem(BaseSystem):
         return loss
 
     def render_image(self, batch, chunk_size=None):
+        """systems/mipnerf_system.py:95-127: same 6-tuple of [1,C,H,W] images, produced by the render driver."""
         rays, rgbs = batch[:2]
         _, height, width, _ = rgbs.shape
-        chunks, _ = rearrange_render_image(rays, chunk_size or self.render_chunk())
-        outs = [[] for _ in range(6)]
-        with torch.no_grad():
-            for batch_rays in chunks:
-                (vol_c, dep_c, _, nor_c), (vol_f, dep_f, _, nor_f) = self.mip_nerf(
-                    rays=batch_rays, randomized=self.val_randomized, white_bkgd=self.white_bkgd, use_ort_loss=True)
-                for lst, v in zip(outs, (vol_c, vol_f, dep_c, dep_f, nor_c, nor_f)):
-                    lst.append(v)
 
-        def compose(x, dim=3):
-            return torch.cat(x, dim=0).view(1, height, width, dim).permute(0, 3, 1, 2)
+        def forward(part):
+            (vol_c, dep_c, _, nor_c), (vol_f, dep_f, _, nor_f) = self.mip_nerf(
+                rays=part, randomized=self.val_randomized, white_bkgd=self.white_bkgd, use_ort_loss=True)
+            return [vol_c, vol_f, dep_c, dep_f, nor_c, nor_f]
 
-        return (compose(outs[0]), compose(outs[1]), compose(outs[2], 1), compose(outs[3], 1), compose(outs[4]),
-                compose(outs[5]))
+        return tuple(self._render_into(rays, height, width, (3, 3, 1, 1, 3, 3), forward, chunk_size))

@@ -2,7 +2,6 @@
 import torch
 
 from .. import ops
-from ..models.mip import rearrange_render_image
 from .base_system import BaseSystem
 
 
@@ -30,23 +29,16 @@ class PanoNeRFSystem(BaseSystem):
         return loss
 
     def render_image(self, batch, chunk_size=None):
+        """systems/panonerf_system.py:133-192: same 9-tuple of [1,C,H,W] images, produced by the render driver."""
         rays, rgbs = batch[:2]
         _, height, width, _ = rgbs.shape
-        chunks, _ = rearrange_render_image(rays, chunk_size or self.render_chunk())
-        keys = ("coarse_rgb", "fine_rgb", "coarse_dep", "fine_dep", "fine_nor", "albedo", "surface_rgb", "shading")
-        acc = {k: [] for k in keys}
-        with torch.no_grad():
-            for batch_rays in chunks:
-                (c_rgb, c_dep, *_), (f_rgb, f_dep, _, f_nor, alb, rhn, sf_rgb, _, sd) = self.mip_nerf(
-                    rays=batch_rays, env_rays=self.env_rays, randomized=self.val_randomized,
-                    white_bkgd=self.white_bkgd, enable_surf=True, use_ort_loss=True)
-                for k, v in zip(keys, (c_rgb, f_rgb, c_dep, f_dep, f_nor, alb, sf_rgb, sd)):
-                    if v is not None:
-                        acc[k].append(v)
 
-        def compose(x, dim=3):
-            return torch.cat(x, dim=0).view(1, height, width, dim).permute(0, 3, 1, 2) if len(x) else None
+        def forward(part):
+            (c_rgb, c_dep, *_), (f_rgb, f_dep, _, f_nor, alb, rhn, sf_rgb, _, sd) = self.mip_nerf(
+                rays=part, env_rays=self.env_rays, randomized=self.val_randomized, white_bkgd=self.white_bkgd,
+                enable_surf=True, use_ort_loss=True)
+            return [c_rgb, f_rgb, c_dep, f_dep, f_nor, alb, sf_rgb, sd]
 
-        return (compose(acc["coarse_rgb"]), compose(acc["fine_rgb"]), compose(acc["coarse_dep"], 1),
-                compose(acc["fine_dep"], 1), compose(acc["fine_nor"]), compose(acc["albedo"]), [],
-                compose(acc["surface_rgb"]), compose(acc["shading"]))
+        c_rgb, f_rgb, c_dep, f_dep, nor, alb, sf, sd = self._render_into(rays, height, width, (3, 3, 1, 1, 3, 3, 3, 3),
+                                                                        forward, chunk_size)
+        return c_rgb, f_rgb, c_dep, f_dep, nor, alb, [], sf, sd

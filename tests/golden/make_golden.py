@@ -173,6 +173,28 @@ def model_fixture(ns, name, pano, width, b, n, h, w, sd_from_seed=None, store_gr
             out["grad/" + k] = npy(g)
         else:
             out["gslice/" + k] = npy(g.reshape(-1)[:: max(1, g.numel() // gslice)][:gslice])
+    if not store_grads:
+        # float64 evaluation of the oracle on the same inputs: the yardstick for the gradient bounds.  Sums over ~1e6
+        # samples with heavy cancellation (high IPE frequencies, 1/|grad sigma| in the normals) make every fp32
+        # gradient - the reference's own included - deviate from the exact value; the tests require ours to be as
+        # close to this float64 value as the reference's fp32 gradient is.
+        for tag, ort_on in (("g64", True),) + ((("noort/g64", False),) if not pano else ()):
+            sd64 = {k: v.detach().double().clone().requires_grad_() for k, v in model.mlp.state_dict().items()}
+            r64 = O.Rays(*[x.double() for x in r])
+            if pano:
+                e64 = O.Rays(*[x.double() for x in env32])
+                res64, _ = O.panonerf_forward(sd64, r64, e64, dict(num_samples=n), train=True)
+                l64 = O.panonerf_loss(res64, r64, gt.double())
+            else:
+                res64, _ = O.mipnerf_forward(sd64, r64, dict(num_samples=n), use_ort_loss=ort_on, train=True)
+                l64 = O.mipnerf_loss(res64, r64, gt.double(), ort_mult=0.1 if ort_on else 0.0)
+            l64.backward()
+            out[tag + "/loss"] = np.array(float(l64))
+            for k, v in sd64.items():
+                g = v.grad
+                out[tag + "/gnorm/" + k] = np.array(float(g.norm()))
+                out[tag + "/gslice/" + k] = npy(g.reshape(-1)[:: max(1, g.numel() // gslice)][:gslice])
+            print(name, tag, "float64 loss", float(l64))
     if not pano and not store_grads:
         # first-order variant (configs/mipnerf.yaml: ort_loss 0 -> no normals, no second-order terms): the gradient is a
         # plain sum over samples, so the fp32 parity path can be held to a 1e-5-class bound

@@ -123,8 +123,10 @@ def test_adam_hyper_parameters_for_the_graph_step():
 
 
 def test_bench_roofline_report_schema():
-    """bench.py's roofline object from a (fake) per-kernel profile: dominant family first, the contract's keys present,
-    tensor-bound families measured in TFLOP/s against the sustained peak, HBM-bound ones in GB/s."""
+    """bench.py's roofline object from a (fake) per-kernel profile: every MLP family is TENSOR-bound (SURVEY.md
+    section 8d) and measured in TFLOP/s against the sustained peak; the programs of mlp_fused_kernel<P> are one
+    family; the headline is the family with the most device time; the MLP stage and the whole step are reported;
+    the HBM view (designed bytes, GB/s) sits beside it and the fused-ideal I/O is the algorithmic byte count."""
     import bench
 
     class Ev:
@@ -136,13 +138,17 @@ def test_bench_roofline_report_schema():
 
     prof = {"wgrad_batch": dict(events=[(Ev(0), Ev(2.0))], bytes=10e9, flops=1e12),
             "mlp_fused": dict(events=[(Ev(0), Ev(1.0))], bytes=1e9, flops=1.2e12),
-            "mlp_fused_bwd": dict(events=[(Ev(0), Ev(0.5))], bytes=1e9, flops=0.3e12)}
-    r = bench.roofline_from_profile(prof, 1, dict(hbm=6500.0, tf_burst=1685.0, tf_sust=1382.0, src="measured"))
-    assert r["kernel"] == "wgrad_batch" and r["bound"] == "hbm" and r["unit"] == "GB/s"
-    assert abs(r["achieved"] - 5000.0) < 1e-6 and abs(r["frac"] - 5000.0 / 6500.0) < 1e-9
-    for k in ("peak", "traffic", "launches_per_step", "avg_launch_ms", "kernel_ms_per_step", "other_kernels"):
+            "mlp_fused_bwd": dict(events=[(Ev(0), Ev(1.5))], bytes=1e9, flops=0.3e12)}
+    pk = dict(hbm=6500.0, tf_burst=1685.0, tf_sust=1382.0, src="measured")
+    r = bench.roofline_from_profile(prof, 1, pk, step_ms=5.0, step_flop=2.5e12, ideal_bytes_per_step=3e8)
+    assert r["kernel"] == "mlp_fused_kernel" and r["bound"] == "tensor" and r["unit"] == "TFLOP/s"
+    assert abs(r["achieved"] - 600.0) < 1e-6 and abs(r["frac"] - 600.0 / 1382.0) < 1e-9 and r["peak"] == 1382.0
+    for k in ("traffic", "launches_per_step", "avg_launch_ms", "kernel_ms_per_step", "other_kernels", "hbm"):
         assert k in r
-    o = r["other_kernels"]["mlp_fused"]
-    assert o["bound"] == "tensor" and o["unit"] == "TFLOP/s" and abs(o["achieved"] - 1200.0) < 1e-6
-    allp = r["fused_mlp_all_programs"]
-    assert abs(allp["kernel_ms_per_step"] - 1.5) < 1e-9 and abs(allp["achieved"] - 1000.0) < 1e-6
+    assert set(r["programs"]) == {"mlp_fused", "mlp_fused_bwd"}
+    o = r["other_kernels"]["wgrad_batch_kernel"]
+    assert o["bound"] == "tensor" and abs(o["achieved"] - 500.0) < 1e-6
+    assert abs(o["hbm"]["gbps"] - 5000.0) < 1e-6 and abs(o["hbm"]["frac_of_copy_bandwidth"] - 5000.0 / 6500.0) < 1e-9
+    assert abs(r["mlp_stage"]["kernel_ms_per_step"] - 4.5) < 1e-9 and abs(r["mlp_stage"]["achieved"] - 2.5e3 / 4.5) < 1e-6
+    assert abs(r["whole_step"]["achieved"] - 500.0) < 1e-6 and abs(r["whole_step"]["frac"] - 500.0 / 1382.0) < 1e-9
+    assert r["algorithmic_bytes_per_step"] == 3e8 and r["designed_bytes_per_step"] == 12e9

@@ -220,3 +220,62 @@ def test_head_grad_padding_and_group_sum():
     out = field._group_sum(z[:, :128], S)
     ref = z[:, :128].float().view(M // S, S, 128).sum(1)
     assert_close(out, ref, 1e-6, "group_sum (bf16x2 path)")
+
+
+@pytest.mark.parametrize("S,R,with_normals", [(64, 16, False), (64, 16, True), (10, 13, False), (64, 700, True)])
+def test_in_kernel_ipe_is_bit_identical_to_the_two_kernel_path(S, R, with_normals):
+    """Inference forward: the encoder warps of the fused kernel evaluate the IPE in the kernel (no [M,96] array);
+    the raw outputs and the density-gradient normals must equal those of pnb_ipe_fwd + pnb_mlp_fused_fwd bit for bit
+    (same arithmetic, same bf16 rounding of the features).  Sizes cover a partial tile, an odd number of tiles (the
+    phantom tile of the last pair) and several pairs per CTA-free grid."""
+    _tc_or_skip()
+    if R > 16:
+        g = load_golden("panonerf_c2s.npz")
+        sd = golden_state_dict(g)
+        rays, _ = golden_rays(g, DEV)
+        from panonerf_b200 import ops
+        rays = type(rays)(*[x[:R].contiguous() for x in rays])
+        _, means, covs = ops.sample_cast(rays.origins, rays.directions, rays.radii, rays.near, rays.far, S)
+        venc = ops.pos_enc(rays.viewdirs, 4)
+    else:
+        sd, means, covs, venc = _inputs(S, R)
+    outs = []
+    for no_ipe in (True, False):
+        if no_ipe:
+            os.environ["PNB_NO_FUSED_IPE"] = "1"
+        try:
+            outs.append(_field(sd, means, covs, venc, S, True, with_normals))
+        finally:
+            os.environ.pop("PNB_NO_FUSED_IPE", None)
+    a, b = outs
+    assert torch.equal(a["raw_rgb"], b["raw_rgb"]) and torch.equal(a["raw_den"], b["raw_den"])
+    if with_normals:
+        assert torch.equal(a["n_raw"], b["n_raw"])
+    assert torch.isfinite(b["raw_rgb"]).all()
+
+
+def test_env_view_term_indexed_modulo_directions():
+    """Env rays share their D directions: passing the D view encodings with venc_mod = D must equal passing the
+    expanded [R*D, 27] encodings (models/pano_mip_nerf.py:337-341), in inference (in-kernel IPE) and in training."""
+    _tc_or_skip()
+    from panonerf_b200 import field
+    sd, means, covs, venc = _inputs(10, 16)            # 16 "env rays" of 10 samples: 8 points x D = 2 directions
+    D = 2
+    venc_d = venc[:D].contiguous()
+    venc_full = venc_d[None].expand(8, D, -1).reshape(16, -1).contiguous()
+    params = {k: v.clone().to(DEV) for k, v in sd.items()}
+    kw = dict(precision="bf16", samples_per_ray=10, min_deg=0, max_deg=16, density_bias=-1.0, skip=4, with_normals=False)
+    with torch.no_grad():
+        a = field.radiance_field(means, covs, venc_full, params, **kw)
+        b = field.radiance_field(means, covs, venc_d, params, venc_mod=D, **kw)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    gen = torch.Generator().manual_seed(0)
+    g1 = torch.randn(16, 10, 3, generator=gen).to(DEV)
+    grads = []
+    for ve, mod in ((venc_full, 0), (venc_d, D)):
+        ps = {k: v.clone().to(DEV).requires_grad_() for k, v in sd.items()}
+        rgb, den, _ = field.radiance_field(means, covs, ve, ps, venc_mod=mod, **kw)
+        (rgb * g1).sum().backward()
+        grads.append({k: p.grad.clone() for k, p in ps.items()})
+    for k in grads[0]:      # (not bit-equal run to run: the head-bias sums use float atomics)
+        assert_close(grads[1][k], grads[0][k], 1e-5, k, floor=max(float(grads[0][k].abs().max()), 1e-12))

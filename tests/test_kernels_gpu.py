@@ -107,30 +107,15 @@ def test_ipe_and_posenc(golden_ops):
     from panonerf_b200 import ops
     out = torch.empty(4096, 96, device=DEV)
     ops.ipe_into(mean.to(DEV), cov.to(DEV), 0, 16, out)
-    diff = (out.cpu() - ref.detach()).abs()
-    if float(diff.max()) >= 2e-6:
-        # Seen intermittently (about 1 full-suite run in 5, never in isolation): one or two of the 393 216 features
-        # differ from the CPU evaluation by ~1e-4.  Pin the blame before failing: the two GPU kernels (SFU fast path
-        # and double-precision exact path) must agree with each other everywhere, and the kernel must be repeatable;
-        # then at most a handful of isolated outliers against the CPU reference are tolerated (and reported).
-        import os
-        import warnings
-        m_, j_ = divmod(int(diff.argmax()), 96)
-        again = torch.empty(4096, 96, device=DEV)
-        ops.ipe_into(mean.to(DEV), cov.to(DEV), 0, 16, again)
-        os.environ["PNB_IPE_SLOW"] = "1"
-        try:
-            exact = torch.empty(4096, 96, device=DEV)
-            ops.ipe_into(mean.to(DEV), cov.to(DEV), 0, 16, exact)
-        finally:
-            del os.environ["PNB_IPE_SLOW"]
-        msg = (f"ipe vs CPU: err {float(diff.max()):.3e} at sample {m_} feature {j_}: gpu {float(out[m_, j_])!r} "
-               f"rerun {float(again[m_, j_])!r} exact-path {float(exact[m_, j_])!r} cpu {float(ref[m_, j_])!r} "
-               f"mean {mean[m_].tolist()} cov {cov[m_].tolist()} outliers {int((diff >= 2e-6).sum())}")
-        assert torch.equal(out, again), "ipe kernel is not repeatable: " + msg
-        assert float((out - exact).abs().max()) < 2e-6, "fast and exact GPU paths disagree: " + msg
-        assert int((diff >= 2e-6).sum()) <= 8 and float(diff.max()) < 1e-3, msg
-        warnings.warn(msg)
+    # Strict pin, twice: against the CPU oracle (fp32 torch.sin / exp on this host) and against the float64 value of
+    # the reference's formula on the reference's own fp32 arguments (oracle.ipe_exact) - the number any correct fp32
+    # sin approximates, independent of the host's libm.  Round 1 tolerated "1-2 outliers of 1e-4 in about 1 of 5
+    # suite runs"; tools/ipe_repro.py (profiles/r02_ipe_outlier_hunt.md) could not reproduce one in 240 seeded cases
+    # on three boxes - CPU oracle, SFU fast path and double-precision path all stay within 4.7e-7 of float64.
+    exact = O.ipe_exact(mean, cov, 0, 16)
+    assert float((out.cpu().double() - exact).abs().max()) < 2e-6, "GPU IPE vs float64 evaluation"
+    assert float((ref.detach().double() - exact).abs().max()) < 2e-6, "this host's fp32 torch.sin/exp vs float64 (CPU side)"
+    assert float((out.cpu() - ref.detach()).abs().max()) < 2e-6, "GPU IPE vs CPU oracle"
     gvec = torch.randn(4096, 96, generator=gen)
     (gref,) = torch.autograd.grad((ref * gvec).sum(), mean_r)
     gout = ops.ipe_vjp(mean.to(DEV), cov.to(DEV), 0, 16, gvec.to(DEV))
@@ -224,11 +209,9 @@ def test_resample_seeded(n):
     t = torch.sort(torch.rand(R, n + 1, generator=gen) * 10, dim=-1).values
     ref, inds_ref, _ = O.pdf_sample(t, O.blur_weights(w, 0.01), n + 1, False, return_aux=True)
     out, inds = ops.resample(t.to(DEV), w.to(DEV), 0.01, return_inds=True)
-    mism = int((inds.cpu() != inds_ref).sum())
-    # the only source of disagreement is the 1-ulp freedom of torch.sum's CPU reduction order in weight_sum (AVX
-    # lane order, not reproducible across hosts); the inverse CDF is continuous, so even then the sample agrees
-    assert mism <= R * (n + 1) // 20000, f"{mism} index mismatches"
-    assert_close(out.cpu(), ref, 5e-5, "new_t", floor=0.1)
+    # bit-exact: the kernel reproduces torch.sum's CPU reduction order (ATen vectorized_inner_sum) and the fp64 cumsum
+    assert torch.equal(inds.cpu(), inds_ref), f"{int((inds.cpu() != inds_ref).sum())} index mismatches"
+    assert torch.equal(out.cpu(), ref), "resampled fence-posts differ from the oracle's"
     assert bool((out[:, 1:] >= out[:, :-1]).all())
     assert float(out.min()) >= float(t.min()) and float(out.max()) <= float(t.max())
 

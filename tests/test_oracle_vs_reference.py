@@ -52,3 +52,24 @@ def test_jacrev_normals_equal_autograd_normals():
     a = O._density_normals(sd, mean, cov, vd, cfg, False)
     b = O._density_normals(sd, mean, cov, vd, {**cfg, "normals_impl": "jacrev"}, False)
     assert torch.allclose(a, b, rtol=1e-4, atol=1e-6)
+
+
+def test_metric_and_image_restatements_match_reference():
+    """oracle.calc_psnr / calc_ws_psnr / solid_angle_refinement / png_pixels against utils/metrics.py,
+    utils/surface_rendering.py and utils/vis.py of the upstream tree."""
+    import importlib
+    import sys
+    ns = rh.load()
+    sys.path.insert(0, rh.REF_ROOT)
+    try:
+        metrics = importlib.import_module("utils.metrics")
+    finally:
+        sys.path.remove(rh.REF_ROOT)
+    g = torch.Generator().manual_seed(0)
+    a, b = torch.rand(3, 16, 32, generator=g), torch.rand(3, 16, 32, generator=g)
+    assert torch.equal(O.solid_angle_refinement(16, 32), ns.surface_rendering.solid_angle_refinement(h=16, w=32))
+    assert float(O.calc_psnr(a, b)) == float(metrics.calc_psnr(a, b))
+    assert float(O.calc_ws_psnr(a, b)) == float(metrics.calc_ws_psnr(a, b))
+    img = a[None]
+    ref = (img[0].permute(1, 2, 0).data.cpu().numpy() * 255).astype(np.uint8)        # utils/vis.py:29-35
+    assert np.array_equal(O.png_pixels(img), ref)

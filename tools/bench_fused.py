@@ -35,6 +35,9 @@ def main():
     masks = field.fused_masks(M, dev, save)
     kernel = "mlp_fused"
     run = lambda: field.fused_forward(enc, vb, S, C, pack, acts, g_enc, masks, save)
+    if "--ipe" in sys.argv:      # IPE computed inside the kernel (encoder warps)
+        run = lambda: field.fused_forward_ipe(means, covs, 0, vb, 0, S, C, pack, g_enc)
+        kernel = "mlp_fused(in-kernel ipe)"
     if "--bwd" in sys.argv or "--jadj" in sys.argv:
         masks = field.fused_masks(M, dev, True)
         field.fused_forward(enc, vb, S, C, pack, None, None, masks, True)        # real sign bits

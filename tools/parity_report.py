@@ -55,6 +55,12 @@ def grads_report(system, g, prefix=""):
         rep[k] = {"slice_rel_err": float((got - ref).norm() / max(float(ref.norm()), 1e-30)),
                   "slice_cos": float((got @ ref) / (got.norm() * ref.norm() + 1e-30)),
                   "gnorm_ratio": float(p.grad.norm()) / max(gn_ref, 1e-30)}
+        tkey = prefix + "g64/gslice/" + k
+        if tkey in g:                       # float64 oracle value: how far are we / is the fp32 reference from it
+            tr = T(g[tkey]).double()
+            rep[k].update(truth_rel_err=float((got - tr).norm() / tr.norm()), truth_cos=float((got @ tr) / (got.norm() * tr.norm())),
+                          ref_truth_rel_err=float((ref - tr).norm() / tr.norm()),
+                          ref_truth_cos=float((ref @ tr) / (ref.norm() * tr.norm())))
     return rep
 
 
