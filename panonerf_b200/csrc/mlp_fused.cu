@@ -47,7 +47,7 @@ constexpr int kSlotBytes = 32768;  // ring slot: a weight tile of up to 256 rows
 constexpr int kKbBytes = 16384;    // one k-block: 128 rows x 64 bf16, 128B-swizzled
 constexpr int kAbufBytes = 4 * kKbBytes;
 constexpr int kFThreads = 384;  // producer, MMA, 2 encoder warps, 8 epilogue warps
-constexpr int kMaxSteps = 80, kMaxOps = 24, kMaxPack = 160, kSlots = 3, kMaxLoads = 2 * 80 + 16;
+constexpr int kMaxSteps = 96, kMaxOps = 24, kMaxPack = 176, kSlots = 3, kMaxLoads = 2 * 96 + 16;
 constexpr int kNumParams = 12;  // weights (and biases) in state-dict order: layers 0..7, density, extra, view, colour
 constexpr int kActPlanes = 18, kBwdPlanes = 10, kAdjPlanes = 8;
 constexpr int kMaskPlanes = 9;  // ReLU sign bits: trunk layers 0..7, view layer
@@ -64,7 +64,15 @@ constexpr int kBiasHE = 2048, kBiasHD = 2304, kBiasC = 2320, kWDen = 2336, kWCol
 // Step flags.  The kernel consumes F_AENC only (A operand = the IPE tile in the ring instead of the activation buffer);
 // the other three annotate the forward walk of a step list - which step needs / releases the IPE tile, which one starts
 // the accumulation - and are re-derived per tile by plan_ring (tile 1 walks every op backwards).
-enum : uint32_t { F_AENC = 1, F_LOADENC = 2, F_RELENC = 4, F_FIRST = 8 };
+enum : uint32_t { F_AENC = 1, F_LOADENC = 2, F_RELENC = 4, F_FIRST = 8, F_ABIAS = 16 };
+// Bias as one more K = 16 MMA step (F_ABIAS): D += ones[128 x 16] * Bt[N x 16]^T with the bias of column n split into two
+// bf16 terms (hi + mid + lo: all 24 mantissa bits) in row n of Bt and zeros elsewhere.  The per-column fp32 add (one FADD + half a
+// uniform load per element, a third of the epilogue's instructions) leaves the epilogue warps, which are the
+// bottleneck of these kernels; the tensor pipe pays 1/16 of an op for it.  Both operands are small un-swizzled K-major
+// tiles (8-row x 16-byte core matrices) that travel together in one 12 KB blob entry: [Bt k 0..7 | Bt k 8..15 | ones].
+// Because A is all ones the position of the three terms inside a row of Bt is irrelevant.
+constexpr uint32_t kBiasTileBytes = 12288, kBiasOnesOff = 8192;
+constexpr uint32_t kBiasB_LBO = 4096, kBiasB_SBO = 128, kBiasA_LBO = 2048, kBiasA_SBO = 128;
 enum { P_FWD = 0, P_FWDJ = 1, P_BWD = 2, P_JADJ = 3, kNumProgs = 4 };
 
 // One step = one ring slot = one weight tile of `nk16` K=16 MMAs.
@@ -196,6 +204,28 @@ struct Builder {
     }
     return off;
   }
+  // bias tile of parameter `param` (transposed == 2 marks it in the pack table)
+  constexpr uint32_t bias_tile(int param) {
+    for (int i = 0; i < n_keys; ++i)
+      if (key[i][0] == param && key[i][1] == 2) return key_off[i];
+    const uint32_t off = s.blob_bytes;
+    key[n_keys][0] = param, key[n_keys][1] = 2;
+    key_off[n_keys++] = off;
+    PackTile pt{};
+    pt.blob_off = off, pt.param = (int16_t)param, pt.transposed = 2, pt.rows = 256;
+    s.pack[s.n_pack++] = pt;
+    s.blob_bytes += kBiasTileBytes;
+    return off;
+  }
+  constexpr void bias_step(int P, int param, int n_mma) {
+    Prog& g = s.prog[P];
+    Step st{};
+    st.blob_off = bias_tile(param);
+    st.bytes = kBiasTileBytes;
+    st.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_mma >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    st.acc_col = 0, st.a_off16 = kBiasOnesOff >> 4, st.b_kb16 = 0, st.flags = F_ABIAS, st.nk16 = 1;
+    g.steps[g.n_steps++] = st;
+  }
   constexpr void step(int P, int param, int transposed, int r0, int c0, int vr, int vc, int rows, int nkb, int n_mma,
                       int acc_col, int a_kb, int nk16, uint32_t flags) {
     Prog& g = s.prog[P];
@@ -232,6 +262,7 @@ struct Builder {
         step(P, 5, 0, 0, 320, 256, 32, 256, 1, 256, 0, 1, 2, F_AENC | F_RELENC);
       }
     }
+    if (epi == E_RELU) bias_step(P, i, 256);  // forward programs: + bias on the tensor pipe
     op(P, s0, epi, 0, i * 256, i, save_plane, 8);
   }
   // a_{i-1} = relu'(h_{i-1}) * (a_i W_i) for i = 7..1 with the transposed tiles, then the two contributions to the
@@ -353,6 +384,7 @@ constexpr Sched make_sched() {
     b.op(P, s0, E_DEN, 0, kBiasHD, -1, -1, 0);
     s0 = b.s.prog[P].n_steps;
     for (int kb = 0; kb < 4; ++kb) b.step(P, W_EXTRA, 0, 0, kb * 64, 256, 64, 256, 1, 256, 0, kb, 4, kb == 0 ? F_FIRST : 0);
+    b.bias_step(P, W_EXTRA, 256);
     b.op(P, s0, E_EXTRA, 0, kBiasHE, -1, 8, 8);
     // view layer, bottleneck columns (the view-direction columns are the per-ray row bias)
     s0 = b.s.prog[P].n_steps;
@@ -424,6 +456,29 @@ __constant__ PackTable c_pack = make_pack_table();
 __global__ void pack_tiles_kernel(const PackArgs a, uint8_t* __restrict__ wblob, long long blob_stride) {
   PackTile t = c_pack.t[blockIdx.x];
   wblob += (size_t)blockIdx.y * blob_stride;
+  if (t.transposed == 2) {  // bias tile: [Bt chunk 0: (hi, lo, 0 x 6) per row | Bt chunk 1: zeros | ones]
+    const float* bsrc = a.b[t.param];
+    uint4* dst = reinterpret_cast<uint4*>(wblob + t.blob_off);
+    for (int i = threadIdx.x; i < (int)(kBiasTileBytes / 16); i += blockDim.x) {
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (i < 256) {  // row n = i: core matrix n / 8 at n / 8 * 128 bytes, row n % 8 inside it
+        // three bf16 terms carry all 24 mantissa bits of the fp32 bias (hi + mid + lo == bias exactly unless the
+        // last term underflows), so the pre-activations - and with them the ReLU pattern the Jacobian sweep
+        // depends on - equal those of an fp32 bias add to the last bit or so
+        const float bv = bsrc[i];
+        const __nv_bfloat16 hi = __float2bfloat16_rn(bv);
+        const float r1 = bv - __bfloat162float(hi);
+        const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+        v.x = (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(mid) << 16);
+        v.y = (uint32_t)__bfloat16_as_ushort(lo);
+      } else if (i >= (int)(kBiasOnesOff / 16)) {
+        v = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+      }
+      dst[i] = v;
+    }
+    return;
+  }
   if (t.param == 8) t.vr = (int16_t)(t.transposed ? t.vr : a.C);  // density head: C valid rows
   if (t.param == 11) t.vr = 3;                                   // colour head: 3 valid rows
   const float* W = a.w[t.param];
@@ -586,6 +641,12 @@ __device__ __forceinline__ void encode_row(const float* __restrict__ means, cons
   for (int k = 0; k < 12; ++k) o[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
 }
 
+// K-major, un-swizzled operand descriptor (8-row x 16-byte core matrices; LBO: K direction, SBO: M / N direction)
+__device__ __forceinline__ uint64_t desc_nosw16(uint32_t addr16, uint32_t lbo, uint32_t sbo) {
+  const uint32_t hi = (sbo >> 4) | (1u << 14);
+  return ((uint64_t)hi << 32) | (uint64_t)((addr16 & 0x3FFFu) | ((lbo >> 4) << 16));
+}
+
 struct EpiCtx {
   uint8_t* abuf;            // this tile's activation buffer
   uint32_t* mask;           // this tile's sign bit-planes [plane][unit][row] (nullptr: not kept)
@@ -619,7 +680,7 @@ __device__ __forceinline__ void rewrite_abuf_hf(const EpiCtx& c, const FusedPara
   constexpr bool kReadsAcc = MODE != M_SEED && MODE != M_BSEED;
   constexpr bool kAppliesMask = MODE == M_MASK || MODE == M_SEED || MODE == M_BSEED || MODE == M_BDZ7;
   constexpr bool kWritesMask = MODE == M_BIAS_RELU || MODE == M_ROWBIAS_RELU;
-  constexpr bool kAddsAux = MODE == M_BIAS_RELU || MODE == M_BIAS || MODE == M_ROWBIAS_RELU;
+  // (trunk / extra-layer biases arrive through the MMA: F_ABIAS; only the per-ray view term is added here)
   constexpr int n_mine = (MODE == M_ROWBIAS_RELU || MODE == M_BSEED) ? 2 : 4;  // units per warp (op.nunits / 2)
   constexpr int ub = HF * n_mine;
   // sign-bit words of this thread's units: bit (31 - j) of word u <-> column 32u + j is positive.
@@ -678,14 +739,6 @@ __device__ __forceinline__ void rewrite_abuf_hf(const EpiCtx& c, const FusedPara
       if (MODE == M_ROWBIAS_RELU) {  // + per-ray view-direction term (prefetched above)
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r[i & 1][j]) + rb[i][j];
-      } else if (kAddsAux) {         // + bias (per column)
-        const float4* cb = reinterpret_cast<const float4*>(c_bblob) + ((coff >> 2) + u * 8);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 t = cb[j];
-          x[4 * j] = __uint_as_float(r[i & 1][4 * j]) + t.x, x[4 * j + 1] = __uint_as_float(r[i & 1][4 * j + 1]) + t.y;
-          x[4 * j + 2] = __uint_as_float(r[i & 1][4 * j + 2]) + t.z, x[4 * j + 3] = __uint_as_float(r[i & 1][4 * j + 3]) + t.w;
-        }
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r[i & 1][j]);
@@ -721,9 +774,12 @@ __device__ __forceinline__ void rewrite_abuf_hf(const EpiCtx& c, const FusedPara
     uint32_t h[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-      __nv_bfloat162 t = __floats2bfloat162_rn(x[2 * k], x[2 * k + 1]);
-      if (MODE == M_BIAS_RELU || MODE == M_ROWBIAS_RELU) t = __hmax2(t, __floats2bfloat162_rn(0.f, 0.f));
-      h[k] = *reinterpret_cast<uint32_t*>(&t);
+      if (MODE == M_BIAS_RELU || MODE == M_ROWBIAS_RELU) {  // ReLU inside the conversion (F2FP.RELU)
+        asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(h[k]) : "f"(x[2 * k + 1]), "f"(x[2 * k]));
+      } else {
+        __nv_bfloat162 t = __floats2bfloat162_rn(x[2 * k], x[2 * k + 1]);
+        h[k] = *reinterpret_cast<uint32_t*>(&t);
+      }
     }
     const uint32_t dst = smem_u32(c.abuf) + (u >> 1) * kKbBytes + c.row * 128;
     const int jb = (u & 1) * 4;
@@ -810,6 +866,10 @@ __device__ __forceinline__ void mma_step(MmaCtx& c) {
                        st.a_off16;
   const uint32_t b16 = c.ring16 + (uint32_t)u.w_slot * (kSlotBytes >> 4);
   const uint32_t d_tmem = c.tmem_base + (uint32_t)T * 256u + st.acc_col;
+  if constexpr ((st.flags & F_ABIAS) != 0) {
+    umma_f16(d_tmem, desc_nosw16(b16 + st.a_off16, kBiasA_LBO, kBiasA_SBO), desc_nosw16(b16, kBiasB_LBO, kBiasB_SBO),
+             st.idesc, u.first != 0 ? 0u : 1u);
+  } else
 #pragma unroll
   for (int k = 0; k < (int)st.nk16; ++k) {
     const uint32_t ak = (uint32_t)((k >> 2) * (kKbBytes >> 4) + (k & 3) * 2);

@@ -512,13 +512,21 @@ def _group_sum(x, group):
 # ----------------------------------------------------------------------------------------------------------------
 # the autograd Function
 # ----------------------------------------------------------------------------------------------------------------
+def _use_fused(cfg, P) -> bool:
+    return (cfg["precision"] == "bf16" and fused_enabled() and fused_supported(cfg, P)
+            and not (cfg["with_normals"] and cfg.get("jac_precision") == "fp32"))
+
+
 class _Field(torch.autograd.Function):
     """(means, covs, venc, *params) -> (raw_rgb [M,3], raw_den [M,C], n_raw [M,3] | None)."""
 
     @staticmethod
     @_amp_fwd
-    def forward(ctx, means, covs, venc, cfg, *params):
+    def forward(ctx, means, covs, venc, cfg, anchor, *params):
         names = cfg["names"]
+        ctx.n_tape_params = len(params)
+        if cfg.get("direct_params") is not None:     # FlatAdam-managed parameters (see radiance_field)
+            params = tuple(cfg["direct_params"])
         P = dict(zip(names, params))
         be = make_backend(cfg["precision"], P)
         depth, skip = cfg["depth"], cfg["skip"]
@@ -530,8 +538,7 @@ class _Field(torch.autograd.Function):
         means2, covs2 = means.reshape(M, 3), covs.reshape(M, 3)
         f32 = torch.float32
 
-        fused = (be.name == "tc" and fused_enabled() and fused_supported(cfg, P)
-                 and not (cfg["with_normals"] and cfg.get("jac_precision") == "fp32"))
+        fused = be.name == "tc" and _use_fused(cfg, P)
         if fused:
             # (inside forward() grad mode is always off: radiance_field() records the caller's mode in cfg)
             need_bwd = cfg.get("grad_enabled", True) and any(ctx.needs_input_grad)
@@ -543,8 +550,14 @@ class _Field(torch.autograd.Function):
             _F32Backend(P).linear(venc, wv[:, width:], vb, bias=P["view_layers.0.0.bias"])
             pack = fused_pack(names, params)
             g_enc = torch.empty(M, xyz, device=dev, dtype=f32) if cfg["with_normals"] else None
+            # In-kernel IPE (encoder warps of the fused kernel, bit-identical to the two-kernel path) is OPT-IN: measured
+            # on B200 it is slower - 1.61 vs 1.14 ms per 1.2 M samples, 208 vs 184 ms per 1024x512 panorama - because
+            # the inference kernel is bound by its epilogue warps' issue slots and the 2 encoder warps (96 sin/cos/exp
+            # features per sample with the reference-exact argument reduction) take slots from them; with the
+            # hand-shakes alone (no arithmetic) the kernel is 5 % FASTER than with HBM-resident encodings
+            # (profiles/r02_in_kernel_ipe_experiment.md).
             in_kernel_ipe = (not need_bwd and xyz == 96 and 0 <= cfg["min_deg"] and cfg["max_deg"] <= 31
-                             and not os.environ.get("PNB_NO_FUSED_IPE"))
+                             and bool(os.environ.get("PNB_FUSED_IPE")))
             if in_kernel_ipe:
                 enc = acts = masks = None
                 raw_den, raw_rgb = fused_forward_ipe(means2, covs2, cfg["min_deg"], vb, vmod, S, C, pack, g_enc)
@@ -758,8 +771,12 @@ class _Field(torch.autograd.Function):
             d_means = ops.ipe_vjp(means, covs, cfg["min_deg"], cfg["max_deg"], d_enc).view(ctx.means_shape)
         ctx.bufs = None
         if direct:
-            return (d_means, None, None, None) + (None,) * len(names)
-        return (d_means, None, None, None) + tuple(G[n] for n in names)
+            return (d_means, None, None, None, None) + (None,) * ctx.n_tape_params
+        if ctx.n_tape_params == 0:                   # off-tape parameters lost their flat views mid-step: fold
+            for nme, p_ in zip(names, ctx.params):
+                p_.grad = G[nme] if p_.grad is None else p_.grad + G[nme]
+            return (d_means, None, None, None, None)
+        return (d_means, None, None, None, None) + tuple(G[n] for n in names)
 
     @staticmethod
     @_amp_bwd
@@ -891,7 +908,7 @@ class _Field(torch.autograd.Function):
         if need_enc:
             d_means = ops.ipe_vjp(means, covs, cfg["min_deg"], cfg["max_deg"], d_enc).view(ctx.means_shape)
         ctx.bufs = None
-        return (d_means, None, None, None) + tuple(G[n] for n in names)
+        return (d_means, None, None, None, None) + tuple(G[n] for n in names)
 
 
 def radiance_field(means, covs, venc, params: Dict[str, torch.Tensor], *, precision: str, samples_per_ray: int,
@@ -912,7 +929,21 @@ def radiance_field(means, covs, venc, params: Dict[str, torch.Tensor], *, precis
     if w0.shape[1] != 6 * (max_deg - min_deg):
         raise RuntimeError("IPE width does not match the first layer")
     R = means.shape[0]
-    raw_rgb, raw_den, n_raw = _Field.apply(means, covs, venc, cfg, *[params[n] for n in names])
+    plist = [params[n] for n in names]
+    anchor = None
+    if (cfg["grad_enabled"] and _use_fused(cfg, params)
+            and all(getattr(p, "_pnb_direct_grad", False) and p.grad is not None for p in plist)):
+        # FlatAdam-managed parameters: the fused backward accumulates straight into their .grad views, so autograd
+        # does not need edges to the 24 leaves at all.  They are handed over outside the tape and a fresh, empty
+        # `anchor` leaf keeps the Function differentiable.  Besides saving 24 no-op AccumulateGrad calls per level
+        # this keeps CUDA-graph capture independent of earlier eager steps: a parameter's cached AccumulateGrad node
+        # is pinned to the stream of the step that created it (e.g. the default stream) as long as any old loss
+        # tensor keeps that tape alive, and the engine would then sync the capture stream with it
+        # ("dependency created on uncaptured work in another stream").
+        cfg["direct_params"] = plist
+        anchor = torch.empty(0, device=means.device, dtype=torch.float32, requires_grad=True)
+        plist = []
+    raw_rgb, raw_den, n_raw = _Field.apply(means, covs, venc, cfg, anchor, *plist)
     raw_rgb = raw_rgb.view(R, samples_per_ray, -1)
     raw_den = raw_den.view(R, samples_per_ray, -1)
     if n_raw is not None:

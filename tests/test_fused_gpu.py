@@ -86,8 +86,16 @@ def test_pack_blob_is_the_swizzled_bf16_image_of_the_weights():
     assert torch.equal(tile(0, 256).float(), w0[:, :64].bfloat16().float())
     t1 = tile(256 * 128, 256).float()
     assert torch.equal(t1[:, :32], w0[:, 64:96].bfloat16().float()) and float(t1[:, 32:].abs().max()) == 0.0
+    # entry 2 of the blob: the bias of layer 0 as an un-swizzled [256 x 16] K-major tile (8-row core matrices of
+    # 16-byte rows) whose row n holds three bf16 terms that sum to the fp32 bias exactly, followed by zeros and a
+    # [128 x 16] tile of ones - the operands of the "bias" MMA step
+    off = 2 * 256 * 128
+    rows = blob[off:off + 4096].view(256, 16).view(torch.bfloat16).float()           # [256, 8]
+    assert torch.equal(rows[:, :3].double().sum(-1).float(), sd["layers.0.0.bias"]) and float(rows[:, 3:].abs().max()) == 0
+    assert float(blob[off + 4096:off + 8192].float().abs().max()) == 0.0
+    assert torch.equal(blob[off + 8192:off + 12288].view(torch.bfloat16).float(), torch.ones(2048))
     w1 = sd["layers.1.0.weight"]
-    assert torch.equal(tile(2 * 256 * 128 + 2 * 256 * 128, 256).float(), w1[:, 128:192].bfloat16().float())
+    assert torch.equal(tile(off + 12288 + 2 * 256 * 128, 256).float(), w1[:, 128:192].bfloat16().float())
     bb = pack["bblob"].cpu()
     assert torch.equal(bb[:256], sd["layers.0.0.bias"]) and torch.equal(bb[2048:2304], sd["extra_layer.bias"])
     assert torch.equal(bb[2304:2309], sd["density_layer.bias"]) and torch.equal(bb[2320:2323], sd["color_layer.bias"])
@@ -224,7 +232,8 @@ def test_head_grad_padding_and_group_sum():
 
 @pytest.mark.parametrize("S,R,with_normals", [(64, 16, False), (64, 16, True), (10, 13, False), (64, 700, True)])
 def test_in_kernel_ipe_is_bit_identical_to_the_two_kernel_path(S, R, with_normals):
-    """Inference forward: the encoder warps of the fused kernel evaluate the IPE in the kernel (no [M,96] array);
+    """Inference forward with PNB_FUSED_IPE=1 (opt-in, see field.py): the encoder warps of the fused kernel evaluate
+    the IPE in the kernel (no [M,96] array);
     the raw outputs and the density-gradient normals must equal those of pnb_ipe_fwd + pnb_mlp_fused_fwd bit for bit
     (same arithmetic, same bf16 rounding of the features).  Sizes cover a partial tile, an odd number of tiles (the
     phantom tile of the last pair) and several pairs per CTA-free grid."""
@@ -240,13 +249,13 @@ def test_in_kernel_ipe_is_bit_identical_to_the_two_kernel_path(S, R, with_normal
     else:
         sd, means, covs, venc = _inputs(S, R)
     outs = []
-    for no_ipe in (True, False):
-        if no_ipe:
-            os.environ["PNB_NO_FUSED_IPE"] = "1"
+    for in_kernel in (False, True):
+        if in_kernel:
+            os.environ["PNB_FUSED_IPE"] = "1"
         try:
             outs.append(_field(sd, means, covs, venc, S, True, with_normals))
         finally:
-            os.environ.pop("PNB_NO_FUSED_IPE", None)
+            os.environ.pop("PNB_FUSED_IPE", None)
     a, b = outs
     assert torch.equal(a["raw_rgb"], b["raw_rgb"]) and torch.equal(a["raw_den"], b["raw_den"])
     if with_normals:
