@@ -14,6 +14,8 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
          "-fmad=false", "-Xcompiler", "-fPIC"]
 if os.environ.get("PNB_PTXAS_V"):
     FLAGS += ["-Xptxas", "-v"]
+if os.environ.get("PNB_EXTRA_NVCC_FLAGS"):          # e.g. -DPNB_MBAR_WATCHDOG: stuck barriers trap instead of hanging
+    FLAGS += os.environ["PNB_EXTRA_NVCC_FLAGS"].split()
 
 
 def needs_build() -> bool:

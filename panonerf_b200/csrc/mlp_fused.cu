@@ -118,7 +118,8 @@ struct Use {
 };
 struct LoadRec {                 // the producer's program: loads in the order the MMA warp needs them
   uint32_t blob_off, bytes;
-  int8_t slot, is_enc, t, pad;
+  int8_t slot, is_enc, t, nkb;   // nkb: k-blocks stacked in the tile (0 for a bias tile)
+  int16_t rows, pad;             // rows of the weight tile (N of the op)
 };
 struct Prog {
   Step steps[kMaxSteps];
@@ -160,6 +161,22 @@ struct FusedParams {
   int ipe_min_deg, vb_mod;     // vb_mod != 0: per-ray row bias of ray (m / S) % vb_mod (env rays share D directions)
   unsigned long long* prof;  // timing experiments: [grid][8] cycle counters (nullable)
 };
+
+// CTA-pair mode (template parameter C2, cta_group::2): two CTAs of a cluster - the two SMs of a TPC - run the
+// schedule in lock-step; one thread of the LEADER (cluster rank 0) issues M = 256 MMAs that take each CTA's own 128-row
+// activation tile as its half of A and HALF of every weight tile (N / 2 rows) from each CTA's ring as B, and write
+// each CTA's accumulator into its own TMEM.  Per SM the weight traffic (L2 -> SMEM fills and the tensor cores' operand
+// reads) halves, which is what bounds the single-CTA kernel (12 KB of operands per 128-cycle MMA = 96 of the 128 B/clk
+// of shared-memory bandwidth, before the epilogue's stores and the ring fills).  Barrier topology: both producers'
+// TMA loads count their bytes on the LEADER's `full` barriers (cp.async.bulk.tensor ... cta_group::2), both CTAs'
+// epilogue warps arrive on the LEADER's `abuf_ready` (the peer through mapa / shared::cluster), and the leader's
+// tcgen05.commit multicasts its arrivals to `acc_full` / `empty` of BOTH CTAs.
+struct WMaps {                   // the weight blob as [bytes / 128][64] bf16, un-swizzled (tiles are pre-swizzled)
+  CUtensorMap m[5];              // box rows 128, 64, 48, 16, 8
+};
+__host__ __device__ constexpr int wmap_index(int box_rows) {
+  return box_rows == 128 ? 0 : box_rows == 64 ? 1 : box_rows == 48 ? 2 : box_rows == 16 ? 3 : box_rows == 8 ? 4 : -1;
+}
 
 struct FBarriers {
   uint64_t full[kSlots];
@@ -358,6 +375,12 @@ constexpr void plan_ring(Prog& g) {
         LoadRec& l = g.loads[g.n_loads++];
         l.slot = (int8_t)slot, l.is_enc = (int8_t)(n == 0), l.t = (int8_t)ev_t[e];
         l.blob_off = g.steps[ev_s[e]].blob_off, l.bytes = g.steps[ev_s[e]].bytes;
+        if ((g.steps[ev_s[e]].flags & F_ABIAS) != 0 || g.steps[ev_s[e]].b_kb16 == 0) {
+          l.rows = 0, l.nkb = 0;
+        } else {
+          l.rows = (int16_t)(g.steps[ev_s[e]].b_kb16 / 8);
+          l.nkb = (int8_t)(l.bytes / ((uint32_t)l.rows * 128u));
+        }
       }
       slot_of[n] = slot;
       last_ev[slot] = e, last_kind[slot] = n == 0 ? 1 : 0;
@@ -648,6 +671,7 @@ __device__ __forceinline__ uint64_t desc_nosw16(uint32_t addr16, uint32_t lbo, u
 }
 
 struct EpiCtx {
+  uint32_t ab_cluster;      // pair mode, peer CTA: shared::cluster address of the LEADER's abuf_ready of this tile (else 0)
   uint8_t* abuf;            // this tile's activation buffer
   uint32_t* mask;           // this tile's sign bit-planes [plane][unit][row] (nullptr: not kept)
   uint64_t* acc_full;
@@ -663,6 +687,12 @@ struct EpiCtx {
 };
 
 enum { M_BIAS_RELU = 0, M_BIAS, M_ROWBIAS_RELU, M_MASK, M_LIN, M_SEED, M_BSEED, M_BDZ7 };
+
+// "this warp is done with the tile's accumulator and activation buffer": the MMA issuer waits on the leader's barrier
+__device__ __forceinline__ void epi_arrive(const EpiCtx& c) {
+  if (c.ab_cluster != 0) mbar_arrive_cluster(c.ab_cluster);
+  else mbar_arrive(c.abuf_ready);
+}
 
 // Rewrite this warp's part of the tile's activation buffer (the next op's A operand) from the accumulator.
 // The two warps of a TMEM lane quadrant split the 32-column units: warp hf handles units [hf*n/2, (hf+1)*n/2), i.e.
@@ -708,7 +738,7 @@ __device__ __forceinline__ void rewrite_abuf_hf(const EpiCtx& c, const FusedPara
   if (c.skip) {  // timing experiment: the epilogue costs nothing
     tc_fence_before();
     __syncwarp();
-    if (c.lane == 0) mbar_arrive(c.abuf_ready);
+    if (c.lane == 0) epi_arrive(c);
     return;
   }
   uint32_t r[2][32];
@@ -810,7 +840,7 @@ __device__ __forceinline__ void rewrite_abuf_hf(const EpiCtx& c, const FusedPara
   }
   tc_fence_before();
   __syncwarp();
-  if (c.lane == 0) mbar_arrive(c.abuf_ready);
+  if (c.lane == 0) epi_arrive(c);
 }
 
 template <int MODE>
@@ -828,7 +858,7 @@ __device__ __forceinline__ void epi_wait(const EpiCtx& c) {
 __device__ __forceinline__ void epi_done(const EpiCtx& c) {
   tc_fence_before();
   __syncwarp();
-  if (c.lane == 0) mbar_arrive(c.abuf_ready);
+  if (c.lane == 0) epi_arrive(c);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -854,7 +884,18 @@ __device__ __forceinline__ void mma_wait_slot(MmaCtx& c) {
   c.full_ph ^= 1u << SLOT;
 }
 
-template <int P, int S, int T>
+template <bool C2>
+__device__ __forceinline__ void umma_any(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accum) {
+  if constexpr (C2) umma_f16_2cta(d, a, b, (idesc & ~(0x1Fu << 24)) | ((256u >> 4) << 24), accum);
+  else umma_f16(d, a, b, idesc, accum);
+}
+template <bool C2>
+__device__ __forceinline__ void commit_any(uint64_t* bar) {
+  if constexpr (C2) umma_commit_2cta(bar, (uint16_t)3);
+  else umma_commit(bar);
+}
+
+template <int P, int S, int T, bool C2>
 __device__ __forceinline__ void mma_step(MmaCtx& c) {
   constexpr Step st = kSched.prog[P].steps[S];
   constexpr Use u = kSched.prog[P].uses[T][S];
@@ -867,26 +908,29 @@ __device__ __forceinline__ void mma_step(MmaCtx& c) {
   const uint32_t b16 = c.ring16 + (uint32_t)u.w_slot * (kSlotBytes >> 4);
   const uint32_t d_tmem = c.tmem_base + (uint32_t)T * 256u + st.acc_col;
   if constexpr ((st.flags & F_ABIAS) != 0) {
-    umma_f16(d_tmem, desc_nosw16(b16 + st.a_off16, kBiasA_LBO, kBiasA_SBO), desc_nosw16(b16, kBiasB_LBO, kBiasB_SBO),
-             st.idesc, u.first != 0 ? 0u : 1u);
+    // pair mode: the slot holds this CTA's 128 rows of Bt ([k 0..7: 2 KB | k 8..15: 2 KB]) and the ones tile at 4 KB
+    constexpr uint32_t a_off = C2 ? (4096u >> 4) : st.a_off16;
+    constexpr uint32_t b_lbo = C2 ? 2048u : kBiasB_LBO;
+    umma_any<C2>(d_tmem, desc_nosw16(b16 + a_off, kBiasA_LBO, kBiasA_SBO), desc_nosw16(b16, b_lbo, kBiasB_SBO),
+                 st.idesc, u.first != 0 ? 0u : 1u);
   } else
 #pragma unroll
   for (int k = 0; k < (int)st.nk16; ++k) {
     const uint32_t ak = (uint32_t)((k >> 2) * (kKbBytes >> 4) + (k & 3) * 2);
-    const uint32_t bk = (uint32_t)(k >> 2) * st.b_kb16 + (uint32_t)(k & 3) * 2;
-    umma_f16(d_tmem, desc_from16(a16 + ak), desc_from16(b16 + bk), st.idesc, (k == 0 && u.first != 0) ? 0u : 1u);
+    const uint32_t bk = (uint32_t)(k >> 2) * (C2 ? st.b_kb16 >> 1 : st.b_kb16) + (uint32_t)(k & 3) * 2;
+    umma_any<C2>(d_tmem, desc_from16(a16 + ak), desc_from16(b16 + bk), st.idesc, (k == 0 && u.first != 0) ? 0u : 1u);
   }
-  if constexpr (u.w_rel != 0) umma_commit(&c.bars->empty[u.w_slot]);
-  if constexpr ((st.flags & F_AENC) != 0 && u.e_rel != 0) umma_commit(&c.bars->empty[u.e_slot]);
+  if constexpr (u.w_rel != 0) commit_any<C2>(&c.bars->empty[u.w_slot]);
+  if constexpr ((st.flags & F_AENC) != 0 && u.e_rel != 0) commit_any<C2>(&c.bars->empty[u.e_slot]);
 }
 
 // tile 0 walks the steps of an op forwards, tile 1 backwards (see plan_ring)
-template <int P, int S0, int N, int T, int... K>
+template <int P, int S0, int N, int T, bool C2, int... K>
 __device__ __forceinline__ void mma_steps(MmaCtx& c, std::integer_sequence<int, K...>) {
-  (mma_step<P, ((T == 0 || PNB_RING_MODE < 2) ? S0 + K : S0 + N - 1 - K), T>(c), ...);
+  (mma_step<P, ((T == 0 || PNB_RING_MODE < 2) ? S0 + K : S0 + N - 1 - K), T, C2>(c), ...);
 }
 
-template <int P, int OP, int T>
+template <int P, int OP, int T, bool C2>
 __device__ __forceinline__ void mma_op_tile(MmaCtx& c) {
   constexpr Op op = kSched.prog[P].ops[OP];
   // the tile's previous epilogue has drained the accumulator and rewritten the activation buffer
@@ -900,34 +944,37 @@ __device__ __forceinline__ void mma_op_tile(MmaCtx& c) {
   c.ab_ph ^= 1u << T;
   if constexpr (op.has_mma != 0) {
     tc_fence_after();
-    mma_steps<P, op.s0, op.s1 - op.s0, T>(c, std::make_integer_sequence<int, op.s1 - op.s0>{});
-    umma_commit(&c.bars->acc_full[T]);
+    mma_steps<P, op.s0, op.s1 - op.s0, T, C2>(c, std::make_integer_sequence<int, op.s1 - op.s0>{});
+    commit_any<C2>(&c.bars->acc_full[T]);
   } else {
     // Epilogue-only op: hand the tile back at once.  The epilogue still waits for this arrival, so it can never
     // complete two phases of abuf_ready ahead of this thread (a parity wait cannot tell phase n from phase n + 2).
     mbar_arrive(&c.bars->acc_full[T]);
+    if constexpr (C2) mbar_arrive_cluster(mapa_u32(smem_u32(&c.bars->acc_full[T]), 1u));  // ... in the peer CTA too
   }
 }
 
-template <int P, int OP>
+template <int P, int OP, bool C2>
 __device__ __forceinline__ void mma_op(MmaCtx& c) {
-  mma_op_tile<P, OP, 0>(c);
-  mma_op_tile<P, OP, 1>(c);
+  mma_op_tile<P, OP, 0, C2>(c);
+  mma_op_tile<P, OP, 1, C2>(c);
 }
 
-template <int P, int... OPS>
+template <int P, bool C2, int... OPS>
 __device__ __forceinline__ void mma_program(MmaCtx& c, std::integer_sequence<int, OPS...>) {
-  (mma_op<P, OPS>(c), ...);
+  (mma_op<P, OPS, C2>(c), ...);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------------
-template <int P>
+template <int P, bool C2>
 __global__ void __launch_bounds__(kFThreads, 1)
 mlp_fused_kernel(const __grid_constant__ CUtensorMap tmEnc, const __grid_constant__ CUtensorMap tmActs,
-                 const FusedParams p) {
+                 const __grid_constant__ WMaps wmaps, const FusedParams p) {
   constexpr int kOps = kSched.prog[P].n_ops;
+  const uint32_t rank = C2 ? cluster_ctarank() : 0u;   // pair mode: 0 = leader (issues the MMAs), 1 = peer
+  const long long pair_first = (long long)blockIdx.x - rank;  // both CTAs of a pair run the same number of rounds
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_1024(smem_raw);
   uint8_t* abuf = smem;                       // [2 tiles][4 k-blocks]
@@ -945,16 +992,20 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmEnc, const __grid_constan
       mbar_init(&bars->empty[s], 1);
     }
     for (int t = 0; t < 2; ++t) {
-      mbar_init(&bars->abuf_ready[t], 8);
+      mbar_init(&bars->abuf_ready[t], C2 ? 16 : 8);  // pair mode: the leader's barrier collects both CTAs' warps
       mbar_init(&bars->acc_full[t], 1);
       mbar_init(&bars->enc_ready[t], 2);
       mbar_init(&bars->enc_free[t], 1);
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(&bars->tmem_base, 512);
+  if (warp == 1) {
+    if constexpr (C2) tmem_alloc_2cta(&bars->tmem_base, 512);
+    else tmem_alloc(&bars->tmem_base, 512);
+  }
   tc_fence_before();
   __syncthreads();
+  if constexpr (C2) cluster_sync_all();  // the peer's barriers are initialised before anything signals them remotely
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
@@ -968,13 +1019,52 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmEnc, const __grid_constan
       const int n_loads = c_prog[P].n_loads;
       const bool ipe = p.means != nullptr;
       uint32_t it = 0;  // this CTA's pair counter: scratch buffer it & 1
-      for (long long pair = blockIdx.x; pair < p.num_pairs; pair += gridDim.x, ++it) {
+      for (long long pair0 = pair_first; pair0 < p.num_pairs; pair0 += gridDim.x, ++it) {
+        const long long pair = pair0 + rank;
         bool enc_waited = false;
         for (int l = 0; l < n_loads; ++l) {
           const LoadRec ld = c_prog[P].loads[l];
           const int slot = ld.slot;
           mbar_wait(&bars->empty[slot], ((eph >> slot) & 1u) ^ 1u);
           eph ^= 1u << slot;
+          if constexpr (C2) {
+            // Pair mode: every load is a 2-D TMA whose bytes are counted on the LEADER's `full` barrier; the leader
+            // arms it with the bytes of both CTAs (the peer's completions may arrive first: the transaction count
+            // may go negative inside a phase).
+            uint8_t* dst = ring + (size_t)slot * kSlotBytes;
+            const uint32_t bar = mapa_u32(smem_u32(&bars->full[slot]), 0u);
+            if (ld.is_enc) {
+              long long tile = pair * 2 + ld.t;
+              if (tile >= p.num_tiles) tile = p.num_tiles - 1;
+              int row0 = (int)(tile * kTileM);
+              if (ipe) {
+                if (!enc_waited) {
+                  mbar_wait(&bars->enc_ready[it & 1u], (it >> 1) & 1u);
+                  enc_waited = true;
+                }
+                row0 = (int)((((long long)blockIdx.x * 2 + (it & 1u)) * 2 + ld.t) * kTileM);
+              }
+              if (rank == 0) mbar_expect_tx(&bars->full[slot], 2 * 2 * kKbBytes);
+              tma_load_2d_2cta(dst, &tmEnc, bar, 0, row0, epol);
+              tma_load_2d_2cta(dst + kKbBytes, &tmEnc, bar, 64, row0, epol);
+            } else if (ld.nkb == 0) {  // bias tile: this CTA's 128 rows of Bt (two 2 KB halves of K) + the ones tile
+              const int r0 = (int)(ld.blob_off >> 7);
+              if (rank == 0) mbar_expect_tx(&bars->full[slot], 2 * 8192);
+              const CUtensorMap* m16 = &wmaps.m[wmap_index(16)];
+              tma_load_2d_2cta(dst, m16, bar, 0, r0 + (int)rank * 16, wpol);
+              tma_load_2d_2cta(dst + 2048, m16, bar, 0, r0 + 32 + (int)rank * 16, wpol);
+              tma_load_2d_2cta(dst + 4096, m16, bar, 0, r0 + 64, wpol);
+              tma_load_2d_2cta(dst + 6144, m16, bar, 0, r0 + 80, wpol);
+            } else {                   // this CTA's half (N / 2 rows) of every k-block of the weight tile
+              const int half = ld.rows >> 1;
+              const CUtensorMap* m = &wmaps.m[wmap_index(half)];
+              if (rank == 0) mbar_expect_tx(&bars->full[slot], ld.bytes);
+              for (int kb = 0; kb < ld.nkb; ++kb)
+                tma_load_2d_2cta(dst + (size_t)kb * half * 128, m, bar, 0,
+                                 (int)(ld.blob_off >> 7) + kb * ld.rows + (int)rank * half, wpol);
+            }
+            continue;
+          }
           if (ld.is_enc) {
             long long tile = pair * 2 + ld.t;
             if (tile >= p.num_tiles) tile = p.num_tiles - 1;  // phantom tile of an odd tail: recompute the last one
@@ -1009,15 +1099,19 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmEnc, const __grid_constan
       mc.bars = bars, mc.full_ph = 0, mc.ab_ph = 0;
       mc.abuf16 = smem_u32(abuf) >> 4, mc.ring16 = smem_u32(ring) >> 4, mc.tmem_base = tmem_base;
       mc.prof = p.prof != nullptr, mc.t_ab = 0, mc.t_full = 0;
-      const long long t_start = clock64();
+      const long long t_start = p.prof != nullptr ? clock64() : 0;
       uint32_t it = 0;
-      for (long long pair = blockIdx.x; pair < p.num_pairs; pair += gridDim.x, ++it) {
-        mma_program<P>(mc, std::make_integer_sequence<int, kOps>{});
+      if (rank == 0)  // (pair mode: the peer's MMA warp only allocates / frees its half of the tensor memory)
+      for (long long pair0 = pair_first; pair0 < p.num_pairs; pair0 += gridDim.x, ++it) {
+        mma_program<P, C2>(mc, std::make_integer_sequence<int, kOps>{});
         // every TMA load of this pair's encodings has landed (their `full` barriers were waited for above): the
         // encoder may overwrite scratch buffer it & 1 for the pair after next
-        if (p.means != nullptr) mbar_arrive(&bars->enc_free[it & 1u]);
+        if (p.means != nullptr) {
+          mbar_arrive(&bars->enc_free[it & 1u]);
+          if constexpr (C2) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->enc_free[it & 1u]), 1u));
+        }
       }
-      if (p.prof != nullptr) {
+      if (p.prof != nullptr && rank == 0) {
         p.prof[blockIdx.x * 8 + 0] = (unsigned long long)(clock64() - t_start);
         p.prof[blockIdx.x * 8 + 1] = (unsigned long long)mc.t_ab;
         p.prof[blockIdx.x * 8 + 2] = (unsigned long long)mc.t_full;
@@ -1029,7 +1123,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmEnc, const __grid_constan
     if ((P == P_FWD || P == P_FWDJ) && p.means != nullptr) {
       const int e = (warp - 2) * 32 + lane;  // 0..63: rows e, e + 64, e + 128, e + 192 of the pair's 256
       uint32_t it = 0;
-      for (long long pair = blockIdx.x; pair < p.num_pairs; pair += gridDim.x, ++it) {
+      for (long long pair0 = pair_first; pair0 < p.num_pairs; pair0 += gridDim.x, ++it) {
+        const long long pair = pair0 + rank;
         const uint32_t b = it & 1u;
         if (it >= 2) mbar_wait(&bars->enc_free[b], ((it >> 1) - 1u) & 1u);
         __nv_bfloat16* dst = p.enc_scratch + (((size_t)blockIdx.x * 2 + b) * 2 * kTileM) * kEncDim;
@@ -1056,9 +1151,14 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmEnc, const __grid_constan
     c.direct = p.save == 2, c.tma = p.save == 1;
     c.store_policy = l2_policy_evict_first();
     const uint32_t tlane = tmem_base + ((uint32_t)(c.q * 32) << 16);
+    // pair mode: every `abuf_ready` arrival of the peer CTA goes to the leader's barrier
+    const uint32_t ab_cluster0 = (C2 && rank != 0) ? mapa_u32(smem_u32(&bars->abuf_ready[0]), 0u) : 0u;
+    const uint32_t ab_cluster1 = (C2 && rank != 0) ? mapa_u32(smem_u32(&bars->abuf_ready[1]), 0u) : 0u;
     if (lane == 0) {           // both activation buffers / accumulators start out free
-      mbar_arrive(&bars->abuf_ready[0]);
-      mbar_arrive(&bars->abuf_ready[1]);
+      c.ab_cluster = ab_cluster0, c.abuf_ready = &bars->abuf_ready[0];
+      epi_arrive(c);
+      c.ab_cluster = ab_cluster1, c.abuf_ready = &bars->abuf_ready[1];
+      epi_arrive(c);
     }
     uint32_t acc_ph = 0;
     long long t_wait = 0;
@@ -1079,8 +1179,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmEnc, const __grid_constan
       return out;
     };
     uint4 nbits = fetch_bits(blockIdx.x, 0, 0);
-    const long long t_epi0 = clock64();
-    for (long long pair = blockIdx.x; pair < p.num_pairs; pair += gridDim.x) {
+    const long long t_epi0 = p.prof != nullptr ? clock64() : 0;
+    for (long long pair0 = pair_first; pair0 < p.num_pairs; pair0 += gridDim.x) {
+      const long long pair = pair0 + rank;
       for (int e = 0; e < kOps; ++e) {
         const Op op = c_prog[P].ops[e];
         for (int t = 0; t < 2; ++t) {
@@ -1094,6 +1195,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmEnc, const __grid_constan
           c.abuf = abuf + t * kAbufBytes;
           c.tacc = tlane + (uint32_t)t * 256u;
           c.acc_full = &bars->acc_full[t], c.abuf_ready = &bars->abuf_ready[t];
+          c.ab_cluster = t == 0 ? ab_cluster0 : ab_cluster1;
           c.acc_parity = (acc_ph >> t) & 1u;
           acc_ph ^= 1u << t;
           if (p.prof != nullptr) {  // (the real wait inside the epilogue then returns at once)
@@ -1213,9 +1315,11 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmEnc, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (C2) cluster_sync_all();  // neither CTA leaves (or frees tensor memory) while the pair's MMAs may still run
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if constexpr (C2) tmem_dealloc_2cta(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -1246,34 +1350,88 @@ static bool make_map_acts(CUtensorMap* out, const void* base, unsigned long long
 // copies are 4 KB-aligned plus an odd number of 256-byte lines apart, so that equal tile offsets land on different slices
 static long long blob_stride() { return ((long long)kSched.blob_bytes + 4095) / 4096 * 4096 + 256 * 37; }
 
-template <int P>
-static int launch(const CUtensorMap& tmEnc, const CUtensorMap& tmActs, FusedParams& p, cudaStream_t st,
-                  const char* what) {
+// The weight blob as a 2-D tensor of 128-byte rows for the pair-mode producer (TMA with cta_group::2); one map per box
+// height.  Encoding is host-only work (no driver call reaches the stream), cached per blob address.
+static bool make_wmaps(WMaps* out, const void* blob) {
+  static thread_local const void* cached_blob = nullptr;
+  static thread_local WMaps cached;
+  if (cached_blob == blob) {
+    *out = cached;
+    return true;
+  }
+  EncodeTiledFn enc = get_encode();
+  if (enc == nullptr) {
+    set_error_msg("cuTensorMapEncodeTiled not available from the driver");
+    return false;
+  }
+  static const unsigned box_rows[5] = {128, 64, 48, 16, 8};
+  const cuuint64_t rows = (cuuint64_t)kSched.blob_bytes / 128;
+  for (int i = 0; i < 5; ++i) {
+    cuuint64_t dims[2] = {64, rows};
+    cuuint64_t strides[1] = {128};
+    cuuint32_t box[2] = {64, box_rows[i]};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&out->m[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(blob), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error_msg("cuTensorMapEncodeTiled failed for the weight blob");
+      return false;
+    }
+  }
+  cached = *out, cached_blob = blob;
+  return true;
+}
+
+// PNB_FUSED_2CTA=1 selects the CTA-pair kernels, =0 the single-CTA ones.
+static bool pair_mode() {
+  static const int v = [] {
+    const char* e = getenv("PNB_FUSED_2CTA");
+    return e == nullptr ? 0 : atoi(e);
+  }();
+  return v != 0;
+}
+
+struct LaunchEnv {  // experiment switches, read once
+  int debug, save_direct, replicas, prof;
+  LaunchEnv() {
+    const char* e = getenv("PNB_FUSED_DEBUG");
+    debug = e ? atoi(e) : 0;
+    e = getenv("PNB_FUSED_SAVE");
+    save_direct = (e != nullptr && e[0] == 'd');
+    e = getenv("PNB_FUSED_REPLICAS");
+    replicas = e ? atoi(e) : kReplicas;
+    if (replicas < 1 || replicas > kReplicas) replicas = kReplicas;
+    prof = getenv("PNB_FUSED_PROF") != nullptr;
+  }
+};
+
+template <int P, bool C2>
+static int launch_impl(const CUtensorMap& tmEnc, const CUtensorMap& tmActs, FusedParams& p, cudaStream_t st,
+                       const char* what) {
+  static const LaunchEnv env;
   const size_t fixed = 1024 + 2 * kAbufBytes + sizeof(FBarriers);
-  const int ns = kSlots;
-  p.nstages = ns;
-  const size_t smem_bytes = fixed + (size_t)ns * kSlotBytes;
-  if (const char* dbg = getenv("PNB_FUSED_DEBUG")) p.debug = atoi(dbg);  // timing experiments only (wrong results)
+  p.nstages = kSlots;
+  const size_t smem_bytes = fixed + (size_t)kSlots * kSlotBytes;
+  p.debug = env.debug;  // timing experiments only (wrong results)
   if (p.save != 0) {
     // default: 16 KB TMA stores from the activation buffer.  "direct" (st.global from the epilogue registers) was
     // measured 25-35 % slower: 16-byte pieces at a 512-byte lane stride saturate the LSU store path.
-    const char* sm = getenv("PNB_FUSED_SAVE");
-    p.save = (sm != nullptr && sm[0] == 'd') ? 2 : 1;
+    p.save = env.save_direct ? 2 : 1;
   }
-  p.replicas = kReplicas, p.blob_stride = blob_stride();
-  if (const char* r = getenv("PNB_FUSED_REPLICAS")) {  // timing experiments only
-    p.replicas = atoi(r);
-    if (p.replicas < 1 || p.replicas > kReplicas) p.replicas = kReplicas;
-  }
-  const long long gx = p.num_pairs < kNumSMs ? p.num_pairs : kNumSMs;
+  p.replicas = C2 ? 1 : env.replicas, p.blob_stride = blob_stride();
+  long long gx = p.num_pairs < kNumSMs ? p.num_pairs : kNumSMs;
+  if (C2) gx = (gx + 1) / 2 * 2;  // whole pairs of CTAs (a pair without a second tile pair recomputes the last one)
+  WMaps wm{};
+  if (C2 && !make_wmaps(&wm, p.wblob)) return PNB_ERR_ARG;
   static unsigned long long* prof_buf = nullptr;
-  const bool prof = getenv("PNB_FUSED_PROF") != nullptr;
-  if (prof) {
+  if (env.prof) {
     if (prof_buf == nullptr) cudaMalloc(&prof_buf, sizeof(unsigned long long) * 8 * kNumSMs);
     cudaMemsetAsync(prof_buf, 0, sizeof(unsigned long long) * 8 * kNumSMs, st);
     p.prof = prof_buf;
   }
-  cudaError_t e = cudaFuncSetAttribute(mlp_fused_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  cudaError_t e = cudaFuncSetAttribute(mlp_fused_kernel<P, C2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem_bytes);
   if (e != cudaSuccess) {
     set_error("mlp_fused(smem attr)", e);
     return (int)e;
@@ -1285,18 +1443,36 @@ static int launch(const CUtensorMap& tmEnc, const CUtensorMap& tmActs, FusedPara
       return (int)e;
     }
   }
-  mlp_fused_kernel<P><<<(unsigned)gx, kFThreads, smem_bytes, st>>>(tmEnc, tmActs, p);
-  if (prof) {  // timing experiments only: per-CTA cycle counters, averaged
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)gx), cfg.blockDim = dim3(kFThreads), cfg.dynamicSmemBytes = smem_bytes, cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C2 ? 2 : 1, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr, cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, mlp_fused_kernel<P, C2>, tmEnc, tmActs, wm, p);
+  if (e != cudaSuccess) {
+    set_error(what, e);
+    return (int)e;
+  }
+  if (env.prof) {  // timing experiments only: per-CTA cycle counters, averaged over the CTAs that issue MMAs
     unsigned long long h[8 * kNumSMs];
     cudaStreamSynchronize(st);
     cudaMemcpy(h, prof_buf, sizeof(h), cudaMemcpyDeviceToHost);
     double a[5] = {0, 0, 0, 0, 0};
-    for (long long b = 0; b < gx; ++b)
-      for (int i = 0; i < 5; ++i) a[i] += (double)h[b * 8 + i] / (double)gx;
-    fprintf(stderr, "[%s] cycles/CTA: mma total %.0f (wait abuf %.0f, wait ring %.0f) | epilogue warp total %.0f (wait acc %.0f)\n",
-            what, a[0], a[1], a[2], a[3], a[4]);
+    const int stride = C2 ? 2 : 1;
+    for (long long b = 0; b < gx; b += stride)
+      for (int i = 0; i < 5; ++i) a[i] += (double)h[b * 8 + i] / (double)(gx / stride);
+    fprintf(stderr, "[%s%s] cycles/CTA: mma total %.0f (wait abuf %.0f, wait ring %.0f) | epilogue warp total %.0f (wait acc %.0f)\n",
+            what, C2 ? ", CTA pairs" : "", a[0], a[1], a[2], a[3], a[4]);
   }
   return finish(what);
+}
+
+template <int P>
+static int launch(const CUtensorMap& tmEnc, const CUtensorMap& tmActs, FusedParams& p, cudaStream_t st,
+                  const char* what) {
+  if (pair_mode()) return launch_impl<P, true>(tmEnc, tmActs, p, st, what);
+  return launch_impl<P, false>(tmEnc, tmActs, p, st, what);
 }
 
 }  // namespace fused
@@ -1313,7 +1489,7 @@ extern "C" int pnb_mlp_fused_adj_planes(void) { return kAdjPlanes; }
 
 extern "C" long long pnb_mlp_fused_mask_words(long long M, int per_tile) {
   const long long tiles = (M + kTileM - 1) / kTileM;
-  const long long slots = per_tile ? (tiles + 1) / 2 * 2 : 2ll * kNumSMs;
+  const long long slots = per_tile ? (tiles + 3) / 4 * 4 : 2ll * kNumSMs;  // (a CTA pair walks 4 tiles per round)
   return slots * kMaskWordsPerTile;
 }
 
