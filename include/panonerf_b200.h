@@ -225,7 +225,8 @@ long long pnb_mlp_fused_mask_words(long long M, int per_tile);
 int pnb_mlp_fused_plan(int prog, long long* out, int cap);
 int pnb_mlp_fused_pack(const void* const* params_host, int C, void* wblob, float* bblob, void* stream);
 /* enc: bf16 [M,96] IPE features (row stride ld_enc); row_bias: fp32 [ceil(M/S),128] per-ray view-direction term
- * (incl. the view-layer bias); outputs raw_den fp32 [M,C], raw_rgb fp32 [M,3].
+ * (incl. the view-layer bias) - or, with vb_mod = D > 0, fp32 [D,128] indexed by ray % D (env rays share their D
+ * directions, models/pano_mip_nerf.py:337-341); outputs raw_den fp32 [M,C], raw_rgb fp32 [M,3].
  * acts (nullable): bf16 [18][M][256] planes written with TMA stores for the backward pass:
  *   0..7 trunk activations h_i, 8 bottleneck, 9 view-layer activation (cols 0..127), 10..17 Jacobian rows a_0..a_7.
  * g_enc (nullable): fp32 [M,96]; when given, the density-Jacobian sweep (pano_mip_nerf.py:295-302 without
@@ -233,8 +234,8 @@ int pnb_mlp_fused_pack(const void* const* params_host, int C, void* wblob, float
  * masks: uint32 [pnb_mlp_fused_mask_words(M, masks_per_tile)] sign bits of the 9 ReLU layers; required with g_enc,
  * required per tile when the backward kernels will run, nullable otherwise. */
 int pnb_mlp_fused_fwd(long long M, int S, int C, const void* enc, int ld_enc, const void* wblob, const float* bblob,
-                      const float* row_bias, float* raw_den, float* raw_rgb, void* acts, float* g_enc, void* masks,
-                      int masks_per_tile, void* stream);
+                      const float* row_bias, int vb_mod, float* raw_den, float* raw_rgb, void* acts, float* g_enc,
+                      void* masks, int masks_per_tile, void* stream);
 /* Inference forward with the integrated positional encoding (models/mip.py:394-428) computed INSIDE the kernel:
  * two encoder warps per CTA evaluate the 96 features of the next tile pair from means / covs [M,3] (24 B per sample)
  * into `scratch` (pnb_mlp_fused_scratch_bytes(), per-CTA double buffer that stays in L2), the [M,96] encoding array

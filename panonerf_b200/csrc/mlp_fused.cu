@@ -1047,6 +1047,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmEnc, const __grid_constan
               if (rank == 0) mbar_expect_tx(&bars->full[slot], 2 * 2 * kKbBytes);
               tma_load_2d_2cta(dst, &tmEnc, bar, 0, row0, epol);
               tma_load_2d_2cta(dst + kKbBytes, &tmEnc, bar, 64, row0, epol);
+            } else if (p.debug & 1) {  // experiment: no weight traffic (the MMAs read whatever the slot holds)
+              if (rank == 0) mbar_arrive(&bars->full[slot]);
             } else if (ld.nkb == 0) {  // bias tile: this CTA's 128 rows of Bt (two 2 KB halves of K) + the ones tile
               const int r0 = (int)(ld.blob_off >> 7);
               if (rank == 0) mbar_expect_tx(&bars->full[slot], 2 * 8192);
@@ -1516,9 +1518,9 @@ extern "C" int pnb_mlp_fused_pack(const void* const* params_host, int C, void* w
 }
 
 extern "C" int pnb_mlp_fused_fwd(long long M, int S, int C, const void* enc, int ld_enc, const void* wblob,
-                                 const float* bblob, const float* row_bias, float* raw_den, float* raw_rgb,
+                                 const float* bblob, const float* row_bias, int vb_mod, float* raw_den, float* raw_rgb,
                                  void* acts, float* g_enc, void* masks, int masks_per_tile, void* stream) {
-  PNB_REQUIRE(M >= 0 && S >= 1 && C >= 1 && C <= 16, "mlp_fused_fwd: bad sizes");
+  PNB_REQUIRE(M >= 0 && S >= 1 && C >= 1 && C <= 16 && vb_mod >= 0, "mlp_fused_fwd: bad sizes");
   PNB_REQUIRE(enc && wblob && bblob && row_bias && raw_den && raw_rgb, "mlp_fused_fwd: null argument");
   PNB_REQUIRE(ld_enc % 8 == 0 && ld_enc >= kEncDim && ((uintptr_t)enc % 16 == 0) && ((uintptr_t)wblob % 16 == 0) &&
                   ((uintptr_t)bblob % 16 == 0) && ((uintptr_t)row_bias % 16 == 0),
@@ -1530,7 +1532,7 @@ extern "C" int pnb_mlp_fused_fwd(long long M, int S, int C, const void* enc, int
   if (M == 0) return 0;
   FusedParams p{};
   p.M = M, p.num_tiles = (M + kTileM - 1) / kTileM, p.num_pairs = (p.num_tiles + 1) / 2;
-  p.S = S, p.C = C, p.save = acts != nullptr;
+  p.S = S, p.C = C, p.save = acts != nullptr, p.vb_mod = vb_mod;
   p.wblob = reinterpret_cast<const uint8_t*>(wblob), p.bblob = bblob, p.row_bias = row_bias;
   p.raw_den = raw_den, p.raw_rgb = raw_rgb, p.g_enc = g_enc;
   p.masks = reinterpret_cast<uint32_t*>(masks), p.masks_per_tile = masks_per_tile;

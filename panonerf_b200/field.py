@@ -352,7 +352,7 @@ def fused_masks(M: int, dev, per_tile: bool) -> torch.Tensor:
     return _mask_scratch[key]
 
 
-def fused_forward(enc, vb, S, C, pack, acts, g_enc, masks=None, masks_per_tile=False):
+def fused_forward(enc, vb, S, C, pack, acts, g_enc, masks=None, masks_per_tile=False, vb_mod=0):
     """Launch the fused kernel on bf16 IPE features `enc` [M,96]; returns (raw_den, raw_rgb)."""
     M = enc.shape[0]
     dev = enc.device
@@ -366,7 +366,7 @@ def fused_forward(enc, vb, S, C, pack, acts, g_enc, masks=None, masks_per_tile=F
                   + (512 * (10 + (8 if g_enc is not None else 0)) if acts is not None else 0))
     with torch.cuda.device(dev), _prof("mlp_fused", nbytes, flops):
         check(_lib.lib().pnb_mlp_fused_fwd(M, S, C, _p(enc), _ld(enc), _p(pack["wblob"]), _p(pack["bblob"]), _p(vb),
-                                           _p(raw_den), _p(raw_rgb), _p(acts), _p(g_enc), _p(masks),
+                                           int(vb_mod), _p(raw_den), _p(raw_rgb), _p(acts), _p(g_enc), _p(masks),
                                            1 if masks_per_tile else 0, _stream()), "mlp_fused_fwd")
     return raw_den, raw_rgb
 
@@ -562,14 +562,12 @@ class _Field(torch.autograd.Function):
                 enc = acts = masks = None
                 raw_den, raw_rgb = fused_forward_ipe(means2, covs2, cfg["min_deg"], vb, vmod, S, C, pack, g_enc)
             else:
-                if vmod:                         # the stand-alone launcher indexes the row bias by ray
-                    vb = vb[None].expand(M // (S * vmod), vmod, vb.shape[1]).reshape(-1, vb.shape[1]).contiguous()
                 enc = torch.empty(M, xyz, device=dev, dtype=dt)
                 ops.ipe_into(means2, covs2, cfg["min_deg"], cfg["max_deg"], enc)
                 planes = int(_lib.lib().pnb_mlp_fused_act_planes())
                 acts = torch.empty(planes, M, width, device=dev, dtype=dt) if need_bwd else None
                 masks = fused_masks(M, dev, True) if need_bwd else None
-                raw_den, raw_rgb = fused_forward(enc, vb, S, C, pack, acts, g_enc, masks, need_bwd)
+                raw_den, raw_rgb = fused_forward(enc, vb, S, C, pack, acts, g_enc, masks, need_bwd, vb_mod=vmod)
             n_raw, jac = None, None
             if cfg["with_normals"]:
                 v = ops.ipe_vjp(means2, covs2, cfg["min_deg"], cfg["max_deg"], g_enc)

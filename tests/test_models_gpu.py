@@ -280,3 +280,47 @@ def test_cuda_graph_step_equals_eager_step():
     assert l0[0] == l1[0], (l0, l1)
     assert abs(l0[1] - l1[1]) <= 2e-5 * abs(l0[1]), (l0, l1)
     assert float((p0 - p1).norm() / p0.norm()) < 1e-5
+
+
+def test_graphed_steps_then_render_sees_current_weights():
+    """after CUDA-graph replays (which update the parameters behind torch's back) an eager render must use
+    the CURRENT weights, not a bf16 pack cached at the last capture: the render after 3 graphed steps is bit-identical
+    to the render of a fresh system loaded with the trained parameters; an eager forward between replays does not
+    freeze the pack either; `global_step` advances; a `surface_start_step` branch flip re-captures the graph."""
+    from panonerf_b200 import _lib
+    if not _lib.lib().pnb_tc_available():
+        pytest.skip("not an sm_100 device")
+    from panonerf_b200.systems.base_system import GraphedTrainStep, default_hparams
+    from panonerf_b200.systems.panonerf_system import PanoNeRFSystem
+    from panonerf_b200.datasets.pano_datasets import generate_rays, generate_lit_rays, pixel_radius
+    c2w = np.eye(4, dtype=np.float32)
+    c2w[:3, 3] = [0.1, 0.2, 0.3]
+    h, w = 16, 32
+    dev = torch.device(DEV, 0)
+    gt = (torch.rand(h * w, 3, generator=torch.Generator().manual_seed(0)) * 2).to(DEV)
+
+    def make(sd):
+        hp = default_hparams("panonerf", precision="bf16")
+        hp.update({"nerf.num_samples": 32, "train.randomized": False, "train.surface_start_step": 2,
+                   "optimizer.lr_delay_steps": 0, "optimizer.lr_init": 5e-3})
+        system = PanoNeRFSystem(hp).to(DEV)
+        system.mip_nerf.mlp.load_state_dict(sd)
+        system.env_rays = generate_lit_rays(pixel_radius(h, w, c2w, dev), num=10, device=dev)
+        return system
+
+    rays = generate_rays(h, w, c2w, 0.0, 10.0, dev)
+    batch = (type(rays)(*[x.view(1, h, w, -1) for x in rays]), torch.zeros(1, h, w, 3, device=DEV))
+    system = make(O.synth_state_dict(seed=4, width=256, c_density=5))
+    before = system.render_image(batch)[1].clone()
+    opt = system.configure_optimizers()
+    step = GraphedTrainStep(system, opt, rays, gt, warmup=0)        # construction runs step 1 (surface off)
+    mid = system.render_image(batch)[1].clone()                      # an eager forward between replays
+    step(rays, gt)                                                   # step 2 (surface still off)
+    step(rays, gt)                                                   # step 3: global_step == 2 -> surface on
+    assert step.captures == 2, "the surface_start_step flip must re-capture the graph"
+    assert system.global_step == 3
+    a = system.render_image(batch)[1].clone()
+    b = system.render_image(batch)[1].clone()
+    assert torch.equal(a, b) and not torch.equal(a, mid) and not torch.equal(mid, before)
+    twin = make({k: v.detach().clone() for k, v in system.mip_nerf.mlp.state_dict().items()})
+    assert torch.equal(twin.render_image(batch)[1], a), "the render used a stale weight pack"
