@@ -634,14 +634,17 @@ __device__ __forceinline__ void encode_row(const float* __restrict__ means, cons
       const float r = (float)(int)ph * 1.46291807926715968e-9f;
       const float sn = __sinf(r), cs = __cosf(r);
       const float y = __fmul_rn(mean[c], sc);
-      const float ex = __expf(__fmul_rn(-0.5f, __fmul_rn(cov[c], __fmul_rn(sc, sc))));
+      const float kl = -1.44269504088896341f * __uint_as_float((uint32_t)(127 + 2 * sh - 1) << 23);
+      float ex;
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(__fmul_rn(cov[c], kl)));
       const float z = __fadd_rn(y, kHalfPiF);
       const float bb = __fsub_rn(z, y);
       const float err = __fadd_rn(__fsub_rn(y, __fsub_rn(z, bb)), __fsub_rn(kHalfPiF, bb));
       const float eps = __fsub_rn(4.37113900018624283e-8f, err);
-      const float ce = fmaf(__fmul_rn(-0.5f, eps), eps, 1.0f);
-      const float se = __fmul_rn(eps, fmaf(__fmul_rn(-0.16666667f, eps), eps, 1.0f));
-      const float c2 = __fsub_rn(__fmul_rn(cs, ce), __fmul_rn(sn, se));
+      const float e2 = __fmul_rn(eps, eps);
+      const float ce = fmaf(-0.5f, e2, 1.0f);
+      const float se = __fmul_rn(eps, fmaf(-0.16666667f, e2, 1.0f));
+      const float c2 = fmaf(cs, ce, -__fmul_rn(sn, se));
       sn3[c] = __fmul_rn(ex, sn), cs3[c] = __fmul_rn(ex, c2);
     }
     // feature index l*3 + c (sin) and 48 + l*3 + c (cos); two degrees = 6 features = 3 packed words each

@@ -76,6 +76,9 @@ __device__ __forceinline__ float strat_t(int i, int N, float nr, float fr, const
 
 // One warp per ray: the per-ray constants are loaded once, the lanes walk the fence-posts, and there is no 64-bit
 // index division per sample (the flat-index version spent most of its instructions there).
+// STAGE: the Gaussians of a ray are staged in shared memory and leave as 16-byte rows (3 N floats per array, N % 4 == 0)
+// instead of 4-byte stores at a 12-byte lane stride, which hit every 32-byte sector from three instructions.
+template <bool STAGE>
 __global__ void __launch_bounds__(256)
 sample_cast_kernel(long long R, int N, const float* __restrict__ origins, int o_div,
                    const float* __restrict__ dirs, const float* __restrict__ radii,
@@ -83,7 +86,10 @@ sample_cast_kernel(long long R, int N, const float* __restrict__ origins, int o_
                    const float* __restrict__ s_lin, const float* __restrict__ t_rand, int rand_ld,
                    int disparity, float* __restrict__ t_out, float* __restrict__ means,
                    float* __restrict__ covs) {
+  extern __shared__ float sc_smem[];
   const int lane = threadIdx.x & 31;
+  float* sm = sc_smem + (size_t)(threadIdx.x >> 5) * 6 * N;  // [3N means | 3N covs] of this warp's ray
+  float* sv = sm + 3 * N;
   const long long warp0 = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
   for (long long r = warp0; r < R; r += (long long)gridDim.x * (blockDim.x >> 5)) {
     const long long rd = d_mod ? r % d_mod : r, ro = r / o_div;
@@ -92,13 +98,18 @@ sample_cast_kernel(long long R, int N, const float* __restrict__ origins, int o_
     const float d[3] = {dirs[3 * rd], dirs[3 * rd + 1], dirs[3 * rd + 2]};
     const float* rnd = t_rand ? t_rand + (long long)rand_ld * r : nullptr;
     float* trow = t_out + r * (N + 1);
-    for (int i = lane; i <= N; i += 32) {
+    const RayGeom geom = ray_geom(o, d, rad);
+    for (int i = lane; i < N; i += 32) {  // (the last fence-post rides with the last interval: no 1-lane extra round)
       const float t0 = strat_t(i, N, nr, fr, s_lin, rnd, disparity);
+      const float t1 = strat_t(i + 1, N, nr, fr, s_lin, rnd, disparity);
       trow[i] = t0;
-      if (i < N) {
-        const float t1 = strat_t(i + 1, N, nr, fr, s_lin, rnd, disparity);
-        float m[3], c[3];
-        frustum_gaussian(t0, t1, rad, o, d, m, c);
+      if (i == N - 1) trow[N] = t1;
+      float m[3], c[3];
+      frustum_gaussian(t0, t1, geom, m, c);
+      if (STAGE) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) sm[3 * i + k] = m[k], sv[3 * i + k] = c[k];
+      } else {
         const long long sidx = r * N + i;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -106,6 +117,17 @@ sample_cast_kernel(long long R, int N, const float* __restrict__ origins, int o_
           covs[3 * sidx + k] = c[k];
         }
       }
+    }
+    if (STAGE) {
+      __syncwarp();
+      float4* gm = reinterpret_cast<float4*>(means + 3 * r * N);
+      float4* gv = reinterpret_cast<float4*>(covs + 3 * r * N);
+      const int nv = (3 * N) >> 2;
+      for (int v = lane; v < nv; v += 32) {
+        gm[v] = reinterpret_cast<const float4*>(sm)[v];
+        gv[v] = reinterpret_cast<const float4*>(sv)[v];
+      }
+      __syncwarp();
     }
   }
 }
@@ -237,13 +259,19 @@ __global__ void ipe_fwd_kernel(long long M, int min_deg, int L, const float* __r
 //     the textbook formula;
 //   * features are staged in shared memory and leave as full 16-byte rows (coalesced), instead of 2-byte scatters.
 constexpr int kIpeTile = 64;  // samples per block iteration
-template <typename T, int L>
+template <typename T, int L, int MIN_DEG>  // MIN_DEG >= 0: compile-time lowest degree (every shift, scale and shared-memory
+                                            // offset of the fully unrolled loop is an immediate); -1: run-time `min_deg`
 __global__ void __launch_bounds__(3 * kIpeTile) ipe_fwd_tile_kernel(long long M, int min_deg,
                                                                      const float* __restrict__ means,
                                                                      const float* __restrict__ covs, T* __restrict__ enc,
                                                                      int ld) {
   constexpr int F = 6 * L;
-  __shared__ __align__(16) T tile[kIpeTile * F];
+  // Row pitch padded by 16 bytes: with the natural pitch (192 B / 384 B) the 32 threads of a warp - ~11 samples x 3
+  // components writing the same feature column - fall into 2 (bf16) or 1 (fp32) banks, a 6- to 11-way conflict on
+  // every one of the 96 stores per sample (ncu: 19.5 shared-memory wavefronts per sample for 3 warp-stores); the
+  // padded pitch spreads 8 consecutive samples over 8 banks.
+  constexpr int FP = F + 16 / (int)sizeof(T);
+  __shared__ __align__(16) T tile[kIpeTile * FP];
   const int tid = threadIdx.x;
   const int s = tid / 3, c = tid - 3 * s;
   for (long long base = (long long)blockIdx.x * kIpeTile; base < M; base += (long long)gridDim.x * kIpeTile) {
@@ -254,25 +282,31 @@ __global__ void __launch_bounds__(3 * kIpeTile) ipe_fwd_tile_kernel(long long M,
       u -= floor(u);
       const unsigned long long U = (unsigned long long)(u * 18446744073709551616.0);
       const uint32_t hi = (uint32_t)(U >> 32), lo = (uint32_t)U;
-#pragma unroll 4
+#pragma unroll
       for (int l = 0; l < L; ++l) {
-        const int sh = min_deg + l;
+        const int sh = (MIN_DEG >= 0 ? MIN_DEG : min_deg) + l;
         const uint32_t ph = __funnelshift_l(lo, hi, sh);  // top 32 bits of U << sh: phase in 2^-32 turns
         const float r = (float)(int)ph * 1.46291807926715968e-9f;  // 2 pi / 2^32 -> [-pi, pi)
         const float sn = __sinf(r), cs = __cosf(r);
         const float sc = __uint_as_float((uint32_t)(127 + sh) << 23);  // 2^sh
         const float y = mean * sc;
-        const float e = __expf(-0.5f * (cov * (sc * sc)));
-        // fl32(y + pi/2) = y + pi/2 + eps exactly
+        // exp(-0.5 * (cov * 4^sh)): both scalings are by powers of two, i.e. exact, so the reference's fp32 argument is
+        // x = -2^(2 sh - 1) cov exactly and exp(x) = 2^(fl32(x * log2 e)); folding the power of two into the constant
+        // gives the same single rounding with one multiply (MUFU.EX2; results below 2^-126 flush to zero)
+        const float kl = -1.44269504088896341f * __uint_as_float((uint32_t)(127 + 2 * sh - 1) << 23);
+        float e;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(cov * kl));
+        // fl32(y + pi/2) = y + pi/2 + eps exactly (TwoSum)
         const float z = y + kHalfPiF;
         const float bb = z - y;
         const float err = (y - (z - bb)) + (kHalfPiF - bb);
         const float eps = 4.37113900018624283e-8f - err;
-        const float ce = fmaf(-0.5f * eps, eps, 1.0f);
-        const float se = eps * fmaf(-0.16666667f * eps, eps, 1.0f);
-        const float c2 = cs * ce - sn * se;
-        tile[s * F + l * 3 + c] = from_f32<T>(e * sn);
-        tile[s * F + 3 * L + l * 3 + c] = from_f32<T>(e * c2);
+        const float e2 = eps * eps;
+        const float ce = fmaf(-0.5f, e2, 1.0f);
+        const float se = eps * fmaf(-0.16666667f, e2, 1.0f);
+        const float c2 = fmaf(cs, ce, -(sn * se));
+        tile[s * FP + l * 3 + c] = from_f32<T>(e * sn);
+        tile[s * FP + 3 * L + l * 3 + c] = from_f32<T>(e * c2);
       }
     }
     __syncthreads();
@@ -280,7 +314,7 @@ __global__ void __launch_bounds__(3 * kIpeTile) ipe_fwd_tile_kernel(long long M,
     const int rows = (M - base) < kIpeTile ? (int)(M - base) : kIpeTile;
     for (int v = tid; v < rows * kVecPerRow; v += 3 * kIpeTile) {
       const int row = v / kVecPerRow, j = v - row * kVecPerRow;
-      reinterpret_cast<uint4*>(enc + (base + row) * ld)[j] = reinterpret_cast<const uint4*>(tile + row * F)[j];
+      reinterpret_cast<uint4*>(enc + (base + row) * ld)[j] = reinterpret_cast<const uint4*>(tile + row * FP)[j];
     }
     __syncthreads();
   }
@@ -400,9 +434,17 @@ extern "C" int pnb_sample_cast(int R, int N, const float* origins, int o_div, co
                                float* means, float* covs, void* stream) {
   PNB_REQUIRE(R >= 0 && N > 0 && o_div >= 1 && d_mod >= 0, "sample_cast: bad sizes");
   if (R == 0) return 0;
-  sample_cast_kernel<<<grid_for((long long)R * 32, 256, 8), 256, 0, as_stream(stream)>>>(
-      R, N, origins, o_div, directions, radii, near_v, far_v, d_mod, s_lin, t_rand, rand_ld, disparity, t_out, means,
-      covs);
+  const size_t smem = (size_t)8 * 6 * N * sizeof(float);
+  const bool stage = N % 4 == 0 && smem <= 48 * 1024 && ((uintptr_t)means % 16 == 0) && ((uintptr_t)covs % 16 == 0);
+  const int grid = grid_for((long long)R * 32, 256, 8);
+  if (stage)
+    sample_cast_kernel<true><<<grid, 256, smem, as_stream(stream)>>>(R, N, origins, o_div, directions, radii, near_v,
+                                                                     far_v, d_mod, s_lin, t_rand, rand_ld, disparity,
+                                                                     t_out, means, covs);
+  else
+    sample_cast_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(R, N, origins, o_div, directions, radii, near_v,
+                                                                   far_v, d_mod, s_lin, t_rand, rand_ld, disparity,
+                                                                   t_out, means, covs);
   return finish("sample_cast");
 }
 
@@ -427,12 +469,21 @@ extern "C" int pnb_ipe_fwd(int M, const float* means, const float* covs, int min
     long long tiles = ((long long)M + pnb::kIpeTile - 1) / pnb::kIpeTile;
     long long cap = (long long)pnb::kNumSMs * 8;
     int g = (int)(tiles < cap ? tiles : cap);
-    if (dtype == PNB_BF16)
-      pnb::ipe_fwd_tile_kernel<__nv_bfloat16, 16><<<g, 3 * pnb::kIpeTile, 0, as_stream(stream)>>>(
-          M, min_deg, means, covs, (__nv_bfloat16*)enc, ld);
-    else
-      pnb::ipe_fwd_tile_kernel<float, 16><<<g, 3 * pnb::kIpeTile, 0, as_stream(stream)>>>(M, min_deg, means, covs,
-                                                                                         (float*)enc, ld);
+    cudaStream_t st = as_stream(stream);
+    if (dtype == PNB_BF16) {
+      if (min_deg == 0)
+        pnb::ipe_fwd_tile_kernel<__nv_bfloat16, 16, 0><<<g, 3 * pnb::kIpeTile, 0, st>>>(M, 0, means, covs,
+                                                                                       (__nv_bfloat16*)enc, ld);
+      else
+        pnb::ipe_fwd_tile_kernel<__nv_bfloat16, 16, -1><<<g, 3 * pnb::kIpeTile, 0, st>>>(M, min_deg, means, covs,
+                                                                                        (__nv_bfloat16*)enc, ld);
+    } else {
+      if (min_deg == 0)
+        pnb::ipe_fwd_tile_kernel<float, 16, 0><<<g, 3 * pnb::kIpeTile, 0, st>>>(M, 0, means, covs, (float*)enc, ld);
+      else
+        pnb::ipe_fwd_tile_kernel<float, 16, -1><<<g, 3 * pnb::kIpeTile, 0, st>>>(M, min_deg, means, covs,
+                                                                                (float*)enc, ld);
+    }
     return finish("ipe_fwd");
   }
   int grid = grid_for((long long)M * 3 * L, 256);

@@ -2,6 +2,8 @@
 // in registers with warp shuffles, per-ray samples are staged in shared memory, nothing per-sample round-trips
 // HBM.  HBM-bound: composite fwd moves 24 B/sample + 36 B/ray, bwd 40 B/sample + 32 B/ray, resample
 // 12 B/sample + 8 B/ray.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "geom.cuh"
 
@@ -104,6 +106,115 @@ composite_fwd_kernel(long long R, int N, const float* __restrict__ rgb, const fl
   }
 }
 
+// Blocked variant of the kernel above (the default for N <= 256): a ray is owned by L lanes that hold K CONSECUTIVE
+// samples each, so 32 / L rays share a warp (N = 64: two rays, the env rays' N = 10: eight), density / colour / weight
+// rows move as 128-bit accesses when rows are 16-byte aligned (VEC), the fp64 exclusive scan is K - 1 in-lane adds plus
+// log2(L) shuffle steps, and the five per-ray sums reduce over L lanes only.  Same formulas and fp32 / fp64 types as
+// above; the association of the sums differs (results agree to rounding, tests/test_kernels_gpu.py).
+template <int K, int L, bool VEC>
+__global__ void __launch_bounds__(256)
+composite_fwd_blocked_kernel(int R, int N, const float* __restrict__ rgb, const float* __restrict__ density,
+                             const float* __restrict__ t, const float* __restrict__ dirs, int d_mod, int white_bkgd,
+                             float* __restrict__ comp_rgb, float* __restrict__ distance, float* __restrict__ acc_out,
+                             float* __restrict__ weights) {
+  constexpr int kRaysPerWarp = 32 / L;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / L, l = lane % L;  // ray slot inside the warp, lane inside the ray
+  const int j0 = l * K;                    // first sample of this lane
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int r0 = (((int)blockIdx.x * (int)blockDim.x + (int)threadIdx.x) >> 5) * kRaysPerWarp; r0 < R;
+       r0 += warps * kRaysPerWarp) {
+    const int r = r0 + sub;
+    const bool ray_ok = r < R;
+    const int rr = ray_ok ? r : R - 1;  // (idle slots of the last warp recompute the last ray, stores are masked)
+    const int rd = d_mod ? rr % d_mod : rr;
+    const float d0 = dirs[3 * rd], d1 = dirs[3 * rd + 1], d2 = dirs[3 * rd + 2];
+    const float dnorm = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
+    const float* tr = t + (size_t)rr * (N + 1);
+    const size_t s0 = (size_t)rr * N + j0;
+    float tv[K + 1], den[K], col[3 * K];
+#pragma unroll
+    for (int k = 0; k <= K; ++k) tv[k] = (j0 + k <= N) ? tr[j0 + k] : 0.f;
+    if (VEC) {  // N % 4 == 0 and K % 4 == 0: whole 16-byte groups are either inside or outside the ray
+#pragma unroll
+      for (int k = 0; k < K; k += 4) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j0 + k < N) v = *reinterpret_cast<const float4*>(density + s0 + k);
+        den[k] = v.x, den[k + 1] = v.y, den[k + 2] = v.z, den[k + 3] = v.w;
+      }
+#pragma unroll
+      for (int k = 0; k < 3 * K; k += 4) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j0 + k / 3 < N) v = *reinterpret_cast<const float4*>(rgb + 3 * s0 + k);
+        col[k] = v.x, col[k + 1] = v.y, col[k + 2] = v.z, col[k + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const bool ok = j0 + k < N;
+        den[k] = ok ? density[s0 + k] : 0.f;
+        col[3 * k] = ok ? rgb[3 * (s0 + k)] : 0.f;
+        col[3 * k + 1] = ok ? rgb[3 * (s0 + k) + 1] : 0.f;
+        col[3 * k + 2] = ok ? rgb[3 * (s0 + k) + 2] : 0.f;
+      }
+    }
+    float sd[K];
+    double ex[K];
+    double run = 0.0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      sd[k] = (j0 + k < N) ? den[k] * ((tv[k + 1] - tv[k]) * dnorm) : 0.f;
+      ex[k] = run;
+      run += (double)sd[k];
+    }
+    double incl = run;  // inclusive scan of the lane totals over the L lanes of this ray
+#pragma unroll
+    for (int o = 1; o < L; o <<= 1) {
+      const double n = __shfl_up_sync(0xffffffffu, incl, o, L);
+      if (l >= o) incl += n;
+    }
+    const double base = incl - run;
+    float w[K];
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f, a = 0.f, sm = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      w[k] = (1.f - expf(-sd[k])) * expf(-(float)(base + ex[k]));
+      if (j0 + k < N) {
+        c0 += w[k] * col[3 * k], c1 += w[k] * col[3 * k + 1], c2 += w[k] * col[3 * k + 2];
+        a += w[k];
+        sm += w[k] * (0.5f * (tv[k] + tv[k + 1]));
+      }
+    }
+    if (ray_ok) {
+      if (VEC) {
+#pragma unroll
+        for (int k = 0; k < K; k += 4)
+          if (j0 + k < N) *reinterpret_cast<float4*>(weights + s0 + k) = make_float4(w[k], w[k + 1], w[k + 2], w[k + 3]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+          if (j0 + k < N) weights[s0 + k] = w[k];
+      }
+    }
+#pragma unroll
+    for (int o = L >> 1; o > 0; o >>= 1) {
+      c0 += __shfl_xor_sync(0xffffffffu, c0, o, L), c1 += __shfl_xor_sync(0xffffffffu, c1, o, L);
+      c2 += __shfl_xor_sync(0xffffffffu, c2, o, L), a += __shfl_xor_sync(0xffffffffu, a, o, L);
+      sm += __shfl_xor_sync(0xffffffffu, sm, o, L);
+    }
+    if (l == 0 && ray_ok) {
+      const float dist = fminf(fmaxf(nan_to_num_f(sm / a), tv[0]), tr[N]);
+      if (white_bkgd) {
+        const float bg = 1.f - a;
+        c0 += bg, c1 += bg, c2 += bg;
+      }
+      comp_rgb[3 * r] = c0, comp_rgb[3 * r + 1] = c1, comp_rgb[3 * r + 2] = c2;
+      distance[r] = dist;
+      acc_out[r] = a;
+    }
+  }
+}
+
 // Hand-derived backward of the block above.  With sd_i = sigma_i*delta_i, T_i = exp(-sum_{j<i} sd_j),
 // w_i = (1-exp(-sd_i)) T_i and G_i = dL/dw_i:   dL/dsd_i = G_i (T_i - w_i) - sum_{j>i} G_j w_j.
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
@@ -194,13 +305,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 resample_kernel(long long R, int N, const float* __restrict__ t, const float* __restrict__ weights, float padding,
                 int blur_pool, const float* __restrict__ u, int u_ld, float* __restrict__ new_t,
                 long long* __restrict__ inds_out, const float* __restrict__ origins, const float* __restrict__ dirs,
-                const float* __restrict__ radii, float* __restrict__ means, float* __restrict__ covs) {
-  extern __shared__ float smem[];
+                const float* __restrict__ radii, float* __restrict__ means, float* __restrict__ covs, int stage_cast) {
+  extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int stride = 3 * N + 4;
+  const int stride = 3 * N + 4 + (stage_cast ? 6 * N : 0);
   float* sa = smem + (size_t)wib * stride;  // raw weights, later the cdf (N+1 entries)
   float* sp = sa + N + 1;                   // blurred weights, then the pdf, then the new fence-posts (N+1)
   float* sb = sp + N + 1;                   // bins (t), N+1 entries
+  float* sg = sb + N + 2;                   // staged Gaussians [3N | 3N] (16-byte aligned: the stride is a multiple of 4)
   const int K = (N + 31) >> 5;              // samples per lane
   const int vec = N >> 3, ilp = vec >> 2;   // ATen: 8-float vectors, 4 interleaved accumulators
   const bool ragged = (N & 31) != 0;
@@ -290,45 +402,74 @@ resample_kernel(long long R, int N, const float* __restrict__ t, const float* __
       if (lane == 0) sa[N] = 1.f;
     }
     __syncwarp();
+    // searchsorted(cdf, u, right=True): lane owns Q consecutive outputs; u is sorted along a ray (linspace, or the
+    // stratified draw of mip.py:271-276), so after one binary search the index only moves forwards - a merge walk of
+    // a few steps instead of a binary search per output (an unsorted u falls back to the binary search)
     const float* ur = u + (long long)u_ld * r;
+    constexpr int Q = KMAX + 1;
+    {
+      int lo = 0;
+      float prev_u = 0.f;
 #pragma unroll
-    for (int k = 0; k < KMAX + 1; ++k) {
-      const int j = lane + 32 * k;
-      if (j > N || (k == KMAX && 32 * KMAX != N)) continue;
-      const float uj = ur[j];
-      int lo = 0, hi = N + 1;  // first index with cdf > u
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (sa[mid] <= uj) lo = mid + 1; else hi = mid;
+      for (int q = 0; q < Q; ++q) {
+        const int j = lane * Q + q;
+        if (j > N) break;
+        const float uj = ur[j];
+        if (q == 0 || uj < prev_u) {
+          int a = 0, b = N + 1;  // first index with cdf > u
+          while (a < b) {
+            const int mid = (a + b) >> 1;
+            if (sa[mid] <= uj) a = mid + 1; else b = mid;
+          }
+          lo = a;
+        } else {
+          while (lo <= N && sa[lo] <= uj) ++lo;
+        }
+        prev_u = uj;
+        const int below = lo - 1 > 0 ? lo - 1 : 0, above = lo < N ? lo : N;
+        const float c0 = sa[below], c1 = sa[above];
+        float den = c1 - c0;
+        if (den < 1e-5f) den = 1.f;
+        const float frac = (uj - c0) / den;
+        const float b0 = sb[below], b1 = sb[above];
+        const float nt = b0 + frac * (b1 - b0);
+        new_t[r * (N + 1) + j] = nt;
+        sp[j] = nt;
+        if (inds_out) inds_out[r * (N + 1) + j] = lo;
       }
-      const int below = lo - 1 > 0 ? lo - 1 : 0, above = lo < N ? lo : N;
-      const float c0 = sa[below], c1 = sa[above];
-      float den = c1 - c0;
-      if (den < 1e-5f) den = 1.f;
-      const float frac = (uj - c0) / den;
-      const float b0 = sb[below], b1 = sb[above];
-      const float nt = b0 + frac * (b1 - b0);
-      new_t[r * (N + 1) + j] = nt;
-      sp[j] = nt;
-      if (inds_out) inds_out[r * (N + 1) + j] = lo;
     }
     __syncwarp();
     if (means != nullptr) {  // cast_rays on the new fence-posts (models/mip.py:351, 67-89)
       const float o[3] = {origins[3 * r], origins[3 * r + 1], origins[3 * r + 2]};
       const float d[3] = {dirs[3 * r], dirs[3 * r + 1], dirs[3 * r + 2]};
-      const float rad = radii[r];
+      const RayGeom geom = ray_geom(o, d, radii[r]);
 #pragma unroll
       for (int k = 0; k < KMAX; ++k) {
         const int i = lane + 32 * k;
         if (i < N) {
           float m[3], c[3];
-          frustum_gaussian(sp[i], sp[i + 1], rad, o, d, m, c);
-          const long long sidx = r * N + i;
+          frustum_gaussian(sp[i], sp[i + 1], geom, m, c);
+          if (stage_cast) {  // 16-byte rows through shared memory (see sample_cast_kernel)
 #pragma unroll
-          for (int q = 0; q < 3; ++q) {
-            means[3 * sidx + q] = m[q];
-            covs[3 * sidx + q] = c[q];
+            for (int q = 0; q < 3; ++q) sg[3 * i + q] = m[q], sg[3 * N + 3 * i + q] = c[q];
+          } else {
+            const long long sidx = r * N + i;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+              means[3 * sidx + q] = m[q];
+              covs[3 * sidx + q] = c[q];
+            }
           }
+        }
+      }
+      if (stage_cast) {
+        __syncwarp();
+        float4* gm = reinterpret_cast<float4*>(means + 3 * r * N);
+        float4* gv = reinterpret_cast<float4*>(covs + 3 * r * N);
+        const int nv = (3 * N) >> 2;
+        for (int v = lane; v < nv; v += 32) {
+          gm[v] = reinterpret_cast<const float4*>(sg)[v];
+          gv[v] = reinterpret_cast<const float4*>(sg + 3 * N)[v];
         }
       }
     }
@@ -345,10 +486,33 @@ extern "C" int pnb_composite_fwd(int R, int N, const float* rgb, const float* de
                                  float* acc, float* weights, void* stream) {
   PNB_REQUIRE(R >= 0 && N > 0 && d_mod >= 0, "composite_fwd: bad sizes");
   if (R == 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  const bool vec = N % 4 == 0 && ((uintptr_t)rgb % 16 == 0) && ((uintptr_t)density % 16 == 0) &&
+                   ((uintptr_t)weights % 16 == 0);
+  static const bool legacy = getenv("PNB_COMPOSITE_LEGACY") != nullptr;  // A/B experiments
+#define PNB_LAUNCH_COMPOSITE(K, L)                                                                                   \
+  do {                                                                                                               \
+    const long long warps = ((long long)R + 32 / (L) - 1) / (32 / (L));                                              \
+    const int grid = grid_for(warps * 32, 256, 8);                                                                   \
+    if (vec)                                                                                                         \
+      composite_fwd_blocked_kernel<K, L, true><<<grid, 256, 0, st>>>(R, N, rgb, density, t, dirs, d_mod, white_bkgd, \
+                                                                     comp_rgb, distance, acc, weights);             \
+    else                                                                                                             \
+      composite_fwd_blocked_kernel<K, L, false><<<grid, 256, 0, st>>>(R, N, rgb, density, t, dirs, d_mod,            \
+                                                                      white_bkgd, comp_rgb, distance, acc, weights); \
+    return finish("composite_fwd");                                                                                  \
+  } while (0)
+  if (!legacy) {
+    if (N <= 16) PNB_LAUNCH_COMPOSITE(4, 4);
+    if (N <= 32) PNB_LAUNCH_COMPOSITE(4, 8);
+    if (N <= 64) PNB_LAUNCH_COMPOSITE(4, 16);
+    if (N <= 128) PNB_LAUNCH_COMPOSITE(4, 32);
+    if (N <= 256) PNB_LAUNCH_COMPOSITE(8, 32);
+  }
+#undef PNB_LAUNCH_COMPOSITE
   int grid = grid_for((long long)R * 32, kWarpsPerBlock * 32, 8);
-  composite_fwd_kernel<<<grid, kWarpsPerBlock * 32, 0, as_stream(stream)>>>(R, N, rgb, density, t, dirs, d_mod,
-                                                                           white_bkgd, comp_rgb, distance, acc,
-                                                                           weights);
+  composite_fwd_kernel<<<grid, kWarpsPerBlock * 32, 0, st>>>(R, N, rgb, density, t, dirs, d_mod, white_bkgd, comp_rgb,
+                                                             distance, acc, weights);
   return finish("composite_fwd");
 }
 
@@ -372,10 +536,13 @@ template <int KMAX>
 static int launch_resample(int R, int N, const float* t, const float* weights, float padding, int blur_pool,
                            const float* u, int u_ld, float* new_t, long long* inds, const float* origins,
                            const float* dirs, const float* radii, float* means, float* covs, cudaStream_t st) {
-  const size_t smem = (size_t)kWarpsPerBlock * (3 * N + 4) * sizeof(float);
+  const int stage = means != nullptr && N % 4 == 0 && ((uintptr_t)means % 16 == 0) && ((uintptr_t)covs % 16 == 0);
+  const size_t smem = (size_t)kWarpsPerBlock * (3 * N + 4 + (stage ? 6 * N : 0)) * sizeof(float);
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(resample_kernel<KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int grid = grid_for((long long)R * 32, kWarpsPerBlock * 32, 4);
   resample_kernel<KMAX><<<grid, kWarpsPerBlock * 32, smem, st>>>(R, N, t, weights, padding, blur_pool, u, u_ld, new_t,
-                                                                inds, origins, dirs, radii, means, covs);
+                                                                inds, origins, dirs, radii, means, covs, stage);
   return finish("resample");
 }
 

@@ -107,15 +107,46 @@ def test_ipe_and_posenc(golden_ops):
     from panonerf_b200 import ops
     out = torch.empty(4096, 96, device=DEV)
     ops.ipe_into(mean.to(DEV), cov.to(DEV), 0, 16, out)
-    # Strict pin, twice: against the CPU oracle (fp32 torch.sin / exp on this host) and against the float64 value of
-    # the reference's formula on the reference's own fp32 arguments (oracle.ipe_exact) - the number any correct fp32
-    # sin approximates, independent of the host's libm.  Round 1 tolerated "1-2 outliers of 1e-4 in about 1 of 5
-    # suite runs"; tools/ipe_repro.py (profiles/r02_ipe_outlier_hunt.md) could not reproduce one in 240 seeded cases
-    # on three boxes - CPU oracle, SFU fast path and double-precision path all stay within 4.7e-7 of float64.
+    # The parity pin is the float64 value of the reference's formula on the reference's own fp32 arguments
+    # (oracle.ipe_exact) - the number any correct fp32 sin / exp approximates, independent of the host's libm: strict,
+    # every element.  Round 1 tolerated "1-2 outliers of 1e-4 in about 1 of 5 suite runs"; round 2 root-caused them
+    # (profiles/r02_ipe_outlier_hunt.md): on some hosts the CPU's fp32 torch.sin / exp - i.e. the ORACLE - is off by
+    # ~1e-4 on one or two elements while the GPU kernel (both its SFU and its double-precision path) agrees with float64.
+    # So: GPU vs float64 strict everywhere; GPU vs CPU oracle strict wherever the CPU oracle itself is within 2e-6 of
+    # float64; elements where the HOST misbehaves are written to gpurun_out/ with full diagnostics and reported.
     exact = O.ipe_exact(mean, cov, 0, 16)
     assert float((out.cpu().double() - exact).abs().max()) < 2e-6, "GPU IPE vs float64 evaluation"
-    assert float((ref.detach().double() - exact).abs().max()) < 2e-6, "this host's fp32 torch.sin/exp vs float64 (CPU side)"
-    assert float((out.cpu() - ref.detach()).abs().max()) < 2e-6, "GPU IPE vs CPU oracle"
+    cpu_err = (ref.detach().double() - exact).abs()
+    host_bad = cpu_err >= 2e-6
+    if bool(host_bad.any()):
+        import json
+        import os
+        import subprocess
+        import warnings
+        idx = [int(i) for i in torch.nonzero(host_bad.flatten()).flatten()[:16]]
+        scales = torch.tensor([2.0 ** i for i in range(16)])
+        y = (mean[..., None, :] * scales[:, None]).flatten(-2)
+        arg = torch.cat([y, y + 0.5 * torch.tensor(np.pi)], -1).flatten()
+        yv = torch.cat([(cov[..., None, :] * scales[:, None] ** 2).flatten(-2)] * 2, -1).flatten()
+        again = O.ipe(mean, cov, 0, 16).flatten()
+        recs = [{"flat_index": i, "arg_fp32": float(arg[i]), "exp_arg_fp32": float(-0.5 * yv[i]),
+                 "cpu_oracle": float(ref.detach().flatten()[i]), "cpu_oracle_recomputed": float(again[i]),
+                 "float64": float(exact.flatten()[i]), "gpu": float(out.cpu().flatten()[i]),
+                 "sin_fp32_vectorised": float(torch.sin(arg)[i]), "sin_fp32_single": float(torch.sin(arg[i:i + 1])),
+                 "exp_fp32_vectorised": float(torch.exp(-0.5 * yv)[i]), "exp_fp32_single": float(torch.exp(-0.5 * yv[i:i + 1])),
+                 "sin_float64": float(torch.sin(arg[i].double())), "exp_float64": float(torch.exp(-0.5 * yv[i].double()))}
+                for i in idx]
+        info = {"n_host_outliers": int(host_bad.sum()), "max_cpu_err": float(cpu_err.max()), "records": recs,
+                "threads": torch.get_num_threads(), "cpu_capability": torch.backends.cpu.get_cpu_capability(),
+                "lscpu": subprocess.run("lscpu | grep -E 'Model name|Flags|^CPU\\(s\\)|Hypervisor'", shell=True,
+                                        capture_output=True, text=True).stdout[:3000]}
+        os.makedirs("gpurun_out", exist_ok=True)
+        with open(os.path.join("gpurun_out", f"ipe_cpu_oracle_outlier_{os.getpid()}.json"), "w") as fh:
+            json.dump(info, fh, indent=1)
+        warnings.warn("host fp32 sin/exp deviates from float64 (CPU oracle, not the GPU kernel): " + json.dumps(info)[:1500])
+        assert int(host_bad.sum()) <= 8, "the host's fp32 sin/exp is broadly wrong: " + json.dumps(info)[:1500]
+    gpu_vs_cpu = (out.cpu() - ref.detach()).abs()
+    assert float(gpu_vs_cpu[~host_bad].max()) < 2e-6, "GPU IPE vs CPU oracle"
     gvec = torch.randn(4096, 96, generator=gen)
     (gref,) = torch.autograd.grad((ref * gvec).sum(), mean_r)
     gout = ops.ipe_vjp(mean.to(DEV), cov.to(DEV), 0, 16, gvec.to(DEV))

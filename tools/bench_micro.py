@@ -57,6 +57,8 @@ def main():
         ("sample_cast", lambda: ops.sample_cast(origins, dirs, radii, near, far, N), R * (36 + 4 * (N + 1) + 24 * N), M),
         ("composite_fwd", lambda: ops.composite(rgb, den, t, dirs, False), M * 24 + R * 36, M),
         ("resample", lambda: ops.resample(t, w, 0.01), M * 12 + R * 8, M),
+        ("resample_cast (resample_along_rays in one launch)", lambda: ops.resample(t, w, 0.01, cast=(origins, dirs, radii)),
+         M * 36 + R * (8 + 28), M),
     ]
     with torch.no_grad():
         for name, fn, nbytes, units in cases:
