@@ -119,13 +119,15 @@ def unpack_rays(packed):
     return Rays(*out)
 
 
-def make_system(device, precision="bf16", seed=4):
+def make_system(device, precision="bf16", seed=4, num_samples=None):
     from oracle import panonerf_oracle as O            # deterministic weight factory (checksummed in the tests)
     from panonerf_b200.systems.base_system import default_hparams
     from panonerf_b200.systems.panonerf_system import PanoNeRFSystem
     from panonerf_b200.datasets.pano_datasets import generate_lit_rays, pixel_radius
     hp = default_hparams("panonerf", precision=precision)
     hp["train.randomized"] = True
+    if num_samples:
+        hp["nerf.num_samples"] = int(num_samples)
     system = PanoNeRFSystem(hp).to(device)
     system.mip_nerf.mlp.load_state_dict(O.synth_state_dict(seed=seed, width=256, c_density=5))
     radius = pixel_radius(GRID_HW[0], GRID_HW[1], camera(), device)
@@ -287,6 +289,7 @@ def run_ours(args):
 
 
 def measure_render(system, dev, world, rank, local, H, W, chunk, steps, warmup):
+    n_s = int(system.hparams["nerf.num_samples"])
     """configs[2]: full-panorama inference render (1024x512 equirect = 524 288 rays), PanoMipNeRF with normals +
     env irradiance + surface rendering (what the reference's render_image does), rows sharded over the ranks, no
     inter-GPU communication.  `e2e` additionally copies the rendered HDR images back to pinned host memory."""
@@ -341,13 +344,13 @@ def measure_render(system, dev, world, rank, local, H, W, chunk, steps, warmup):
     ms, launches, clocks, prof = timed(False, steps)
     ms_e2e, _, _, _ = timed(True, steps)
     rays_total = H * W * steps
-    flop_per_ray = (2 * N_SAMPLES + 100) * MLP_FLOP_PER_SAMPLE + N_SAMPLES * JAC_FLOP_PER_SAMPLE
+    flop_per_ray = (2 * n_s + 100) * MLP_FLOP_PER_SAMPLE + n_s * JAC_FLOP_PER_SAMPLE
     return {"metric": "render_rays_per_s", "value": rays_total / (ms / 1e3), "unit": "rays/s", "n_gpus": world,
             "steps": steps, "warmup": max(warmup, 1), "ms_per_step": ms / steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"full-panorama PanoMipNeRF render {W}x{H}, 64+64 samples, normals + 10x10 env "
+            "config": {"workload": f"full-panorama PanoMipNeRF render {W}x{H}, {n_s}+{n_s} samples, normals + 10x10 env "
                                    f"irradiance + surface rendering, rows sharded over ranks, no collective",
-                       "rays_per_forward": chunk or "all (one forward per panorama)", "parallelism": f"ray-shard{world}",
+                       "rays_per_forward": chunk or system.render_rays_per_launch(nrows * W), "parallelism": f"ray-shard{world}",
                        "l2": "per-chunk activations are several GB (>> 126 MB L2)"},
             "clocks": clocks,
             "e2e": {"value": rays_total / (ms_e2e / 1e3), "unit": "rays/s", "h2d_bytes_per_step": 48,
@@ -367,7 +370,7 @@ def run_render(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    system = make_system(dev)
+    system = make_system(dev, num_samples=args.num_samples)
     H, W = args.render_hw
     line = measure_render(system, dev, world, rank, local, H, W, args.render_chunk, args.steps, args.warmup)
     if rank == 0:
@@ -584,6 +587,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run the training step eagerly instead of as a CUDA graph")
     ap.add_argument("--workload", default="train", choices=["train", "render"])
+    ap.add_argument("--num-samples", type=int, default=0, help="render workload: samples per level (default: 64, the YAML value)")
     ap.add_argument("--preheat", type=float, default=2.0, help="seconds of untimed steps before the timed region")
     ap.add_argument("--no-extras", action="store_true", help="skip the C3 render and C4 65536-ray figures")
     ap.add_argument("--c4-steps", type=int, default=3)
