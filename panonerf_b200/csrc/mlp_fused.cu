@@ -686,7 +686,7 @@ struct EpiCtx {
   long long m;              // global sample row of this thread
   int q, hf, lane, row, tile_row0;
   uint64_t store_policy;    // L2 evict_first for the saved planes
-  bool row_ok, save, skip, direct, tma;  // save: this tile stores its planes; tma / direct: how the kernel stores
+  bool row_ok, save, skip, direct, tma, tmaw;  // save: this tile stores its planes; tma / tmaw / direct: how
 };
 
 enum { M_BIAS_RELU = 0, M_BIAS, M_ROWBIAS_RELU, M_MASK, M_LIN, M_SEED, M_BSEED, M_BDZ7 };
@@ -752,6 +752,11 @@ __device__ __forceinline__ void rewrite_abuf_hf(const EpiCtx& c, const FusedPara
     // tile's) must be done; only the other tile's newer group may stay pending.
     if (c.q == 0 && c.lane == 0) bulk_wait_read<1>();
     named_bar_sync(1 + HF, 128);
+  } else if (c.tmaw) {
+    // per-warp variant: every warp stores its own 32 rows (4 KB boxes) and waits only for its own earlier group -
+    // no rendezvous between the warps of a half
+    if (c.lane == 0) bulk_wait_read<1>();
+    __syncwarp();
   }
 #pragma unroll
   for (int i = 0; i < n_mine; ++i) {
@@ -837,6 +842,18 @@ __device__ __forceinline__ void rewrite_abuf_hf(const EpiCtx& c, const FusedPara
 #pragma unroll
         for (int kb = ub / 2; kb < (ub + n_mine) / 2; ++kb)
           tma_store_3d(c.tmActs, c.abuf + kb * kKbBytes, kb * 64, c.tile_row0, op.save_plane, c.store_policy);
+      }
+      bulk_commit();
+    }
+  }
+  if (c.tmaw) {
+    __syncwarp();
+    if (c.lane == 0) {
+      if (c.save && op.save_plane >= 0) {
+#pragma unroll
+        for (int kb = ub / 2; kb < (ub + n_mine) / 2; ++kb)
+          tma_store_3d(c.tmActs, c.abuf + kb * kKbBytes + c.q * 4096, kb * 64, c.tile_row0 + c.q * 32, op.save_plane,
+                       c.store_policy);
       }
       bulk_commit();
     }
@@ -1153,7 +1170,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmEnc, const __grid_constan
     c.q = warp & 3;            // TMEM lane quadrant (hardware rule: warp id % 4)
     c.hf = (warp - 4) >> 2;    // which of the two warps of the quadrant
     c.lane = lane, c.row = c.q * 32 + lane, c.save = p.save != 0, c.skip = (p.debug & 2) != 0;
-    c.direct = p.save == 2, c.tma = p.save == 1;
+    c.direct = p.save == 2, c.tma = p.save == 1, c.tmaw = p.save == 3;
     c.store_policy = l2_policy_evict_first();
     const uint32_t tlane = tmem_base + ((uint32_t)(c.q * 32) << 16);
     // pair mode: every `abuf_ready` arrival of the peer CTA goes to the leader's barrier
@@ -1332,6 +1349,16 @@ static bool make_map_enc(CUtensorMap* out, const void* base, unsigned long long 
   return make_map(out, base, rows, kEncDim, ld, 64, kTileM);
 }
 
+// PNB_FUSED_SAVE: unset / "t" = 16 KB TMA stores of whole 128-row k-blocks (4 warps rendezvous), "w" = per-warp 4 KB
+// stores (no rendezvous), "d" = st.global from the epilogue registers
+static int save_mode() {
+  static const int m = [] {
+    const char* e = getenv("PNB_FUSED_SAVE");
+    return e == nullptr ? 1 : e[0] == 'd' ? 2 : e[0] == 'w' ? 3 : 1;
+  }();
+  return m;
+}
+
 static bool make_map_acts(CUtensorMap* out, const void* base, unsigned long long planes, unsigned long long rows) {
   EncodeTiledFn enc = get_encode();
   if (enc == nullptr) {
@@ -1340,7 +1367,7 @@ static bool make_map_acts(CUtensorMap* out, const void* base, unsigned long long
   }
   cuuint64_t dims[3] = {(cuuint64_t)kWidth, rows, planes};
   cuuint64_t strides[2] = {(cuuint64_t)kWidth * 2, rows * (cuuint64_t)kWidth * 2};
-  cuuint32_t box[3] = {64, (cuuint32_t)kTileM, 1};
+  cuuint32_t box[3] = {64, (cuuint32_t)(save_mode() == 3 ? 32 : kTileM), 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -1422,7 +1449,7 @@ static int launch_impl(const CUtensorMap& tmEnc, const CUtensorMap& tmActs, Fuse
   if (p.save != 0) {
     // default: 16 KB TMA stores from the activation buffer.  "direct" (st.global from the epilogue registers) was
     // measured 25-35 % slower: 16-byte pieces at a 512-byte lane stride saturate the LSU store path.
-    p.save = env.save_direct ? 2 : 1;
+    p.save = save_mode();
   }
   p.replicas = C2 ? 1 : env.replicas, p.blob_stride = blob_stride();
   long long gx = p.num_pairs < kNumSMs ? p.num_pairs : kNumSMs;
