@@ -201,8 +201,14 @@ int pnb_wgrad_tc(long long M, int Nw, int Kw, const void* dZ, int ldz, const voi
  * map_base: HOST array of n_maps DEVICE pointers to bf16 tensors [planes][M][ld]; map_desc: HOST int64 [n_maps][3] =
  * {planes, ld, cols}.  jobs: HOST int64 [n_jobs][8] = {zmap, zplane, xmap, xplane, Nw, Kw, ldw, want_colsum};
  * dW / db: HOST arrays of n_jobs DEVICE pointers (db entries may be null).  Nw in {128,256}, 16 <= Kw <= 256, Kw%16==0.
- * workspace: pnb_wgrad_batch_workspace() bytes.  Partials are summed in a fixed order (deterministic). */
+ * workspace: pnb_wgrad_batch_workspace() bytes (one slot per segment, see pnb_wgrad_batch_plan).  Partials are summed in
+ * a fixed order (deterministic). */
 long long pnb_wgrad_batch_workspace(void);
+/* Host-only test hook: the work split of pnb_wgrad_batch for (M, jobs).  The (job, 64-sample block) units, in job-major
+ * order and weighted by their operand bytes, are cut into 148 pieces of equal bytes; a CTA's piece may straddle job
+ * boundaries ("segments").  out_segments: HOST int64 [max_segments][5] = {cta, job, first block, end block, slot};
+ * returns the number of segments (or -1). */
+int pnb_wgrad_batch_plan(long long M, int n_jobs, const long long* jobs, long long* out_segments, int max_segments);
 int pnb_wgrad_batch(long long M, int n_maps, const void* const* map_base, const long long* map_desc, int n_jobs,
                     const long long* jobs, const void* const* dW, const void* const* db, float* workspace,
                     void* stream);

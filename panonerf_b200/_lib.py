@@ -65,6 +65,8 @@ def lib():
                 "(there is no CPU fallback for the CUDA hot path)")
         handle = ctypes.CDLL(LIB_PATH)
         for name, (restype, argtypes) in PROTOTYPES.items():
+            if os.environ.get("PNB_LIB_PATH") and not hasattr(handle, name):
+                continue                        # A/B against an older build of the library (experiments only)
             fn = getattr(handle, name)          # AttributeError here == header/library mismatch: fail loudly
             fn.restype, fn.argtypes = restype, argtypes
         if handle.pnb_abi_version() != 1:
