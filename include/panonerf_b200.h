@@ -55,6 +55,11 @@ int pnb_raygen_equirect(int H, int W, int row0, int nrows, const float* c2w_host
 int pnb_sample_cast(int R, int N, const float* origins, int o_div, const float* directions, const float* radii,
                     const float* near_v, const float* far_v, int d_mod, const float* s_lin, const float* t_rand,
                     int rand_ld, int disparity, float* t_out, float* means, float* covs, void* stream);
+/* sample_each_points_hemisp, models/mip.py:197-237: as above with o_div = d_mod = D, but every ray brings its own
+ * direction, directions[R,3] (a hemisphere of D directions rotated onto each surface normal). */
+int pnb_sample_cast_hemisp(int R, int N, const float* origins, int o_div, const float* directions, const float* radii,
+                           const float* near_v, const float* far_v, int d_mod, const float* s_lin,
+                           const float* t_rand, int rand_ld, float* t_out, float* means, float* covs, void* stream);
 /* cast_rays on given fence-posts t[R,N+1] (after resampling): models/mip.py:67-89 */
 int pnb_cast_rays(int R, int N, const float* t, const float* origins, int o_div, const float* directions,
                   const float* radii, int d_mod, float* means, float* covs, void* stream);
@@ -87,7 +92,11 @@ int pnb_density_grad_bwd(int M, int C, const float* raw_den, float density_bias,
                          const float* d_n_raw, float* d_raw0, float* d_v, void* stream);
 
 /* ---- K6  alpha compositing: models/mip.py:444-483 ---------------------------------------------------------
- * density is [R,N] (channel 0 already selected); dirs[(d_mod ? r % d_mod : r)]. */
+ * density is [R,N] (channel 0 already selected); dirs[(d_mod ? r % d_mod : r)].
+ * white_bkgd is a flag word: bit 0 = white background (mip.py:477-478), bit 1 (PNB_COMPOSITE_ATTENUATE) = every
+ * sample's colour is attenuated by 1 / (1 + t_mid^2): `volumetric_lighting_composing`, models/mip.py:486-527. */
+#define PNB_COMPOSITE_WHITE_BKGD 1
+#define PNB_COMPOSITE_ATTENUATE 2
 int pnb_composite_fwd(int R, int N, const float* rgb, const float* density, const float* t, const float* dirs,
                       int d_mod, int white_bkgd, float* comp_rgb, float* distance, float* acc, float* weights,
                       void* stream);
@@ -286,6 +295,27 @@ long long pnb_exr_payload_bytes(int H, int W);
 int pnb_exr_pack(int H, int W, int C, const float* chw, void* out, void* stream);
 long long pnb_png_payload_bytes(int H, int W);
 int pnb_png_pack(int H, int W, int C, const float* chw, void* out, void* stream);
+
+/* ---- variants the upstream hot path does not call today ------------------------
+ * Specular BRDF terms per (ray, light direction): kind 0 = `microfeast_brdf` (utils/surface_rendering.py:6-61),
+ * kind 1 = `blinn_phong_brdf` (:64-101).  normal [R,3], roughness [R], v [R,3]; l is [D,3] (l_per_ray = 0) or
+ * [R,D,3] (l_per_ray = 1); outputs spec [R,D], nol [R,D] (clamped for kind 0, raw for kind 1, as upstream).
+ * Entries upstream turns into 0 with nan_to_num are 0 with zero gradient. */
+int pnb_brdf_terms_fwd(int kind, int R, int D, const float* normal, const float* roughness, const float* l,
+                       int l_per_ray, const float* v, float* spec, float* nol, void* stream);
+int pnb_brdf_terms_bwd(int kind, int R, int D, const float* normal, const float* roughness, const float* l,
+                       int l_per_ray, const float* v, const float* g_spec, const float* g_nol, float* d_normal,
+                       float* d_roughness, void* stream);
+/* the `roughness is not None` branch of `surface_rendering` (utils/surface_rendering.py:147-151,159):
+ * diffuse = sum_d (albedo/pi) env NoL omega, specular = sum_d spec env omega, rgb = diffuse + specular. */
+int pnb_shade_sum_fwd(int R, int D, const float* env_rgb, const float* albedo, const float* spec, const float* nol,
+                      const float* solid_angle, float* rgb, float* diffuse, float* specular, void* stream);
+int pnb_shade_sum_bwd(int R, int D, const float* env_rgb, const float* albedo, const float* spec, const float* nol,
+                      const float* solid_angle, const float* g_rgb, const float* g_diffuse, const float* g_specular,
+                      float* d_env, float* d_albedo, float* d_spec, float* d_nol, void* stream);
+/* `RotToTarget.rot2t` (utils/vector_rotation.py:57-89): rot[R,9] = rotation taking (0,1,0) onto tvec[r]. */
+int pnb_rot_to_target_fwd(int R, const float* tvec, float* rot, void* stream);
+int pnb_rot_to_target_bwd(int R, const float* tvec, const float* g_rot, float* d_tvec, void* stream);
 
 #ifdef __cplusplus
 }

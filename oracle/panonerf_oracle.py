@@ -329,6 +329,99 @@ def lambert_shade(env_rgb, albedo, normal, light_dirs, solid_angle):
     return diffuse + torch.zeros_like(diffuse), diffuse, shading
 
 
+# ---- variants the upstream hot path does not call today ---------------------------
+def _unit_dots(normal, l, v):
+    """Half vector and the clamped cosines shared by the two specular BRDFs (utils/surface_rendering.py:28-44)."""
+    d = l.shape[1]
+    vv = v[:, None, :].expand(-1, d, -1)
+    nn = normal[:, None, :].expand(-1, d, -1)
+    h = F.normalize(l + vv, dim=-1)
+    dot = lambda a, b: (a * b).sum(-1, keepdim=True)
+    return dot(nn, h), dot(vv, h), dot(nn, l), dot(nn, vv)
+
+
+def microfacet_terms(albedo, normal, roughness, l, v, masked: bool = False):
+    """utils/surface_rendering.py:6-61 (`microfeast_brdf`, UE4 GGX / Schlick / Smith for image-based lighting).
+    Returns (diffuse_brdf [B,D,3], specular_brdf [B,D,1], NoL [B,D,1]).  `masked=True` evaluates the same specular
+    term with the 0/0 entries masked BEFORE the division: identical forward values, but a finite gradient (upstream's
+    `nan_to_num` after the division back-propagates NaN into every ray that has a light below its horizon)."""
+    d = l.shape[1]
+    noh, voh, nol, nov = [torch.relu(x) for x in _unit_dots(normal, l, v)]
+    r = roughness[:, None, :].expand(-1, d, -1)
+    alpha = r ** 2
+    k = r ** 2 / 2
+    dist = alpha ** 2 / (np.pi * ((noh ** 2) * (alpha ** 2 - 1) + 1) ** 2)
+    fres = 0.04 + (1 - 0.04) * 2 ** (-(5.55473 * voh + 6.98316) * voh)
+    geom = nol / ((1 - k) * nol + k) * (nov / ((1 - k) * nov + k))
+    den = 4 * nol * nov
+    if masked:
+        ok = den > 0
+        spec = torch.where(ok, dist * fres * geom / torch.where(ok, den, torch.ones_like(den)), torch.zeros_like(den))
+    else:
+        spec = (dist * fres * geom / den).nan_to_num(nan=0, posinf=0)
+    return (albedo / np.pi)[:, None, :].expand(-1, d, -1), spec, nol
+
+
+def blinn_phong_terms(albedo, normal, roughness, l, v):
+    """utils/surface_rendering.py:64-101 (`blinn_phong_brdf`): specular = relu(n.h) ** roughness, NoL NOT clamped."""
+    d = l.shape[1]
+    noh, _, nol, _ = _unit_dots(normal, l, v)
+    spec = torch.pow(torch.relu(noh), roughness[:, None, :].expand(-1, d, -1)).nan_to_num(nan=0, posinf=0)
+    return (albedo / np.pi)[:, None, :].expand(-1, d, -1), spec, nol
+
+
+def rough_shade(env_rgb, albedo, normal, roughness, l, v, solid_angle, masked: bool = False):
+    """utils/surface_rendering.py:147-151,159 (the `roughness is not None` branch of `surface_rendering`)."""
+    dif_b, spec_b, nol = microfacet_terms(albedo, normal, roughness, l, v, masked)
+    diffuse = torch.sum(dif_b * env_rgb * nol * solid_angle, dim=1)
+    specular = torch.sum(spec_b * env_rgb * solid_angle, dim=1)
+    return diffuse + specular, diffuse, specular
+
+
+def rot_to_target(tvec):
+    """utils/vector_rotation.py:57-89 (`RotToTarget.rot2t`): Rodrigues rotation taking (0,1,0) onto each row of
+    tvec [B,3] -> [B,3,3]; the antipodal case (theta == pi) is the fixed reflection diag(1,-1,1)."""
+    up = torch.tensor([0.0, 1.0, 0.0], dtype=tvec.dtype)
+    theta = torch.acos((tvec * up).sum(-1)).view(-1, 1, 1)
+    axis = F.normalize(torch.cross(up[None].expand_as(tvec), tvec, dim=-1), dim=-1)
+    z = torch.zeros_like(axis[:, 0])
+    skew = torch.stack([z, -axis[:, 2], axis[:, 1], axis[:, 2], z, -axis[:, 0], -axis[:, 1], axis[:, 0], z], -1)
+    skew = skew.view(-1, 3, 3)
+    rm = torch.eye(3, dtype=tvec.dtype)[None] + torch.sin(theta) * skew + torch.bmm(skew, skew) * (1 - torch.cos(theta))
+    flip = (theta.view(-1) == np.pi)
+    return torch.where(flip[:, None, None], torch.diag(torch.tensor([1.0, -1.0, 1.0], dtype=tvec.dtype))[None], rm)
+
+
+def env_samples_hemisp(points, dirs, env: Rays, n_env: int, randomized: bool, t_rand=None):
+    """models/mip.py:197-237 (`sample_each_points_hemisp`, num_points == 1): like env_samples, but every surface
+    point brings its own D directions, dirs [B,D,3]."""
+    b, d = dirs.shape[0], dirs.shape[1]
+    o = points[:, None, :].expand(b, d, 3).reshape(-1, 3)
+    rep = lambda x: x[None].expand(b, *x.shape).reshape(-1, x.shape[-1])
+    radii, near, far = rep(env.radii), rep(env.near), rep(env.far)
+    t = near + (far - near) * torch.linspace(0.0, 1.0, n_env + 1)
+    if randomized:
+        mids = 0.5 * (t[..., 1:] + t[..., :-1])
+        upper = torch.cat([mids, t[..., -1:]], -1)
+        lower = torch.cat([t[..., :1], mids], -1)
+        if t_rand is None:
+            t_rand = torch.rand(1, n_env + 1)
+        t = lower + (upper - lower) * t_rand
+    flat = dirs.reshape(-1, 3)
+    return t, cast_cone(t, o, flat, radii), flat
+
+
+def composite_lighting(rgb, density, t, dirs, white_bkgd: bool):
+    """models/mip.py:486-527 (`volumetric_lighting_composing`): alpha compositing with the colour of every sample
+    attenuated by 1 / (1 + t_mid^2); weights, acc and distance are those of `composite`."""
+    _, dist, acc, w = composite(rgb, density, t, dirs, False)
+    t_mid = 0.5 * (t[..., :-1] + t[..., 1:])
+    comp = (w[..., None] * (1 / (1 + t_mid ** 2))[..., None] * rgb).sum(-2)
+    if white_bkgd:
+        comp = comp + (1.0 - acc[..., None])
+    return comp, dist, acc, w
+
+
 def hdr_to_ldr(c, gamma=2.2, quantize=False, clamp=True):
     """utils/surface_rendering.py:319-344 (ACES + gamma; `quantize` == dtype='uint8')."""
     c = (c * (2.51 * c + 0.03)) / (c * (2.43 * c + 0.59) + 0.14)

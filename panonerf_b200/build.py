@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpanonerf_b200.so")
-SOURCES = ["api.cu", "rays.cu", "render.cu", "shade.cu", "gemm_simt.cu", "gemm_tc.cu", "wgrad_batch.cu", "mlp_fused.cu", "image.cu"]
+SOURCES = ["api.cu", "rays.cu", "render.cu", "shade.cu", "gemm_simt.cu", "gemm_tc.cu", "wgrad_batch.cu", "mlp_fused.cu", "image.cu", "variants.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          # un-fused fp32 arithmetic so element-wise kernels round like the reference's PyTorch ops; the GEMM inner

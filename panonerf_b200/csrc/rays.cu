@@ -82,7 +82,7 @@ template <bool STAGE>
 __global__ void __launch_bounds__(256)
 sample_cast_kernel(long long R, int N, const float* __restrict__ origins, int o_div,
                    const float* __restrict__ dirs, const float* __restrict__ radii,
-                   const float* __restrict__ near_v, const float* __restrict__ far_v, int d_mod,
+                   const float* __restrict__ near_v, const float* __restrict__ far_v, int d_mod, int dir_mod,
                    const float* __restrict__ s_lin, const float* __restrict__ t_rand, int rand_ld,
                    int disparity, float* __restrict__ t_out, float* __restrict__ means,
                    float* __restrict__ covs) {
@@ -93,9 +93,10 @@ sample_cast_kernel(long long R, int N, const float* __restrict__ origins, int o_
   const long long warp0 = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
   for (long long r = warp0; r < R; r += (long long)gridDim.x * (blockDim.x >> 5)) {
     const long long rd = d_mod ? r % d_mod : r, ro = r / o_div;
+    const long long rdir = dir_mod ? r % dir_mod : r;  // (sample_each_points_hemisp: one direction per ray)
     const float nr = near_v[rd], fr = far_v[rd], rad = radii[rd];
     const float o[3] = {origins[3 * ro], origins[3 * ro + 1], origins[3 * ro + 2]};
-    const float d[3] = {dirs[3 * rd], dirs[3 * rd + 1], dirs[3 * rd + 2]};
+    const float d[3] = {dirs[3 * rdir], dirs[3 * rdir + 1], dirs[3 * rdir + 2]};
     const float* rnd = t_rand ? t_rand + (long long)rand_ld * r : nullptr;
     float* trow = t_out + r * (N + 1);
     const RayGeom geom = ray_geom(o, d, rad);
@@ -428,10 +429,10 @@ extern "C" int pnb_raygen_equirect(int H, int W, int row0, int nrows, const floa
   return finish("raygen_equirect");
 }
 
-extern "C" int pnb_sample_cast(int R, int N, const float* origins, int o_div, const float* directions,
-                               const float* radii, const float* near_v, const float* far_v, int d_mod,
-                               const float* s_lin, const float* t_rand, int rand_ld, int disparity, float* t_out,
-                               float* means, float* covs, void* stream) {
+static int launch_sample_cast(int R, int N, const float* origins, int o_div, const float* directions,
+                              const float* radii, const float* near_v, const float* far_v, int d_mod, int dir_mod,
+                              const float* s_lin, const float* t_rand, int rand_ld, int disparity, float* t_out,
+                              float* means, float* covs, void* stream) {
   PNB_REQUIRE(R >= 0 && N > 0 && o_div >= 1 && d_mod >= 0, "sample_cast: bad sizes");
   if (R == 0) return 0;
   const size_t smem = (size_t)8 * 6 * N * sizeof(float);
@@ -439,13 +440,29 @@ extern "C" int pnb_sample_cast(int R, int N, const float* origins, int o_div, co
   const int grid = grid_for((long long)R * 32, 256, 8);
   if (stage)
     sample_cast_kernel<true><<<grid, 256, smem, as_stream(stream)>>>(R, N, origins, o_div, directions, radii, near_v,
-                                                                     far_v, d_mod, s_lin, t_rand, rand_ld, disparity,
-                                                                     t_out, means, covs);
+                                                                     far_v, d_mod, dir_mod, s_lin, t_rand, rand_ld,
+                                                                     disparity, t_out, means, covs);
   else
     sample_cast_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(R, N, origins, o_div, directions, radii, near_v,
-                                                                   far_v, d_mod, s_lin, t_rand, rand_ld, disparity,
-                                                                   t_out, means, covs);
+                                                                   far_v, d_mod, dir_mod, s_lin, t_rand, rand_ld,
+                                                                   disparity, t_out, means, covs);
   return finish("sample_cast");
+}
+
+extern "C" int pnb_sample_cast(int R, int N, const float* origins, int o_div, const float* directions,
+                               const float* radii, const float* near_v, const float* far_v, int d_mod,
+                               const float* s_lin, const float* t_rand, int rand_ld, int disparity, float* t_out,
+                               float* means, float* covs, void* stream) {
+  return launch_sample_cast(R, N, origins, o_div, directions, radii, near_v, far_v, d_mod, d_mod, s_lin, t_rand,
+                            rand_ld, disparity, t_out, means, covs, stream);
+}
+
+extern "C" int pnb_sample_cast_hemisp(int R, int N, const float* origins, int o_div, const float* directions,
+                                      const float* radii, const float* near_v, const float* far_v, int d_mod,
+                                      const float* s_lin, const float* t_rand, int rand_ld, float* t_out, float* means,
+                                      float* covs, void* stream) {
+  return launch_sample_cast(R, N, origins, o_div, directions, radii, near_v, far_v, d_mod, 0, s_lin, t_rand, rand_ld, 0,
+                            t_out, means, covs, stream);
 }
 
 extern "C" int pnb_cast_rays(int R, int N, const float* t, const float* origins, int o_div, const float* directions,

@@ -11,6 +11,9 @@ namespace pnb {
 
 constexpr int kWarpsPerBlock = 8;
 
+// models/mip.py:510 (`volumetric_lighting_composing`): attenuation = 1 / (1 + t_mid^2)
+__device__ __forceinline__ float atten_of(float t_mid) { return 1.f / (1.f + t_mid * t_mid); }
+
 __device__ __forceinline__ float nan_to_num_f(float x) {
   if (isnan(x)) return 0.f;
   if (isinf(x)) return x > 0.f ? 3.402823466e+38f : -3.402823466e+38f;
@@ -24,6 +27,8 @@ composite_fwd_kernel(long long R, int N, const float* __restrict__ rgb, const fl
                      float* __restrict__ comp_rgb, float* __restrict__ distance, float* __restrict__ acc_out,
                      float* __restrict__ weights) {
   const int lane = threadIdx.x & 31;
+  const bool atten = (white_bkgd & PNB_COMPOSITE_ATTENUATE) != 0;
+  white_bkgd &= PNB_COMPOSITE_WHITE_BKGD;
   const long long warp0 = blockIdx.x * (long long)kWarpsPerBlock + (threadIdx.x >> 5);
   for (long long r = warp0; r < R; r += (long long)gridDim.x * kWarpsPerBlock) {
     long long rd = d_mod ? r % d_mod : r;
@@ -61,13 +66,15 @@ composite_fwd_kernel(long long R, int N, const float* __restrict__ rgb, const fl
       const float w1 = (1.f - expf(-sd1)) * expf(-(float)excl1);
       if (ok0) {
         weights[r * N + i0] = w0;
-        c0 += w0 * ca[0], c1 += w0 * ca[1], c2 += w0 * ca[2];
+        const float wa = atten ? w0 * atten_of(0.5f * (t00 + t01)) : w0;
+        c0 += wa * ca[0], c1 += wa * ca[1], c2 += wa * ca[2];
         a += w0;
         s += w0 * (0.5f * (t00 + t01));
       }
       if (ok1) {
         weights[r * N + i1] = w1;
-        c0 += w1 * cb[0], c1 += w1 * cb[1], c2 += w1 * cb[2];
+        const float wa = atten ? w1 * atten_of(0.5f * (t10 + t11)) : w1;
+        c0 += wa * cb[0], c1 += wa * cb[1], c2 += wa * cb[2];
         a += w1;
         s += w1 * (0.5f * (t10 + t11));
       }
@@ -85,9 +92,10 @@ composite_fwd_kernel(long long R, int N, const float* __restrict__ rgb, const fl
       if (ok) {
         weights[r * N + i] = w;
         const float* c = rgb + 3 * (r * N + i);
-        c0 += w * c[0];
-        c1 += w * c[1];
-        c2 += w * c[2];
+        const float wa = atten ? w * atten_of(0.5f * (t0 + t1)) : w;
+        c0 += wa * c[0];
+        c1 += wa * c[1];
+        c2 += wa * c[2];
         a += w;
         s += w * (0.5f * (t0 + t1));
       }
@@ -118,6 +126,8 @@ composite_fwd_blocked_kernel(int R, int N, const float* __restrict__ rgb, const 
                              float* __restrict__ comp_rgb, float* __restrict__ distance, float* __restrict__ acc_out,
                              float* __restrict__ weights) {
   constexpr int kRaysPerWarp = 32 / L;
+  const bool atten = (white_bkgd & PNB_COMPOSITE_ATTENUATE) != 0;
+  white_bkgd &= PNB_COMPOSITE_WHITE_BKGD;
   const int lane = threadIdx.x & 31;
   const int sub = lane / L, l = lane % L;  // ray slot inside the warp, lane inside the ray
   const int j0 = l * K;                    // first sample of this lane
@@ -180,7 +190,8 @@ composite_fwd_blocked_kernel(int R, int N, const float* __restrict__ rgb, const 
     for (int k = 0; k < K; ++k) {
       w[k] = (1.f - expf(-sd[k])) * expf(-(float)(base + ex[k]));
       if (j0 + k < N) {
-        c0 += w[k] * col[3 * k], c1 += w[k] * col[3 * k + 1], c2 += w[k] * col[3 * k + 2];
+        const float wa = atten ? w[k] * atten_of(0.5f * (tv[k] + tv[k + 1])) : w[k];
+        c0 += wa * col[3 * k], c1 += wa * col[3 * k + 1], c2 += wa * col[3 * k + 2];
         a += w[k];
         sm += w[k] * (0.5f * (tv[k] + tv[k + 1]));
       }
@@ -224,6 +235,8 @@ composite_bwd_kernel(long long R, int N, const float* __restrict__ rgb, const fl
                      const float* __restrict__ g_acc, const float* __restrict__ g_w, float* __restrict__ d_rgb,
                      float* __restrict__ d_density) {
   extern __shared__ float smem[];
+  const bool atten = (white_bkgd & PNB_COMPOSITE_ATTENUATE) != 0;
+  white_bkgd &= PNB_COMPOSITE_WHITE_BKGD;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   float* sT = smem + (size_t)wib * 3 * N;  // transmittance
   float* sW = sT + N;                      // weights
@@ -266,13 +279,15 @@ composite_bwd_kernel(long long R, int N, const float* __restrict__ rgb, const fl
     for (int i = lane; i < N; i += 32) {
       const float* c = rgb + 3 * (r * N + i);
       float tm = 0.5f * (tr[i] + tr[i + 1]);
-      float G = gc0 * c[0] + gc1 * c[1] + gc2 * c[2] + ga + (g_w ? g_w[r * N + i] : 0.f);
+      const float att = atten ? atten_of(tm) : 1.f;
+      float G = (gc0 * c[0] + gc1 * c[1] + gc2 * c[2]) * att + ga + (g_w ? g_w[r * N + i] : 0.f);
       if (gd != 0.f) G += gd * (tm - draw);  // `draw` is NaN on an empty ray; the reference would propagate it
       float w = sW[i];
       sQ[i] = G * w;
       sT[i] = G * (sT[i] - w);  // re-use: G_i (T_i - w_i)
       float* o = d_rgb + 3 * (r * N + i);
-      o[0] = w * gc0, o[1] = w * gc1, o[2] = w * gc2;
+      const float wa = w * att;
+      o[0] = wa * gc0, o[1] = wa * gc1, o[2] = wa * gc2;
     }
     __syncwarp();
     // suffix-exclusive sum of Q, walking the chunks from the far end of the ray

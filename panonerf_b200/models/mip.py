@@ -106,6 +106,34 @@ def volumetric_rendering(rgb, density, t_samples, dirs, white_bkgd, output_t=Fal
     return comp, dist, acc, w
 
 
+def volumetric_lighting_composing(rgb, density, t_samples, dirs, white_bkgd, output_t=False):
+    """models/mip.py:486-527: volumetric_rendering with every sample's colour attenuated by 1 / (1 + t_mid^2)
+    (the commented-out `enable_dist_att` branch of pano_mip_nerf.py:340-343)."""
+    f = ops._f32c
+    den = density[..., 0].contiguous() if density.dim() == 3 else density
+    comp, dist, acc, w = ops.composite(rgb.contiguous(), den, f(t_samples), f(dirs), white_bkgd, attenuate=True)
+    if output_t:
+        return comp, dist, acc, w, 0.5 * (t_samples[..., :-1] + t_samples[..., 1:])
+    return comp, dist, acc, w
+
+
+def sample_each_points_hemisp(point_origins, directions, num_samples, near, far, radii, randomized, t_rand=None):
+    """models/mip.py:197-237 with num_points == 1: `directions` is [batch, num_lit_rays, 3], one hemisphere of light
+    directions per surface point (e.g. `RotToTarget.rot2t(normal) @ dirs`)."""
+    b, npts, _ = point_origins.shape
+    if npts != 1:
+        raise NotImplementedError("num_points must be 1")
+    f = ops._f32c
+    if randomized and t_rand is None:
+        t_rand = torch.rand(1, num_samples + 1, device=point_origins.device)
+    dirs = f(directions)
+    pts = point_origins.reshape(b, 3)
+    pts = pts if pts.requires_grad else f(pts)
+    t, means, covs = ops.env_cast_hemisp(pts.contiguous(), dirs, f(radii), f(near), f(far), num_samples,
+                                         t_rand if randomized else None)
+    return t, (means, covs), dirs.reshape(-1, 3)
+
+
 def sample_each_points(point_origins, directions, num_samples, near, far, radii, randomized, t_rand=None):
     """models/mip.py:154-194 with num_points == 1 (the only shape the model passes, pano_mip_nerf.py:327)."""
     b, npts, _ = point_origins.shape

@@ -293,9 +293,10 @@ class _Composite(torch.autograd.Function):
         return d_rgb, d_den, None, None, None, None
 
 
-def composite(rgb, density, t, dirs, white_bkgd, d_mod=0):
-    """rgb [R,N,3], density [R,N], t [R,N+1], dirs [R,3] (or [D,3] with d_mod=D) -> comp, distance, acc, weights."""
-    return _Composite.apply(rgb, density, t, dirs, d_mod, white_bkgd)
+def composite(rgb, density, t, dirs, white_bkgd, d_mod=0, attenuate=False):
+    """rgb [R,N,3], density [R,N], t [R,N+1], dirs [R,3] (or [D,3] with d_mod=D) -> comp, distance, acc, weights.
+    `attenuate`: the 1 / (1 + t_mid^2) colour attenuation of volumetric_lighting_composing (models/mip.py:486-527)."""
+    return _Composite.apply(rgb, density, t, dirs, d_mod, int(bool(white_bkgd)) | (2 if attenuate else 0))
 
 
 class _Normals(torch.autograd.Function):
@@ -409,6 +410,156 @@ class _Shade(torch.autograd.Function):
 
 def shade(env_rgb, albedo, normal, light_dirs, solid_angle):
     return _Shade.apply(env_rgb, albedo, normal, light_dirs, solid_angle)
+
+
+# ---- variants the upstream hot path does not call today (csrc/variants.cu) ----------
+BRDF_MICROFACET, BRDF_BLINN_PHONG = 0, 1
+
+
+class _BrdfTerms(torch.autograd.Function):
+    """Specular ratio and NoL per (ray, light direction): `microfeast_brdf` / `blinn_phong_brdf`
+    (utils/surface_rendering.py:6-61, 64-101).  Differentiable w.r.t. normal and roughness."""
+
+    @staticmethod
+    @_amp_fwd
+    def forward(ctx, kind, normal, roughness, l, v):
+        r = normal.shape[0]
+        per_ray = int(l.dim() == 3)
+        d = l.shape[-2]
+        spec = torch.empty(r, d, device=normal.device, dtype=torch.float32)
+        nol = torch.empty(r, d, device=normal.device, dtype=torch.float32)
+        with torch.cuda.device(normal.device):
+            check(_lib.lib().pnb_brdf_terms_fwd(kind, r, d, _p(_req(normal, "normal")), _p(_req(roughness, "roughness")),
+                                                _p(_req(l, "l")), per_ray, _p(_req(v, "v")), _p(spec), _p(nol),
+                                                _stream()), "brdf_terms_fwd")
+        ctx.save_for_backward(normal, roughness, l, v)
+        ctx.cfg = (kind, per_ray, d)
+        return spec, nol
+
+    @staticmethod
+    @_amp_bwd
+    def backward(ctx, g_spec, g_nol):
+        normal, roughness, l, v = ctx.saved_tensors
+        kind, per_ray, d = ctx.cfg
+        d_n, d_r = torch.empty_like(normal), torch.empty_like(roughness)
+        cg = lambda g: None if g is None else g.contiguous()
+        g_spec, g_nol = cg(g_spec), cg(g_nol)
+        with torch.cuda.device(normal.device):
+            check(_lib.lib().pnb_brdf_terms_bwd(kind, normal.shape[0], d, _p(normal), _p(roughness), _p(l), per_ray,
+                                                _p(v), _p(g_spec), _p(g_nol), _p(d_n), _p(d_r), _stream()),
+                  "brdf_terms_bwd")
+        return None, d_n, d_r, None, None
+
+
+def brdf_terms(kind, normal, roughness, l, v):
+    """normal [R,3], roughness [R], l [D,3] or [R,D,3], v [R,3] -> spec [R,D], NoL [R,D]."""
+    return _BrdfTerms.apply(kind, normal, roughness, l, v)
+
+
+class _ShadeSum(torch.autograd.Function):
+    """diffuse / specular sums of the `roughness is not None` branch of surface_rendering
+    (utils/surface_rendering.py:147-151,159)."""
+
+    @staticmethod
+    @_amp_fwd
+    def forward(ctx, env_rgb, albedo, spec, nol, solid_angle):
+        r, d = env_rgb.shape[0], env_rgb.shape[1]
+        dev = env_rgb.device
+        rgb, dif, spc = (torch.empty(r, 3, device=dev, dtype=torch.float32) for _ in range(3))
+        with torch.cuda.device(dev):
+            check(_lib.lib().pnb_shade_sum_fwd(r, d, _p(_req(env_rgb, "env_rgb")), _p(_req(albedo, "albedo")),
+                                               _p(_req(spec, "spec")), _p(_req(nol, "nol")),
+                                               _p(_req(solid_angle, "solid_angle")), _p(rgb), _p(dif), _p(spc),
+                                               _stream()), "shade_sum_fwd")
+        ctx.save_for_backward(env_rgb, albedo, spec, nol, solid_angle)
+        return rgb, dif, spc
+
+    @staticmethod
+    @_amp_bwd
+    def backward(ctx, g_rgb, g_dif, g_spc):
+        env_rgb, albedo, spec, nol, solid_angle = ctx.saved_tensors
+        r, d = env_rgb.shape[0], env_rgb.shape[1]
+        d_env, d_alb = torch.empty_like(env_rgb), torch.empty_like(albedo)
+        d_spec, d_nol = torch.empty_like(spec), torch.empty_like(nol)
+        cg = lambda g: None if g is None else g.contiguous()
+        g_rgb, g_dif, g_spc = cg(g_rgb), cg(g_dif), cg(g_spc)
+        with torch.cuda.device(env_rgb.device):
+            check(_lib.lib().pnb_shade_sum_bwd(r, d, _p(env_rgb), _p(albedo), _p(spec), _p(nol), _p(solid_angle),
+                                               _p(g_rgb), _p(g_dif), _p(g_spc), _p(d_env), _p(d_alb), _p(d_spec),
+                                               _p(d_nol), _stream()), "shade_sum_bwd")
+        return d_env, d_alb, d_spec, d_nol, None
+
+
+def shade_sum(env_rgb, albedo, spec, nol, solid_angle):
+    return _ShadeSum.apply(env_rgb, albedo, spec, nol, solid_angle)
+
+
+class _RotToTarget(torch.autograd.Function):
+    """`RotToTarget.rot2t` (utils/vector_rotation.py:57-89)."""
+
+    @staticmethod
+    @_amp_fwd
+    def forward(ctx, tvec):
+        r = tvec.shape[0]
+        rot = torch.empty(r, 3, 3, device=tvec.device, dtype=torch.float32)
+        with torch.cuda.device(tvec.device):
+            check(_lib.lib().pnb_rot_to_target_fwd(r, _p(_req(tvec, "tvec")), _p(rot), _stream()), "rot_to_target_fwd")
+        ctx.save_for_backward(tvec)
+        return rot
+
+    @staticmethod
+    @_amp_bwd
+    def backward(ctx, g_rot):
+        (tvec,) = ctx.saved_tensors
+        d_t = torch.empty_like(tvec)
+        with torch.cuda.device(tvec.device):
+            check(_lib.lib().pnb_rot_to_target_bwd(tvec.shape[0], _p(tvec), _p(g_rot.contiguous()), _p(d_t), _stream()),
+                  "rot_to_target_bwd")
+        return d_t
+
+
+def rot_to_target(tvec):
+    return _RotToTarget.apply(tvec)
+
+
+class _EnvCastHemisp(torch.autograd.Function):
+    """Env-ray Gaussians of `sample_each_points_hemisp` (models/mip.py:197-237): every surface point brings its own D
+    directions.  Differentiable w.r.t. the surface points (the means are `point + dir * t_mean`); the directions are
+    treated as data."""
+
+    @staticmethod
+    @_amp_fwd
+    def forward(ctx, points, dirs, env_radii, env_near, env_far, n_env, t_rand):
+        b, d = dirs.shape[0], dirs.shape[1]
+        dev = points.device
+        r = b * d
+        t = torch.empty(r, n_env + 1, device=dev, dtype=torch.float32)
+        means = torch.empty(r, n_env, 3, device=dev, dtype=torch.float32)
+        covs = torch.empty(r, n_env, 3, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            check(_lib.lib().pnb_sample_cast_hemisp(r, n_env, _p(_req(points, "points")), d, _p(_req(dirs, "dirs")),
+                                                    _p(_req(env_radii, "radii")), _p(_req(env_near, "near")),
+                                                    _p(_req(env_far, "far")), d, _p(linspace01(n_env + 1, dev)),
+                                                    _p(None if t_rand is None else _req(t_rand, "t_rand")), 0, _p(t),
+                                                    _p(means), _p(covs), _stream()), "sample_cast_hemisp")
+        ctx.k = d * n_env
+        ctx.b = b
+        ctx.mark_non_differentiable(t, covs)
+        return t, means, covs
+
+    @staticmethod
+    @_amp_bwd
+    def backward(ctx, g_t, g_means, g_covs):
+        # d point = sum of the mean gradients of its D * Ne samples
+        g = g_means.contiguous().view(ctx.b, ctx.k * 3)
+        out = torch.empty(ctx.b * 3, device=g.device, dtype=torch.float32)
+        with torch.cuda.device(g.device):
+            check(_lib.lib().pnb_group_sum(ctx.b * ctx.k, 3, ctx.k, _p(g), 3, PNB_F32, _p(out), _stream()), "group_sum")
+        return out.view(ctx.b, 3), None, None, None, None, None, None
+
+
+def env_cast_hemisp(points, dirs, env_radii, env_near, env_far, n_env, t_rand=None):
+    return _EnvCastHemisp.apply(points, dirs, env_radii, env_near, env_far, n_env, t_rand)
 
 
 class _TonemapMSE(torch.autograd.Function):

@@ -236,11 +236,70 @@ def resample_fixture(ns):
     print("resample_large.npz", len(out), "arrays")
 
 
+def variants_fixture(ns):
+    """Functions the upstream hot path does not call today: specular BRDFs, the microfacet
+    branch of surface_rendering, RotToTarget.rot2t, sample_each_points_hemisp, volumetric_lighting_composing."""
+    import importlib
+    sys.path.insert(0, rh.REF_ROOT)
+    try:
+        vr = importlib.import_module("utils.vector_rotation")
+    finally:
+        sys.path.remove(rh.REF_ROOT)
+    out = {}
+    mip, sr = ns.mip, ns.surface_rendering
+    g = torch.Generator().manual_seed(21)
+    b, d, ne = 48, 10, 8
+    nrm = torch.nn.functional.normalize(torch.randn(b, 3, generator=g), dim=-1)
+    alb = torch.rand(b, 3, generator=g)
+    rough = torch.rand(b, 1, generator=g) + 0.05
+    v = torch.nn.functional.normalize(torch.randn(b, 3, generator=g), dim=-1)
+    env = torch.rand(b, d, 3, generator=g) * 3
+    tv = nrm.clone()
+    tv[1] = torch.tensor([0.0, -1.0, 0.0])
+    tv[2] = torch.tensor([0.0, 1.0, 0.0])
+    rot = vr.RotToTarget().rot2t(tv.clone())
+    envr = O.fibonacci_env_rays(d, 0.0035)
+    e32 = ns.Rays(*[x.float() for x in envr])
+    hemi = e32.directions.clone()
+    hemi[:, 1] = hemi[:, 1].abs()                                  # upper hemisphere around +y
+    l = torch.einsum("bij,dj->bdi", rot, hemi).contiguous()        # per-ray light directions
+    om = e32.lossmult
+    out.update(normal=npy(nrm), albedo=npy(alb), roughness=npy(rough), v=npy(v), env=npy(env), tvec=npy(tv),
+               rot=npy(rot), l=npy(l), omega=npy(om))
+    for name, fn in (("mf", sr.microfeast_brdf), ("bp", sr.blinn_phong_brdf)):
+        dif, spec, nol = fn(alb, nrm, rough, l, v)
+        out.update({f"{name}_diffuse_brdf": npy(dif), f"{name}_spec": npy(spec), f"{name}_nol": npy(nol)})
+    rgb, dif, spc = sr.surface_rendering(env, alb, nrm, rough, l, v, om)
+    out.update(sr_rgb=npy(rgb), sr_diffuse=npy(dif), sr_specular=npy(spc))
+    pts = torch.randn(b, 3, generator=g)
+    torch.manual_seed(13)
+    t_rand = torch.rand(1, ne + 1)
+    torch.manual_seed(13)
+    t, (mean, cov), dirs = mip.sample_each_points_hemisp(pts.view(-1, 1, 3), l, ne, e32.near, e32.far, e32.radii, True)
+    t0, (mean0, cov0), _ = mip.sample_each_points_hemisp(pts.view(-1, 1, 3), l, ne, e32.near, e32.far, e32.radii, False)
+    out.update(points=npy(pts), env_near=npy(e32.near), env_far=npy(e32.far), env_radii=npy(e32.radii),
+               hs_t_rand=npy(t_rand), hs_t=npy(t), hs_mean=npy(mean), hs_cov=npy(cov), hs_dirs=npy(dirs),
+               hs_t_det=npy(t0.contiguous()), hs_mean_det=npy(mean0), hs_cov_det=npy(cov0))
+    crgb = torch.rand(b * d, ne, 3, generator=g, requires_grad=True)
+    cden = (-torch.log(torch.rand(b * d, ne, 1, generator=g))).requires_grad_(True)
+    comp, dist, acc, w = mip.volumetric_lighting_composing(crgb, cden, t, dirs, True)
+    gc, gd, ga, gw = (torch.rand(b * d, 3, generator=g), torch.rand(b * d, generator=g), torch.rand(b * d, generator=g),
+                      torch.rand(b * d, ne, generator=g))
+    (comp * gc).sum().add((dist * gd).sum()).add((acc * ga).sum()).add((w * gw).sum()).backward()
+    out.update(vl_rgb=npy(crgb), vl_density=npy(cden), vl_comp=npy(comp), vl_dist=npy(dist), vl_acc=npy(acc),
+               vl_weights=npy(w), vl_g_comp=npy(gc), vl_g_dist=npy(gd), vl_g_acc=npy(ga), vl_g_w=npy(gw),
+               vl_d_rgb=npy(crgb.grad), vl_d_density=npy(cden.grad))
+    np.savez_compressed(os.path.join(HERE, "variants.npz"), **out)
+    print("variants.npz", len(out), "arrays")
+
+
 def main():
     assert rh.available(), "reference tree not found"
     torch.set_num_threads(8)
     ns = rh.load()
-    which = set(sys.argv[1:]) or {"ops", "small", "resample", "c1", "c2s"}
+    which = set(sys.argv[1:]) or {"ops", "small", "resample", "c1", "c2s", "variants"}
+    if "variants" in which:
+        variants_fixture(ns)
     if "ops" in which:
         ops_fixture(ns)
     if "small" in which:

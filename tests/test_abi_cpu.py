@@ -80,8 +80,18 @@ def test_module_interface_mirrors_reference():
                      ("cast_rays", ["t_samples", "origins", "directions", "radii", "ray_shape"]),
                      ("volumetric_rendering", ["rgb", "density", "t_samples", "dirs", "white_bkgd"]),
                      ("integrated_pos_enc", ["means_covs", "min_deg", "max_deg"]),
-                     ("pos_enc", ["x", "min_deg", "max_deg"])):
+                     ("pos_enc", ["x", "min_deg", "max_deg"]),
+                     # SURVEY 8f rank 4 variants (mip.py:197-237, 486-527)
+                     ("sample_each_points_hemisp", ["point_origins", "directions", "num_samples", "near", "far", "radii",
+                                                    "randomized"]),
+                     ("volumetric_lighting_composing", ["rgb", "density", "t_samples", "dirs", "white_bkgd", "output_t"])):
         assert list(inspect.signature(getattr(mip, fn)).parameters)[:len(args)] == args, fn
+    from panonerf_b200.utils import surface_rendering as sr, vector_rotation as vr
+    for fn in ("microfeast_brdf", "blinn_phong_brdf"):                     # utils/surface_rendering.py:6, 64
+        assert list(inspect.signature(getattr(sr, fn)).parameters) == ["albedo", "normal", "roughness", "l", "v"]
+    assert list(inspect.signature(sr.surface_rendering).parameters) == ["env", "albedo", "normal", "roughness", "l", "v",
+                                                                        "solid_angle", "output_sd"]
+    assert list(inspect.signature(vr.RotToTarget().rot2t).parameters) == ["tvec"]   # utils/vector_rotation.py:57
     with pytest.raises(NotImplementedError):
         MipNeRF(rgb_activation="sigmoid")                                  # mip_nerf.py:155-158
     with pytest.raises(NotImplementedError):

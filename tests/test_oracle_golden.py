@@ -106,3 +106,35 @@ def test_models_forward_loss_grads(name, pano):
         if "grad/" + k in g:
             ref = T(g["grad/" + k])
             assert torch.allclose(p.grad, ref, rtol=1e-3, atol=2e-5 * float(ref.abs().max())), k
+
+
+def test_variant_functions():
+    """specular BRDFs, microfacet surface_rendering, rot2t, hemisphere env sampling, attenuated
+    compositing - the oracle restatements against the reference's outputs (tests/golden/variants.npz)."""
+    g = load_golden("variants.npz")
+    f = lambda k: T(g[k])
+    for name, fn in (("mf", O.microfacet_terms), ("bp", O.blinn_phong_terms)):
+        dif, spec, nol = fn(f("albedo"), f("normal"), f("roughness"), f("l"), f("v"))
+        assert torch.equal(dif, f(f"{name}_diffuse_brdf")) and torch.equal(nol, f(f"{name}_nol"))
+        assert torch.allclose(spec, f(f"{name}_spec"), rtol=1e-6, atol=1e-7)
+    # the masked form (finite gradient) has the same forward values
+    assert torch.equal(O.microfacet_terms(f("albedo"), f("normal"), f("roughness"), f("l"), f("v"), masked=True)[1],
+                       O.microfacet_terms(f("albedo"), f("normal"), f("roughness"), f("l"), f("v"))[1])
+    rgb, dif, spc = O.rough_shade(f("env"), f("albedo"), f("normal"), f("roughness"), f("l"), f("v"), f("omega"))
+    assert torch.equal(rgb, f("sr_rgb")) and torch.equal(dif, f("sr_diffuse")) and torch.equal(spc, f("sr_specular"))
+    assert torch.equal(O.rot_to_target(f("tvec")), f("rot"))
+    env = O.Rays(None, None, None, f("env_radii"), None, f("env_near"), f("env_far"), None)
+    b, d = f("l").shape[:2]
+    t, (m, c), dirs = O.env_samples_hemisp(f("points"), f("l"), env, 8, True, t_rand=f("hs_t_rand"))
+    assert torch.equal(t, f("hs_t")) and torch.equal(m, f("hs_mean")) and torch.equal(c, f("hs_cov"))
+    assert torch.equal(dirs, f("hs_dirs"))
+    t0, (m0, c0), _ = O.env_samples_hemisp(f("points"), f("l"), env, 8, False)
+    assert torch.equal(t0.expand(b * d, -1), f("hs_t_det")) and torch.equal(m0, f("hs_mean_det"))
+    rgb_in, den = f("vl_rgb").requires_grad_(), f("vl_density").requires_grad_()
+    comp, dist, acc, w = O.composite_lighting(rgb_in, den, t, dirs, True)
+    for a, k in ((comp, "vl_comp"), (dist, "vl_dist"), (acc, "vl_acc"), (w, "vl_weights")):
+        assert torch.equal(a, f(k)), k
+    (comp * f("vl_g_comp")).sum().add((dist * f("vl_g_dist")).sum()).add((acc * f("vl_g_acc")).sum()).add(
+        (w * f("vl_g_w")).sum()).backward()
+    assert torch.allclose(rgb_in.grad, f("vl_d_rgb"), rtol=1e-6, atol=1e-8)
+    assert torch.allclose(den.grad, f("vl_d_density"), rtol=1e-5, atol=1e-7)

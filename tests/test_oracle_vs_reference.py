@@ -73,3 +73,40 @@ def test_metric_and_image_restatements_match_reference():
     img = a[None]
     ref = (img[0].permute(1, 2, 0).data.cpu().numpy() * 255).astype(np.uint8)        # utils/vis.py:29-35
     assert np.array_equal(O.png_pixels(img), ref)
+
+
+def test_variant_restatements_match_reference():
+    """SURVEY 8f rank 4 functions (dead upstream, restated in the oracle) against the upstream tree on fresh inputs."""
+    import importlib
+    import sys
+    ns = rh.load()
+    sys.path.insert(0, rh.REF_ROOT)
+    try:
+        vr = importlib.import_module("utils.vector_rotation")
+    finally:
+        sys.path.remove(rh.REF_ROOT)
+    sr, mip = ns.surface_rendering, ns.mip
+    g = torch.Generator().manual_seed(0)
+    b, d = 37, 10
+    nz = lambda *s: torch.nn.functional.normalize(torch.randn(*s, generator=g), dim=-1)
+    alb, nrm, rough, l, v = torch.rand(b, 3, generator=g), nz(b, 3), torch.rand(b, 1, generator=g) + 0.05, nz(b, d, 3), nz(b, 3)
+    env, om = torch.rand(b, d, 3, generator=g) * 3, torch.full((1, d, 1), 4 * np.pi / d)
+    for fr, fo in ((sr.microfeast_brdf, O.microfacet_terms), (sr.blinn_phong_brdf, O.blinn_phong_terms)):
+        for x, y in zip(fr(alb, nrm, rough, l, v), fo(alb, nrm, rough, l, v)):
+            assert torch.allclose(x, y, rtol=1e-6, atol=1e-7)
+    assert torch.equal(sr.microfeast_brdf(alb, nrm, rough, l, v)[1], O.microfacet_terms(alb, nrm, rough, l, v, masked=True)[1])
+    for x, y in zip(sr.surface_rendering(env, alb, nrm, rough, l, v, om), O.rough_shade(env, alb, nrm, rough, l, v, om)):
+        assert torch.equal(x, y)
+    tv = nz(20, 3)
+    tv[3], tv[4] = torch.tensor([0.0, -1.0, 0.0]), torch.tensor([0.0, 1.0, 0.0])
+    assert torch.equal(vr.RotToTarget().rot2t(tv.clone()), O.rot_to_target(tv))
+    pts = torch.randn(b, 3, generator=g)
+    e32 = O.Rays(*[x.float() for x in O.fibonacci_env_rays(d, 0.0035)])
+    torch.manual_seed(5)
+    tr, (mr, cr), dr = mip.sample_each_points_hemisp(pts.view(-1, 1, 3), l, 7, e32.near, e32.far, e32.radii, True)
+    torch.manual_seed(5)
+    to, (mo, co), do = O.env_samples_hemisp(pts, l, e32, 7, True)
+    assert torch.equal(tr, to) and torch.equal(mr, mo) and torch.equal(cr, co) and torch.equal(dr, do)
+    rgb, den = torch.rand(b * d, 7, 3, generator=g), -torch.log(torch.rand(b * d, 7, 1, generator=g))
+    for x, y in zip(mip.volumetric_lighting_composing(rgb, den, tr, dr, True), O.composite_lighting(rgb, den, to, do, True)):
+        assert torch.equal(x, y)
