@@ -274,6 +274,12 @@ def run_ours(args):
             line["c4"] = {"error": f"{type(e).__name__}: {e}", "traceback": traceback.format_exc()[-3000:]}
         graphed = None
         torch.cuda.empty_cache()
+        if rank == 0:
+            try:
+                line["c1"] = measure_c1(dev)
+            except Exception as e:               # noqa: BLE001
+                line["c1"] = {"error": f"{type(e).__name__}: {e}"}
+            torch.cuda.empty_cache()
         try:
             r = measure_render(system, dev, world, rank, local, 512, 1024, args.render_chunk, args.render_steps, 1)
             line["render"] = {k: r[k] for k in ("metric", "value", "unit", "ms_per_step", "scaling", "config", "e2e",
@@ -411,6 +417,48 @@ def measure_c4(system, opt, dev, world, rank, steps):
             "steps": steps, "ms_per_step": ms, "value": n * world / (ms / 1e3), "unit": "rays/s",
             "step_tflops": step_flops() * (n / RAYS_PER_GPU) * world / (ms / 1e3) / 1e12,
             "peak_memory_gb": torch.cuda.max_memory_allocated(dev) / 1e9, "final_loss": float(loss)}
+
+
+def measure_c1(dev, steps=10):
+    """BASELINE.json configs[0] on the GPU: configs/mipnerf.yaml training step (MipNeRF, C = 1 density channel, no ort
+    loss), 4096 rays of a 64 x 128 equirect grid, 128 coarse + 128 fine samples, forward + backward + Adam, eager (no
+    CUDA graph).  The reference runs this configuration in fp32 on the CPU (~27 s per step on 8 cores)."""
+    from oracle import panonerf_oracle as O            # input / weight synthesis only
+    from panonerf_b200.systems.base_system import default_hparams
+    from panonerf_b200.systems.mipnerf_system import MipNeRFSystem
+    n, ns = 4096, 128
+    hp = default_hparams("mipnerf", precision="bf16")
+    hp.update({"nerf.num_samples": ns, "train.randomized": True})
+    system = MipNeRFSystem(hp).to(dev)
+    system.mip_nerf.mlp.load_state_dict(O.synth_state_dict(seed=4, width=256, c_density=1))
+    opt = system.configure_optimizers()
+    rays = O.equirect_rays(64, 128, camera(), 0.0, 10.0)
+    g = torch.Generator().manual_seed(0)
+    from panonerf_b200.datasets.base_datasets import Rays
+    rays_d = Rays(*[getattr(rays, k)[:n].contiguous().to(dev) for k in O.Rays._fields])
+    gt_d = (torch.rand(n, 3, generator=g) * 2).to(dev)
+
+    def step():
+        opt.zero_grad()
+        loss = system.training_step((rays_d, gt_d))
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(3):
+        loss = step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    flop = n * 3 * (2 * ns) * (MLP_FLOP_PER_SAMPLE - 2 * 256 * 4)       # C = 1: 1 220 608 FLOP per sample
+    return {"workload": "configs/mipnerf.yaml training step: MipNeRF, 4096 rays, 128+128 samples, fwd+bwd+Adam, eager",
+            "rays": n, "num_samples": ns, "steps": steps, "ms_per_step": ms, "value": n / (ms / 1e3), "unit": "rays/s",
+            "step_tflops": flop / (ms / 1e3) / 1e12, "final_loss": float(loss)}
 
 
 def step_flops():

@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
 L=gpurun_out/r2_fused_save_modes.log; : > $L
-for mode in t w; do
+for mode in ${MODES:-t w}; do
   export PNB_FUSED_SAVE=$mode
   timeout 300 python -m pytest tests/test_fused_gpu.py -q -x 2>&1 | tail -1 >> $L
   for args in "--save" "--normals --save" "--bwd" "--jadj"; do
