@@ -72,7 +72,8 @@ int pnb_ipe_fwd(int M, const float* means, const float* covs, int min_deg, int m
  * the env-branch gradient into the surface point) */
 int pnb_ipe_vjp(int M, const float* means, const float* covs, int min_deg, int max_deg, const void* d_enc,
                 int ld, int dtype, float* d_means, void* stream);
-/* out[m,f] = sum_c (d enc_f / d mean_c) * v[m,c]   (Jacobian-vector product: the adjoint of pnb_ipe_vjp) */
+/* out[m,f] = sum_c (d enc_f / d mean_c) * v[m,c]   (Jacobian-vector product: the adjoint of pnb_ipe_vjp); bf16 rows
+ * (the tensor-core path's operand) take sin / cos / exp2 from the SFU, fp32 rows keep ~1 ulp cosines on the exact phase */
 int pnb_ipe_jvp(int M, const float* means, const float* covs, int min_deg, int max_deg, const float* v,
                 void* out, int ld, int dtype, void* stream);
 int pnb_pos_enc(int R, const float* x, int deg, float* out, void* stream);

@@ -406,6 +406,42 @@ def test_ipe_fast_path_matches_the_exact_path(monkeypatch):
     assert float((fast.cpu() - ref).abs().max()) < 2e-6
 
 
+def test_ipe_jvp_tile_kernel(monkeypatch):
+    """The tiled IPE jvp kernel (one thread per sample and component, 16-byte rows through shared memory): fp32 rows
+    are bit-identical to the per-feature kernel it replaces; bf16 rows (SFU sin / cos / exp2) stay within one bf16 ulp;
+    a ragged sample count (not a multiple of the 128-sample tile) and strided rows."""
+    from panonerf_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    M = 10007
+    mean = ((torch.rand(M, 3, generator=g) * 2 - 1) * torch.tensor([0.5, 8.0, 60.0])).to(DEV)
+    cov = (torch.rand(M, 3, generator=g) * torch.tensor([1e-9, 1e-5, 3e-2])).to(DEV)
+    v = torch.randn(M, 3, generator=g).to(DEV)
+
+    def run():
+        jv = torch.empty(M, 96, device=DEV)
+        ops.ipe_jvp_into(mean, cov, 0, 16, v, jv)
+        jw = torch.zeros(M, 352, device=DEV, dtype=torch.bfloat16)
+        ops.ipe_jvp_into(mean, cov, 0, 16, v, jw[:, 256:])
+        assert float(jw[:, :256].abs().max()) == 0.0
+        return jv, jw[:, 256:].float()
+
+    jv, jw = run()
+    monkeypatch.setenv("PNB_IPE_SLOW", "1")
+    jv_ref, jw_ref = run()
+    monkeypatch.delenv("PNB_IPE_SLOW")
+    assert torch.equal(jv, jv_ref)
+    # one bf16 ulp of the exact rows plus the SFU's ~5e-7 absolute sine error at the scale of the row (2^l v)
+    d = (jw - jw_ref).abs()
+    assert float((d - 2.0 ** -7 * jw_ref.abs() - 4e-6 * jw_ref.abs().amax(1, keepdim=True)).max()) <= 1e-6
+    # <J v, g> == <v, J^T g> with J^T g from autograd through the oracle
+    gvec = torch.randn(M, 96, generator=g)
+    mean_r = mean.cpu().clone().requires_grad_()
+    (gref,) = torch.autograd.grad((O.ipe(mean_r, cov.cpu(), 0, 16) * gvec).sum(), mean_r)
+    lhs = float((jv.cpu().double() * gvec.double()).sum())
+    rhs = float((gref.double() * v.cpu().double()).sum())
+    assert abs(lhs - rhs) <= 1e-4 * max(abs(rhs), 1.0)
+
+
 def test_device_ray_feed_gathers_the_rays_of_its_pixels():
     """DeviceRayFeed: a sampled batch is exactly the K1 rays / GT colours of the drawn pixel ids,
     over two cameras, and a training step runs on it."""

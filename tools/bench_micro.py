@@ -43,6 +43,7 @@ def main():
     covs = torch.rand(M, 3, device=dev, generator=g)
     enc16 = torch.empty(M, 96, device=dev, dtype=torch.bfloat16)
     enc32 = torch.empty(M, 96, device=dev, dtype=torch.float32)
+    vdir = torch.randn(M, 3, device=dev, generator=g)
     rgb = torch.rand(R, N, 3, device=dev, generator=g)
     den = -torch.log(torch.rand(R, N, device=dev, generator=g).clamp_min(1e-6))
     t = torch.sort(torch.rand(R, N + 1, device=dev, generator=g) * 10, dim=1).values.contiguous()
@@ -54,6 +55,9 @@ def main():
     cases = [
         ("ipe_fwd(bf16 out)", lambda: ops.ipe_into(means, covs, 0, 16, enc16), M * (24 + 192), M),
         ("ipe_fwd(fp32 out)", lambda: ops.ipe_into(means, covs, 0, 16, enc32), M * (24 + 384), M),
+        ("ipe_vjp(bf16 rows)", lambda: ops.ipe_vjp(means, covs, 0, 16, enc16), M * (36 + 192), M),
+        ("ipe_vjp(fp32 rows)", lambda: ops.ipe_vjp(means, covs, 0, 16, enc32), M * (36 + 384), M),
+        ("ipe_jvp(bf16 rows)", lambda: ops.ipe_jvp_into(means, covs, 0, 16, vdir, enc16), M * (36 + 192), M),
         ("sample_cast", lambda: ops.sample_cast(origins, dirs, radii, near, far, N), R * (36 + 4 * (N + 1) + 24 * N), M),
         ("composite_fwd", lambda: ops.composite(rgb, den, t, dirs, False), M * 24 + R * 36, M),
         ("resample", lambda: ops.resample(t, w, 0.01), M * 12 + R * 8, M),
