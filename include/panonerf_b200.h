@@ -105,6 +105,20 @@ int pnb_composite_bwd(int R, int N, const float* rgb, const float* density, cons
                       int d_mod, int white_bkgd, const float* g_comp, const float* g_dist, const float* g_acc,
                       const float* g_weights, float* d_rgb, float* d_density, void* stream);
 
+/* K6 with compute_graph's activations fused in (models/pano_mip_nerf.py:264-278 + models/mip.py:444-483 in one pass):
+ * raw_rgb [R*N,3] and raw_den [R*N,C] are the MLP's head outputs; rgb = softplus(raw_rgb) (1 + 2 pad) - pad and
+ * density = softplus(raw_den[:,0] + density_bias) live in registers only; albedo (nullable, [R*N,3], needs C >= 4)
+ * receives sigmoid(raw_den[:,1:4]) 0.77 + 0.03.  Results are bit-identical to pnb_act_fwd + pnb_composite_fwd
+ * (N <= 256) and pnb_composite_bwd + pnb_act_bwd.  d_raw_den is [R*N,C]: channel 0 = density, 1..3 = g_albedo through
+ * the sigmoid (zero when g_albedo is null), the rest zero. */
+int pnb_act_composite_fwd(int R, int N, int C, const float* raw_rgb, const float* raw_den, float density_bias,
+                          float rgb_padding, const float* t, const float* dirs, int d_mod, int white_bkgd,
+                          float* comp_rgb, float* distance, float* acc, float* weights, float* albedo, void* stream);
+int pnb_act_composite_bwd(int R, int N, int C, const float* raw_rgb, const float* raw_den, float density_bias,
+                          float rgb_padding, const float* t, const float* dirs, int d_mod, int white_bkgd,
+                          const float* g_comp, const float* g_dist, const float* g_acc, const float* g_weights,
+                          const float* g_albedo, float* d_raw_rgb, float* d_raw_den, void* stream);
+
 /* ---- K7  hierarchical resampling: models/mip.py:304-352 (blur-pool) + 240-301 (PDF/CDF/searchsorted/lerp) --
  * u: [N+1] when u_ld==0 (deterministic linspace(0,1-eps,N+1)) or [R,N+1] (u_ld=N+1, randomized).
  * inds (nullable) receives torch.searchsorted(cdf,u,right=True) as int64 — bit-exact contract.

@@ -119,12 +119,22 @@ composite_fwd_kernel(long long R, int N, const float* __restrict__ rgb, const fl
 // rows move as 128-bit accesses when rows are 16-byte aligned (VEC), the fp64 exclusive scan is K - 1 in-lane adds plus
 // log2(L) shuffle steps, and the five per-ray sums reduce over L lanes only.  Same formulas and fp32 / fp64 types as
 // above; the association of the sums differs (results agree to rounding, tests/test_kernels_gpu.py).
-template <int K, int L, bool VEC>
+//
+// ACT = true fuses compute_graph's activations (models/pano_mip_nerf.py:264-278, the arithmetic of act_fwd_kernel in
+// shade.cu, same expressions in the same order) into the loads: `rgb` / `density` are then the RAW head outputs
+// ([M,3] and [M,C], channel 0 = density, 1..3 = albedo), the activated colours and densities live in registers only,
+// and the per-sample albedos (needed by the normals stage) leave as one more [M,3] row when `act.albedo` is set.
+struct ActArgs {
+  int C;
+  float bias, pad;
+  float* albedo;  // nullable
+};
+template <int K, int L, bool VEC, bool ACT>
 __global__ void __launch_bounds__(256)
 composite_fwd_blocked_kernel(int R, int N, const float* __restrict__ rgb, const float* __restrict__ density,
                              const float* __restrict__ t, const float* __restrict__ dirs, int d_mod, int white_bkgd,
                              float* __restrict__ comp_rgb, float* __restrict__ distance, float* __restrict__ acc_out,
-                             float* __restrict__ weights) {
+                             float* __restrict__ weights, const ActArgs act) {
   constexpr int kRaysPerWarp = 32 / L;
   const bool atten = (white_bkgd & PNB_COMPOSITE_ATTENUATE) != 0;
   white_bkgd &= PNB_COMPOSITE_WHITE_BKGD;
@@ -146,11 +156,16 @@ composite_fwd_blocked_kernel(int R, int N, const float* __restrict__ rgb, const 
 #pragma unroll
     for (int k = 0; k <= K; ++k) tv[k] = (j0 + k <= N) ? tr[j0 + k] : 0.f;
     if (VEC) {  // N % 4 == 0 and K % 4 == 0: whole 16-byte groups are either inside or outside the ray
+      if (ACT && act.C != 1) {  // raw density is channel 0 of a [M,C] row
 #pragma unroll
-      for (int k = 0; k < K; k += 4) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (j0 + k < N) v = *reinterpret_cast<const float4*>(density + s0 + k);
-        den[k] = v.x, den[k + 1] = v.y, den[k + 2] = v.z, den[k + 3] = v.w;
+        for (int k = 0; k < K; ++k) den[k] = (j0 + k < N) ? density[(s0 + k) * act.C] : 0.f;
+      } else {
+#pragma unroll
+        for (int k = 0; k < K; k += 4) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (j0 + k < N) v = *reinterpret_cast<const float4*>(density + s0 + k);
+          den[k] = v.x, den[k + 1] = v.y, den[k + 2] = v.z, den[k + 3] = v.w;
+        }
       }
 #pragma unroll
       for (int k = 0; k < 3 * K; k += 4) {
@@ -162,10 +177,25 @@ composite_fwd_blocked_kernel(int R, int N, const float* __restrict__ rgb, const 
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         const bool ok = j0 + k < N;
-        den[k] = ok ? density[s0 + k] : 0.f;
+        den[k] = ok ? density[(s0 + k) * (ACT ? act.C : 1)] : 0.f;
         col[3 * k] = ok ? rgb[3 * (s0 + k)] : 0.f;
         col[3 * k + 1] = ok ? rgb[3 * (s0 + k) + 1] : 0.f;
         col[3 * k + 2] = ok ? rgb[3 * (s0 + k) + 2] : 0.f;
+      }
+    }
+    if (ACT) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        if (j0 + k < N) {
+          den[k] = softplus_f(den[k] + act.bias);
+#pragma unroll
+          for (int q = 0; q < 3; ++q) col[3 * k + q] = softplus_f(col[3 * k + q]) * (1.f + 2.f * act.pad) - act.pad;
+          if (act.albedo != nullptr && ray_ok) {
+            const float* ra = density + (s0 + k) * act.C + 1;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) act.albedo[3 * (s0 + k) + q] = (1.f / (1.f + expf(-ra[q]))) * 0.77f + 0.03f;
+          }
+        }
       }
     }
     float sd[K];
@@ -228,12 +258,17 @@ composite_fwd_blocked_kernel(int R, int N, const float* __restrict__ rgb, const 
 
 // Hand-derived backward of the block above.  With sd_i = sigma_i*delta_i, T_i = exp(-sum_{j<i} sd_j),
 // w_i = (1-exp(-sd_i)) T_i and G_i = dL/dw_i:   dL/dsd_i = G_i (T_i - w_i) - sum_{j>i} G_j w_j.
+// ACT = true: `rgb` / `density` are the raw head outputs (see composite_fwd_blocked_kernel), the activations are
+// recomputed, and the kernel applies act_bwd_kernel's chain-rule factors (shade.cu, same expressions) on the way out:
+// d_rgb receives d raw_rgb [M,3], d_density receives d raw_density [M,C] (channel 0 = density, 1..3 = the albedo
+// gradient `g_alb` through the sigmoid, the rest zero).
+template <bool ACT>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 composite_bwd_kernel(long long R, int N, const float* __restrict__ rgb, const float* __restrict__ density,
                      const float* __restrict__ t, const float* __restrict__ dirs, int d_mod, int white_bkgd,
                      const float* __restrict__ g_comp, const float* __restrict__ g_dist,
                      const float* __restrict__ g_acc, const float* __restrict__ g_w, float* __restrict__ d_rgb,
-                     float* __restrict__ d_density) {
+                     float* __restrict__ d_density, const ActArgs act, const float* __restrict__ g_alb) {
   extern __shared__ float smem[];
   const bool atten = (white_bkgd & PNB_COMPOSITE_ATTENUATE) != 0;
   white_bkgd &= PNB_COMPOSITE_WHITE_BKGD;
@@ -253,7 +288,9 @@ composite_bwd_kernel(long long R, int N, const float* __restrict__ rgb, const fl
       int i = base + lane;
       bool ok = i < N;
       float t0 = ok ? tr[i] : 0.f, t1 = ok ? tr[i + 1] : 0.f;
-      float sd = ok ? density[r * N + i] * ((t1 - t0) * dnorm) : 0.f;
+      float den_i = 0.f;
+      if (ok) den_i = ACT ? softplus_f(density[(r * N + i) * act.C] + act.bias) : density[r * N + i];
+      float sd = ok ? den_i * ((t1 - t0) * dnorm) : 0.f;
       double incl = warp_scan_incl((double)sd, lane);
       double prev = __shfl_up_sync(0xffffffffu, incl, 1);
       double excl = carry + (lane == 0 ? 0.0 : prev);
@@ -277,7 +314,12 @@ composite_bwd_kernel(long long R, int N, const float* __restrict__ rgb, const fl
     float gd = (g_dist && pass) ? g_dist[r] / a : 0.f;
     __syncwarp();
     for (int i = lane; i < N; i += 32) {
-      const float* c = rgb + 3 * (r * N + i);
+      const float* cr = rgb + 3 * (r * N + i);
+      float c[3] = {cr[0], cr[1], cr[2]};
+      if (ACT) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) c[q] = softplus_f(c[q]) * (1.f + 2.f * act.pad) - act.pad;
+      }
       float tm = 0.5f * (tr[i] + tr[i + 1]);
       const float att = atten ? atten_of(tm) : 1.f;
       float G = (gc0 * c[0] + gc1 * c[1] + gc2 * c[2]) * att + ga + (g_w ? g_w[r * N + i] : 0.f);
@@ -287,7 +329,13 @@ composite_bwd_kernel(long long R, int N, const float* __restrict__ rgb, const fl
       sT[i] = G * (sT[i] - w);  // re-use: G_i (T_i - w_i)
       float* o = d_rgb + 3 * (r * N + i);
       const float wa = w * att;
-      o[0] = wa * gc0, o[1] = wa * gc1, o[2] = wa * gc2;
+      if (ACT) {  // act_bwd_kernel: d_rgb * (1 + 2 pad) * softplus'(raw)   (0 without any colour gradient)
+        const float gk[3] = {wa * gc0, wa * gc1, wa * gc2};
+#pragma unroll
+        for (int q = 0; q < 3; ++q) o[q] = g_comp ? gk[q] * (1.f + 2.f * act.pad) * softplus_d1(cr[q]) : 0.f;
+      } else {
+        o[0] = wa * gc0, o[1] = wa * gc1, o[2] = wa * gc2;
+      }
     }
     __syncwarp();
     // suffix-exclusive sum of Q, walking the chunks from the far end of the ray
@@ -299,7 +347,24 @@ composite_bwd_kernel(long long R, int N, const float* __restrict__ rgb, const fl
       float incl = warp_scan_incl(q, lane);
       float excl = tail + incl - q;
       tail += __shfl_sync(0xffffffffu, incl, 31);
-      if (ok) d_density[r * N + i] = (sT[i] - excl) * ((tr[i + 1] - tr[i]) * dnorm);
+      if (ok) {
+        const float dd = (sT[i] - excl) * ((tr[i + 1] - tr[i]) * dnorm);
+        if (ACT) {
+          const float* rw = density + (r * N + i) * act.C;
+          float* od = d_density + (r * N + i) * act.C;
+          od[0] = dd * softplus_d1(rw[0] + act.bias);
+          for (int k = 1; k < act.C; ++k) {
+            float g = 0.f;
+            if (g_alb != nullptr && k <= 3) {
+              const float sg = 1.f / (1.f + expf(-rw[k]));
+              g = g_alb[3 * (r * N + i) + k - 1] * 0.77f * sg * (1.f - sg);
+            }
+            od[k] = g;
+          }
+        } else {
+          d_density[r * N + i] = dd;
+        }
+      }
     }
     __syncwarp();
   }
@@ -496,12 +561,10 @@ resample_kernel(long long R, int N, const float* __restrict__ t, const float* __
 
 using namespace pnb;
 
-extern "C" int pnb_composite_fwd(int R, int N, const float* rgb, const float* density, const float* t,
-                                 const float* dirs, int d_mod, int white_bkgd, float* comp_rgb, float* distance,
-                                 float* acc, float* weights, void* stream) {
-  PNB_REQUIRE(R >= 0 && N > 0 && d_mod >= 0, "composite_fwd: bad sizes");
-  if (R == 0) return 0;
-  cudaStream_t st = as_stream(stream);
+template <bool ACT>
+static int launch_composite_fwd(int R, int N, const float* rgb, const float* density, const float* t,
+                                const float* dirs, int d_mod, int white_bkgd, float* comp_rgb, float* distance,
+                                float* acc, float* weights, const ActArgs act, cudaStream_t st) {
   const bool vec = N % 4 == 0 && ((uintptr_t)rgb % 16 == 0) && ((uintptr_t)density % 16 == 0) &&
                    ((uintptr_t)weights % 16 == 0);
   static const bool legacy = getenv("PNB_COMPOSITE_LEGACY") != nullptr;  // A/B experiments
@@ -510,14 +573,14 @@ extern "C" int pnb_composite_fwd(int R, int N, const float* rgb, const float* de
     const long long warps = ((long long)R + 32 / (L) - 1) / (32 / (L));                                              \
     const int grid = grid_for(warps * 32, 256, 8);                                                                   \
     if (vec)                                                                                                         \
-      composite_fwd_blocked_kernel<K, L, true><<<grid, 256, 0, st>>>(R, N, rgb, density, t, dirs, d_mod, white_bkgd, \
-                                                                     comp_rgb, distance, acc, weights);             \
+      composite_fwd_blocked_kernel<K, L, true, ACT><<<grid, 256, 0, st>>>(                                          \
+          R, N, rgb, density, t, dirs, d_mod, white_bkgd, comp_rgb, distance, acc, weights, act);                    \
     else                                                                                                             \
-      composite_fwd_blocked_kernel<K, L, false><<<grid, 256, 0, st>>>(R, N, rgb, density, t, dirs, d_mod,            \
-                                                                      white_bkgd, comp_rgb, distance, acc, weights); \
+      composite_fwd_blocked_kernel<K, L, false, ACT><<<grid, 256, 0, st>>>(                                         \
+          R, N, rgb, density, t, dirs, d_mod, white_bkgd, comp_rgb, distance, acc, weights, act);                    \
     return finish("composite_fwd");                                                                                  \
   } while (0)
-  if (!legacy) {
+  if (!legacy || ACT) {
     if (N <= 16) PNB_LAUNCH_COMPOSITE(4, 4);
     if (N <= 32) PNB_LAUNCH_COMPOSITE(4, 8);
     if (N <= 64) PNB_LAUNCH_COMPOSITE(4, 16);
@@ -525,10 +588,34 @@ extern "C" int pnb_composite_fwd(int R, int N, const float* rgb, const float* de
     if (N <= 256) PNB_LAUNCH_COMPOSITE(8, 32);
   }
 #undef PNB_LAUNCH_COMPOSITE
+  if (ACT) {
+    set_error_msg("act_composite_fwd: N > 256 is not supported by the fused kernel");
+    return PNB_ERR_ARG;
+  }
   int grid = grid_for((long long)R * 32, kWarpsPerBlock * 32, 8);
   composite_fwd_kernel<<<grid, kWarpsPerBlock * 32, 0, st>>>(R, N, rgb, density, t, dirs, d_mod, white_bkgd, comp_rgb,
                                                              distance, acc, weights);
   return finish("composite_fwd");
+}
+
+extern "C" int pnb_composite_fwd(int R, int N, const float* rgb, const float* density, const float* t,
+                                 const float* dirs, int d_mod, int white_bkgd, float* comp_rgb, float* distance,
+                                 float* acc, float* weights, void* stream) {
+  PNB_REQUIRE(R >= 0 && N > 0 && d_mod >= 0, "composite_fwd: bad sizes");
+  if (R == 0) return 0;
+  return launch_composite_fwd<false>(R, N, rgb, density, t, dirs, d_mod, white_bkgd, comp_rgb, distance, acc, weights,
+                                     ActArgs{1, 0.f, 0.f, nullptr}, as_stream(stream));
+}
+
+extern "C" int pnb_act_composite_fwd(int R, int N, int C, const float* raw_rgb, const float* raw_den,
+                                     float density_bias, float rgb_padding, const float* t, const float* dirs,
+                                     int d_mod, int white_bkgd, float* comp_rgb, float* distance, float* acc,
+                                     float* weights, float* albedo, void* stream) {
+  PNB_REQUIRE(R >= 0 && N > 0 && N <= 256 && d_mod >= 0 && C >= 1 && (albedo == nullptr || C >= 4),
+              "act_composite_fwd: bad sizes (N <= 256, albedo needs C >= 4)");
+  if (R == 0) return 0;
+  return launch_composite_fwd<true>(R, N, raw_rgb, raw_den, t, dirs, d_mod, white_bkgd, comp_rgb, distance, acc,
+                                    weights, ActArgs{C, density_bias, rgb_padding, albedo}, as_stream(stream));
 }
 
 extern "C" int pnb_composite_bwd(int R, int N, const float* rgb, const float* density, const float* t,
@@ -540,11 +627,31 @@ extern "C" int pnb_composite_bwd(int R, int N, const float* rgb, const float* de
   size_t smem = (size_t)kWarpsPerBlock * 3 * N * sizeof(float);
   PNB_REQUIRE(smem <= 200 * 1024, "composite_bwd: N too large for the per-warp shared-memory staging");
   if (smem > 48 * 1024)
-    cudaFuncSetAttribute(composite_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(composite_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int grid = grid_for((long long)R * 32, kWarpsPerBlock * 32, 4);
-  composite_bwd_kernel<<<grid, kWarpsPerBlock * 32, smem, as_stream(stream)>>>(
-      R, N, rgb, density, t, dirs, d_mod, white_bkgd, g_comp, g_dist, g_acc, g_weights, d_rgb, d_density);
+  composite_bwd_kernel<false><<<grid, kWarpsPerBlock * 32, smem, as_stream(stream)>>>(
+      R, N, rgb, density, t, dirs, d_mod, white_bkgd, g_comp, g_dist, g_acc, g_weights, d_rgb, d_density,
+      ActArgs{1, 0.f, 0.f, nullptr}, nullptr);
   return finish("composite_bwd");
+}
+
+extern "C" int pnb_act_composite_bwd(int R, int N, int C, const float* raw_rgb, const float* raw_den,
+                                     float density_bias, float rgb_padding, const float* t, const float* dirs,
+                                     int d_mod, int white_bkgd, const float* g_comp, const float* g_dist,
+                                     const float* g_acc, const float* g_weights, const float* g_albedo,
+                                     float* d_raw_rgb, float* d_raw_den, void* stream) {
+  PNB_REQUIRE(R >= 0 && N > 0 && d_mod >= 0 && C >= 1 && (g_albedo == nullptr || C >= 4),
+              "act_composite_bwd: bad sizes (albedo needs C >= 4)");
+  if (R == 0) return 0;
+  size_t smem = (size_t)kWarpsPerBlock * 3 * N * sizeof(float);
+  PNB_REQUIRE(smem <= 200 * 1024, "act_composite_bwd: N too large for the per-warp shared-memory staging");
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(composite_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int grid = grid_for((long long)R * 32, kWarpsPerBlock * 32, 4);
+  composite_bwd_kernel<true><<<grid, kWarpsPerBlock * 32, smem, as_stream(stream)>>>(
+      R, N, raw_rgb, raw_den, t, dirs, d_mod, white_bkgd, g_comp, g_dist, g_acc, g_weights, d_raw_rgb, d_raw_den,
+      ActArgs{C, density_bias, rgb_padding, nullptr}, g_albedo);
+  return finish("act_composite_bwd");
 }
 
 template <int KMAX>

@@ -702,26 +702,44 @@ __global__ void group_sum_kernel(long long G, int N, int group, const T* __restr
     out[idx] = s;
   }
 }
-// bf16 fast path: one warp per (group, 64-column slab), every lane sums one bf16x2 column pair over the rows of the
-// group: 128-byte coalesced row reads, float2 stores.
+// bf16 fast path: one warp per (group, 64-column slab); eight lanes cover the 128 bytes of a row with 16-byte loads, the
+// four lane groups take rows i = q, q + 4, ... (four rows per instruction, 4x the bytes in flight of a 4-byte-per-lane
+// walk), then two shuffle steps add the four partial rows.  Row order inside a column differs from a sequential sum
+// (4 interleaved partials), as with any parallel reduction; float4 stores.
 __global__ void group_sum_bf16x2_kernel(long long G, int N, int group, const __nv_bfloat16* __restrict__ x, int ldx,
                                         float* __restrict__ out) {
   const int lane = threadIdx.x & 31;
+  const int q = lane >> 3, c8 = lane & 7;  // row phase, 16-byte column chunk
   const int slabs = N / 64;
   const long long total = G * slabs;
   for (long long w = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5); w < total;
        w += (long long)gridDim.x * (blockDim.x >> 5)) {
     const long long g = w / slabs;
-    const int col = (int)(w - g * slabs) * 64 + 2 * lane;
+    const int col = (int)(w - g * slabs) * 64 + 8 * c8;
     const __nv_bfloat16* base = x + g * group * (long long)ldx + col;
-    float s0 = 0.f, s1 = 0.f;
+    float s[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s[k] = 0.f;
 #pragma unroll 4
-    for (int i = 0; i < group; ++i) {
-      const uint32_t v = *reinterpret_cast<const uint32_t*>(base + (long long)i * ldx);
-      s0 += __uint_as_float(v << 16);
-      s1 += __uint_as_float(v & 0xffff0000u);
+    for (int i = q; i < group; i += 4) {
+      const uint4 v = __ldcs(reinterpret_cast<const uint4*>(base + (long long)i * ldx));
+      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        s[2 * k] += __uint_as_float(u[k] << 16);
+        s[2 * k + 1] += __uint_as_float(u[k] & 0xffff0000u);
+      }
     }
-    *reinterpret_cast<float2*>(out + g * N + col) = make_float2(s0, s1);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      s[k] += __shfl_xor_sync(0xffffffffu, s[k], 8);
+      s[k] += __shfl_xor_sync(0xffffffffu, s[k], 16);
+    }
+    if (q == 0) {
+      float4* o = reinterpret_cast<float4*>(out + g * N + col);
+      o[0] = make_float4(s[0], s[1], s[2], s[3]);
+      o[1] = make_float4(s[4], s[5], s[6], s[7]);
+    }
   }
 }
 
@@ -775,7 +793,7 @@ extern "C" int pnb_group_sum(long long M, int N, int group, const void* x, int l
   PNB_REQUIRE(M >= 0 && N > 0 && group > 0 && M % group == 0, "group_sum: M must be a multiple of group");
   if (M == 0) return 0;
   long long G = M / group;
-  if (dtype == PNB_BF16 && N % 64 == 0 && ldx % 2 == 0 && ((uintptr_t)x % 4) == 0) {
+  if (dtype == PNB_BF16 && N % 64 == 0 && ldx % 8 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)out % 16) == 0) {
     const long long warps = G * (N / 64);
     const int grid = grid_for(warps * 32, 256, 8);
     pnb::group_sum_bf16x2_kernel<<<grid, 256, 0, as_stream(stream)>>>(G, N, group, (const __nv_bfloat16*)x, ldx, out);

@@ -152,10 +152,9 @@ class MipNeRF(_NerfBase):
             want_normals = lvl == 1 and use_ort_loss
             raw_rgb, raw_den, n_raw = self._field(means, covs, venc, means.shape[1], want_normals)
             R, S = means.shape[0], means.shape[1]
-            rgb, den, _ = ops.activations(raw_rgb.view(R * S, -1), raw_den.view(R * S, -1), self.density_bias,
-                                          self.rgb_padding, False)
-            comp_rgb, distance, acc, weights = ops.composite(rgb.view(R, S, 3), den.view(R, S), t, rays.directions,
-                                                            white_bkgd)
+            comp_rgb, distance, acc, weights, _ = ops.act_composite(
+                raw_rgb.view(R * S, -1), raw_den.view(R * S, -1), t, rays.directions, white_bkgd, self.density_bias,
+                self.rgb_padding, False)
             if want_normals:
                 normal, ort, _ = ops.normals_aggregate(n_raw, weights, rays.directions, None)
                 ret.append((comp_rgb, distance, ops.dmean(ort), normal))

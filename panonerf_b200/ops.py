@@ -7,6 +7,8 @@ from __future__ import annotations
 import ctypes
 from typing import Optional
 
+import os
+
 import torch
 
 from . import _lib
@@ -297,6 +299,59 @@ def composite(rgb, density, t, dirs, white_bkgd, d_mod=0, attenuate=False):
     """rgb [R,N,3], density [R,N], t [R,N+1], dirs [R,3] (or [D,3] with d_mod=D) -> comp, distance, acc, weights.
     `attenuate`: the 1 / (1 + t_mid^2) colour attenuation of volumetric_lighting_composing (models/mip.py:486-527)."""
     return _Composite.apply(rgb, density, t, dirs, d_mod, int(bool(white_bkgd)) | (2 if attenuate else 0))
+
+
+class _ActComposite(torch.autograd.Function):
+    """compute_graph's activations (models/pano_mip_nerf.py:264-278) + volumetric_rendering (models/mip.py:444-483) in
+    one kernel each way: the activated colours / densities never reach HBM.  Bit-identical to _Act followed by
+    _Composite."""
+
+    @staticmethod
+    @_amp_fwd
+    def forward(ctx, raw_rgb, raw_den, t, dirs, r, n, d_mod, white_bkgd, density_bias, rgb_padding, want_albedo):
+        m, c = raw_den.shape
+        dev = raw_den.device
+        comp = torch.empty(r, 3, device=dev, dtype=torch.float32)
+        dist = torch.empty(r, device=dev, dtype=torch.float32)
+        acc = torch.empty(r, device=dev, dtype=torch.float32)
+        w = torch.empty(r, n, device=dev, dtype=torch.float32)
+        alb = torch.empty(m, 3, device=dev, dtype=torch.float32) if want_albedo else None
+        with torch.cuda.device(dev):
+            check(_lib.lib().pnb_act_composite_fwd(r, n, c, _p(_req(raw_rgb, "raw_rgb")), _p(_req(raw_den, "raw_den")),
+                                                   float(density_bias), float(rgb_padding), _p(_req(t, "t")),
+                                                   _p(_req(dirs, "dirs")), d_mod, int(white_bkgd), _p(comp), _p(dist),
+                                                   _p(acc), _p(w), _p(alb), _stream()), "act_composite_fwd")
+        ctx.save_for_backward(raw_rgb, raw_den, t, dirs)
+        ctx.cfg = (r, n, d_mod, int(white_bkgd), float(density_bias), float(rgb_padding))
+        return comp, dist, acc, w, alb
+
+    @staticmethod
+    @_amp_bwd
+    def backward(ctx, g_comp, g_dist, g_acc, g_w, g_alb):
+        raw_rgb, raw_den, t, dirs = ctx.saved_tensors
+        r, n, d_mod, white, bias, pad = ctx.cfg
+        d_raw_rgb = torch.empty_like(raw_rgb)
+        d_raw_den = torch.empty_like(raw_den)
+        cg = lambda g: None if g is None else g.contiguous()
+        g_comp, g_dist, g_acc, g_w, g_alb = cg(g_comp), cg(g_dist), cg(g_acc), cg(g_w), cg(g_alb)
+        with torch.cuda.device(raw_den.device):
+            check(_lib.lib().pnb_act_composite_bwd(r, n, raw_den.shape[1], _p(raw_rgb), _p(raw_den), bias, pad, _p(t),
+                                                   _p(dirs), d_mod, white, _p(g_comp), _p(g_dist), _p(g_acc), _p(g_w),
+                                                   _p(g_alb), _p(d_raw_rgb), _p(d_raw_den), _stream()),
+                  "act_composite_bwd")
+        return (d_raw_rgb, d_raw_den) + (None,) * 9
+
+
+def act_composite(raw_rgb, raw_den, t, dirs, white_bkgd, density_bias, rgb_padding, want_albedo, d_mod=0):
+    """raw_rgb [R*N,3], raw_den [R*N,C], t [R,N+1], dirs [R,3] (or [D,3] with d_mod=D) -> comp, distance, acc, weights,
+    albedos ([R*N,3] or None).  One launch when N <= 256 (the fused kernel), otherwise activations() + composite()."""
+    r, n = t.shape[0], t.shape[1] - 1
+    if n > 256 or os.environ.get("PNB_UNFUSED_ACT") == "1":
+        rgb, den, alb = activations(raw_rgb, raw_den, density_bias, rgb_padding, want_albedo)
+        comp, dist, acc, w = composite(rgb.view(r, n, 3), den.view(r, n), t, dirs, white_bkgd, d_mod=d_mod)
+        return comp, dist, acc, w, alb
+    return _ActComposite.apply(raw_rgb, raw_den, t, dirs, r, n, d_mod, int(bool(white_bkgd)), density_bias,
+                               rgb_padding, bool(want_albedo))
 
 
 class _Normals(torch.autograd.Function):

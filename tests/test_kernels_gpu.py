@@ -382,6 +382,53 @@ def test_adam_matches_torch():
     assert_close(p.cpu(), ref.detach(), 1e-6, "adam")
 
 
+@pytest.mark.parametrize("R,N,C,d_mod,white,want_alb", [(301, 64, 5, 0, False, True), (257, 10, 5, 10, False, False),
+                                                        (100, 128, 1, 0, True, False), (33, 256, 5, 0, False, True),
+                                                        (64, 7, 1, 0, False, False)])
+def test_act_composite_fused_is_bit_identical(R, N, C, d_mod, white, want_alb):
+    """pnb_act_composite_fwd/bwd (activations inside the compositing kernels) against the two-kernel sequence
+    pnb_act_fwd + pnb_composite_fwd / pnb_composite_bwd + pnb_act_bwd: every output and every gradient bit for bit,
+    and the forward against the oracle's compute_graph activations + volumetric_rendering."""
+    from panonerf_b200 import ops
+    g = torch.Generator().manual_seed(R * 1000 + N)
+    raw_rgb = (torch.randn(R * N, 3, generator=g) * 2).to(DEV)
+    raw_den = (torch.randn(R * N, C, generator=g) * 3).to(DEV)
+    raw_den[::7, 0] = 25.0                                      # the softplus threshold branch
+    t = torch.sort(torch.rand(R, N + 1, generator=g) * 6, dim=1).values.contiguous().to(DEV)
+    nd = d_mod if d_mod else R
+    dirs = torch.randn(nd, 3, generator=g).to(DEV)
+    gs = [torch.randn(R, 3, generator=g).to(DEV), torch.randn(R, generator=g).to(DEV),
+          torch.randn(R, generator=g).to(DEV), torch.randn(R, N, generator=g).to(DEV),
+          torch.randn(R * N, 3, generator=g).to(DEV)]
+
+    def run(fused):
+        a, b = raw_rgb.clone().requires_grad_(), raw_den.clone().requires_grad_()
+        if fused:
+            outs = ops.act_composite(a, b, t, dirs, white, -1.0, 0.001, want_alb, d_mod=d_mod)
+        else:
+            rgb, den, alb = ops.activations(a, b, -1.0, 0.001, want_alb)
+            outs = ops.composite(rgb.view(R, N, 3), den.view(R, N), t, dirs, white, d_mod=d_mod) + (alb,)
+        loss = sum((o * gg).sum() for o, gg in zip(outs, gs) if o is not None)
+        loss.backward()
+        return [o.detach() for o in outs if o is not None], a.grad, b.grad
+
+    of, ga_f, gb_f = run(True)
+    ou, ga_u, gb_u = run(False)
+    assert len(of) == len(ou) == (5 if want_alb else 4)
+    for x, y in zip(of, ou):
+        assert torch.equal(x, y)
+    assert torch.equal(ga_f, ga_u) and torch.equal(gb_f, gb_u)
+    # oracle: activations of compute_graph + volumetric_rendering
+    rgb_o = torch.nn.functional.softplus(raw_rgb.cpu()) * (1 + 2 * 0.001) - 0.001
+    den_o = torch.nn.functional.softplus(raw_den.cpu()[:, 0] - 1.0)
+    d_o = dirs.cpu() if not d_mod else dirs.cpu().repeat((R + d_mod - 1) // d_mod, 1)[:R]
+    comp, dist, acc, w = O.composite(rgb_o.view(R, N, 3), den_o.view(R, N, 1), t.cpu(), d_o, white)
+    assert_close(of[0].cpu(), comp, 2e-5, "comp_rgb")
+    assert_close(of[3].cpu(), w, 2e-5, "weights")
+    if want_alb:
+        assert_close(of[4].cpu(), torch.sigmoid(raw_den.cpu()[:, 1:4]) * 0.77 + 0.03, 1e-6, "albedo")
+
+
 def test_no_cpu_fallback():
     from panonerf_b200 import ops
     with pytest.raises(RuntimeError):
