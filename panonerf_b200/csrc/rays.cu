@@ -91,12 +91,23 @@ sample_cast_kernel(long long R, int N, const float* __restrict__ origins, int o_
   float* sm = sc_smem + (size_t)(threadIdx.x >> 5) * 6 * N;  // [3N means | 3N covs] of this warp's ray
   float* sv = sm + 3 * N;
   const long long warp0 = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
-  for (long long r = warp0; r < R; r += (long long)gridDim.x * (blockDim.x >> 5)) {
+  const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+  // The nine per-ray scalars of the NEXT ray are requested before the current ray is worked on: a warp otherwise starts
+  // every ray with a dependent ~700 ns load (ncu: long-scoreboard stalls dominated, 50 % occupancy could not hide them).
+  float nxt[9];
+  auto fetch = [&](long long r) {
     const long long rd = d_mod ? r % d_mod : r, ro = r / o_div;
     const long long rdir = dir_mod ? r % dir_mod : r;  // (sample_each_points_hemisp: one direction per ray)
-    const float nr = near_v[rd], fr = far_v[rd], rad = radii[rd];
-    const float o[3] = {origins[3 * ro], origins[3 * ro + 1], origins[3 * ro + 2]};
-    const float d[3] = {dirs[3 * rdir], dirs[3 * rdir + 1], dirs[3 * rdir + 2]};
+    nxt[0] = near_v[rd], nxt[1] = far_v[rd], nxt[2] = radii[rd];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) nxt[3 + k] = origins[3 * ro + k], nxt[6 + k] = dirs[3 * rdir + k];
+  };
+  if (warp0 < R) fetch(warp0);
+  for (long long r = warp0; r < R; r += wstride) {
+    const float nr = nxt[0], fr = nxt[1], rad = nxt[2];
+    const float o[3] = {nxt[3], nxt[4], nxt[5]};
+    const float d[3] = {nxt[6], nxt[7], nxt[8]};
+    if (r + wstride < R) fetch(r + wstride);
     const float* rnd = t_rand ? t_rand + (long long)rand_ld * r : nullptr;
     float* trow = t_out + r * (N + 1);
     const RayGeom geom = ray_geom(o, d, rad);

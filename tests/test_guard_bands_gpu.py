@@ -93,6 +93,41 @@ def test_guard_bands_sampling_compositing_resampling(R, N):
         assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("R,N,C,d_mod", [(37, 64, 5, 0), (1000, 12, 1, 0), (513, 128, 5, 0), (130, 256, 5, 0),
+                                         (770, 10, 5, 10)])
+def test_guard_bands_fused_activation_compositing(R, N, C, d_mod):
+    """pnb_act_composite_fwd / bwd: guard bands, no element left unwritten, bit-repeatable over three runs."""
+    from panonerf_b200 import _lib
+    lib = _lib.lib()
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    gen = torch.Generator().manual_seed(R * 1000 + N)
+    raw_rgb = (torch.randn(R * N, 3, generator=gen) * 2).to(DEV)
+    raw_den = (torch.randn(R * N, C, generator=gen) * 3).to(DEV)
+    t = torch.sort(torch.rand(R, N + 1, generator=gen) * 6, dim=1).values.contiguous().to(DEV)
+    d = torch.randn(d_mod if d_mod else R, 3, generator=gen).to(DEV)
+    want_alb = C >= 4
+    runs = []
+    for rep in range(3):
+        comp, dist, acc, w = Guarded((R, 3)), Guarded((R,)), Guarded((R,)), Guarded((R, N))
+        alb = Guarded((R * N, 3)) if want_alb else None
+        _call(lib.pnb_act_composite_fwd, R, N, C, _p(raw_rgb), _p(raw_den), -1.0, 0.001, _p(t), _p(d), d_mod, 0,
+              _p(comp.t), _p(dist.t), _p(acc.t), _p(w.t), _p(alb.t) if alb else None, st)
+        outs = [comp.check("comp"), dist.check("dist"), acc.check("acc"), w.check("weights")]
+        if alb:
+            outs.append(alb.check("albedo"))
+        g = [torch.rand(x.shape, generator=torch.Generator().manual_seed(3 + i)).to(DEV) for i, x in enumerate(outs)]
+        d_rgb, d_den = Guarded((R * N, 3)), Guarded((R * N, C))
+        _call(lib.pnb_act_composite_bwd, R, N, C, _p(raw_rgb), _p(raw_den), -1.0, 0.001, _p(t), _p(d), d_mod, 0,
+              _p(g[0]), _p(g[1]), _p(g[2]), _p(g[3]), _p(g[4]) if alb else None, _p(d_rgb.t), _p(d_den.t), st)
+        outs += [d_rgb.check("d_raw_rgb"), d_den.check("d_raw_den")]
+        if C == 5:
+            assert float(outs[-1][:, 4].abs().max()) == 0.0      # the roughness channel never reaches a loss
+        runs.append(outs)
+    for other in runs[1:]:
+        for a, b in zip(runs[0], other):
+            assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize("M", [1, 63, 64, 65, 4097])
 def test_guard_bands_encodings(M):
     from panonerf_b200 import _lib

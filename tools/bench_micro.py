@@ -13,18 +13,24 @@ sys.path.insert(0, ROOT)
 from panonerf_b200 import ops  # noqa: E402
 
 
-def timeit(fn, iters=10):
+def timeit(fn, groups=5, per_group=10):
+    """Median over `groups` of the mean device time of `per_group` back-to-back calls (CUDA events on the launching
+    stream).  One event pair per CALL would add the host-side cost of the Python wrapper (output allocation + ctypes,
+    20-40 us) to every sample - the device idles between the start event and the launch - which is a fifth of a 0.1 ms
+    kernel; back to back the host runs ahead of the device and only the first call of a group pays it.  Every buffer is
+    far larger than the 126 MB L2, so consecutive calls do not feed each other from cache."""
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
     ts = []
-    for _ in range(iters):
+    for _ in range(groups):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        fn()
+        for _ in range(per_group):
+            fn()
         e1.record()
         torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
+        ts.append(e0.elapsed_time(e1) / per_group)
     return sorted(ts)[len(ts) // 2]
 
 
