@@ -286,6 +286,19 @@ def run_ours(args):
                                                 "gpu_launches", "roofline", "step_tflops", "steps")}
         except Exception as e:                   # noqa: BLE001
             line["render"] = {"error": f"{type(e).__name__}: {e}"}
+        if rank == 0 and world == 1:
+            # the memory-bound stages alone against the HBM roofline (>= 0.7 of the copy bandwidth is the
+            # bar per kernel): tools/bench_micro.py, 16.8 M samples, CUDA events over back-to-back launches
+            try:
+                system = opt = None
+                torch.cuda.empty_cache()
+                sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools"))
+                import bench_micro
+                line["micro_kernels"] = {r["kernel"]: {"ms": round(r["ms"], 4), "GBps": round(r["algorithmic_GBps"], 1),
+                                                       "frac_of_hbm_roofline": round(r["frac_of_hbm_roofline"], 3)}
+                                         for r in bench_micro.run(24, dev, peaks()["hbm"])}
+            except Exception as e:               # noqa: BLE001
+                line["micro_kernels"] = {"error": f"{type(e).__name__}: {e}"}
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.cpu_rays)

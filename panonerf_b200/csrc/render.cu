@@ -156,7 +156,31 @@ composite_fwd_blocked_kernel(int R, int N, const float* __restrict__ rgb, const 
 #pragma unroll
     for (int k = 0; k <= K; ++k) tv[k] = (j0 + k <= N) ? tr[j0 + k] : 0.f;
     if (VEC) {  // N % 4 == 0 and K % 4 == 0: whole 16-byte groups are either inside or outside the ray
-      if (ACT && act.C != 1) {  // raw density is channel 0 of a [M,C] row
+      if (ACT && act.C == 5) {  // [M,5] rows: the 4 samples of a group are 20 contiguous floats = five 16-byte loads
+#pragma unroll
+        for (int k = 0; k < K; k += 4) {
+          float rw[20];
+          const bool in = j0 + k < N;
+#pragma unroll
+          for (int v = 0; v < 5; ++v) {
+            float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (in) q = *reinterpret_cast<const float4*>(density + (s0 + k) * 5 + 4 * v);
+            rw[4 * v] = q.x, rw[4 * v + 1] = q.y, rw[4 * v + 2] = q.z, rw[4 * v + 3] = q.w;
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) den[k + i] = rw[5 * i];
+          if (act.albedo != nullptr && in && ray_ok) {
+            float ab[12];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int q = 0; q < 3; ++q) ab[3 * i + q] = (1.f / (1.f + expf(-rw[5 * i + 1 + q]))) * 0.77f + 0.03f;
+            float4* o = reinterpret_cast<float4*>(act.albedo + 3 * (s0 + k));
+#pragma unroll
+            for (int v = 0; v < 3; ++v) o[v] = make_float4(ab[4 * v], ab[4 * v + 1], ab[4 * v + 2], ab[4 * v + 3]);
+          }
+        }
+      } else if (ACT && act.C != 1) {  // raw density is channel 0 of a [M,C] row
 #pragma unroll
         for (int k = 0; k < K; ++k) den[k] = (j0 + k < N) ? density[(s0 + k) * act.C] : 0.f;
       } else {
@@ -190,7 +214,7 @@ composite_fwd_blocked_kernel(int R, int N, const float* __restrict__ rgb, const 
           den[k] = softplus_f(den[k] + act.bias);
 #pragma unroll
           for (int q = 0; q < 3; ++q) col[3 * k + q] = softplus_f(col[3 * k + q]) * (1.f + 2.f * act.pad) - act.pad;
-          if (act.albedo != nullptr && ray_ok) {
+          if (act.albedo != nullptr && ray_ok && !(VEC && act.C == 5)) {  // (VEC, C = 5: written with the loads above)
             const float* ra = density + (s0 + k) * act.C + 1;
 #pragma unroll
             for (int q = 0; q < 3; ++q) act.albedo[3 * (s0 + k) + q] = (1.f / (1.f + expf(-ra[q]))) * 0.77f + 0.03f;
@@ -566,7 +590,7 @@ static int launch_composite_fwd(int R, int N, const float* rgb, const float* den
                                 const float* dirs, int d_mod, int white_bkgd, float* comp_rgb, float* distance,
                                 float* acc, float* weights, const ActArgs act, cudaStream_t st) {
   const bool vec = N % 4 == 0 && ((uintptr_t)rgb % 16 == 0) && ((uintptr_t)density % 16 == 0) &&
-                   ((uintptr_t)weights % 16 == 0);
+                   ((uintptr_t)weights % 16 == 0) && ((uintptr_t)act.albedo % 16 == 0);
   static const bool legacy = getenv("PNB_COMPOSITE_LEGACY") != nullptr;  // A/B experiments
 #define PNB_LAUNCH_COMPOSITE(K, L)                                                                                   \
   do {                                                                                                               \

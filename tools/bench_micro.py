@@ -34,16 +34,17 @@ def timeit(fn, groups=5, per_group=10):
     return sorted(ts)[len(ts) // 2]
 
 
-def main():
-    lg = int(sys.argv[1]) if len(sys.argv) > 1 else 24          # 16.8 M samples: every buffer >> 126 MB L2
+def run(lg=24, dev=None, peak=None):
+    """-> one dict per kernel: algorithmic bytes / device time against the measured copy bandwidth."""
     N = 64
     R = (1 << lg) // N
     M = R * N
-    dev = torch.device("cuda", 0)
-    peak = 6650.0
-    pp = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(pp):
-        peak = json.load(open(pp))["hbm_gbs"]
+    dev = dev or torch.device("cuda", 0)
+    if peak is None:
+        peak = 6650.0
+        pp = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pp):
+            peak = json.load(open(pp))["hbm_gbs"]
     g = torch.Generator(device=dev).manual_seed(0)
     means = (torch.rand(M, 3, device=dev, generator=g) * 10 - 5)
     covs = torch.rand(M, 3, device=dev, generator=g)
@@ -52,6 +53,7 @@ def main():
     vdir = torch.randn(M, 3, device=dev, generator=g)
     rgb = torch.rand(R, N, 3, device=dev, generator=g)
     den = -torch.log(torch.rand(R, N, device=dev, generator=g).clamp_min(1e-6))
+    raw_den5 = torch.randn(M, 5, device=dev, generator=g)
     t = torch.sort(torch.rand(R, N + 1, device=dev, generator=g) * 10, dim=1).values.contiguous()
     dirs = torch.nn.functional.normalize(torch.randn(R, 3, device=dev, generator=g), dim=-1)
     w = torch.rand(R, N, device=dev, generator=g)
@@ -66,16 +68,27 @@ def main():
         ("ipe_jvp(bf16 rows)", lambda: ops.ipe_jvp_into(means, covs, 0, 16, vdir, enc16), M * (36 + 192), M),
         ("sample_cast", lambda: ops.sample_cast(origins, dirs, radii, near, far, N), R * (36 + 4 * (N + 1) + 24 * N), M),
         ("composite_fwd", lambda: ops.composite(rgb, den, t, dirs, False), M * 24 + R * 36, M),
+        # activations inside the compositing kernel: raw heads in (12 + 4 C B / sample, C = 5), weights + albedos out
+        ("act_composite_fwd (C = 5, with albedos)",
+         lambda: ops.act_composite(rgb.view(M, 3), raw_den5, t, dirs, False, -1.0, 0.001, True), M * (12 + 20 + 4 + 4 + 12) + R * 36, M),
         ("resample", lambda: ops.resample(t, w, 0.01), M * 12 + R * 8, M),
         ("resample_cast (resample_along_rays in one launch)", lambda: ops.resample(t, w, 0.01, cast=(origins, dirs, radii)),
          M * 36 + R * (8 + 28), M),
     ]
+    out = []
     with torch.no_grad():
         for name, fn, nbytes, units in cases:
             ms = timeit(fn)
             gbs = nbytes / ms / 1e6
-            print(json.dumps({"kernel": name, "samples": units, "ms": ms, "algorithmic_GBps": gbs, "hbm_peak_GBps": peak,
-                              "frac_of_hbm_roofline": gbs / peak, "Gsamples_per_s": units / ms / 1e6}), flush=True)
+            out.append({"kernel": name, "samples": units, "ms": ms, "algorithmic_GBps": gbs, "hbm_peak_GBps": peak,
+                        "frac_of_hbm_roofline": gbs / peak, "Gsamples_per_s": units / ms / 1e6})
+    return out
+
+
+def main():
+    lg = int(sys.argv[1]) if len(sys.argv) > 1 else 24          # 16.8 M samples: every buffer >> 126 MB L2
+    for rec in run(lg):
+        print(json.dumps(rec), flush=True)
 
 
 if __name__ == "__main__":
