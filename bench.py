@@ -13,6 +13,7 @@ One JSON line is printed by rank 0.  `--impl reference` times the reference algo
 (oracle/ port of the pure-PyTorch reference; the upstream tree itself is not present on the GPU box).
 """
 import argparse
+import datetime
 import json
 import os
 import statistics
@@ -149,7 +150,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     torch.manual_seed(4 + rank)
     system = make_system(dev)
     opt = system.configure_optimizers()
@@ -274,8 +275,8 @@ def run_ours(args):
             line["c4"] = {"error": f"{type(e).__name__}: {e}", "traceback": traceback.format_exc()[-3000:]}
         graphed = None
         torch.cuda.empty_cache()
-        if rank == 0:
-            try:
+        if world == 1:                           # (single-process configuration; with more ranks its optimiser step
+            try:                                 # would enter an all-reduce the other ranks never join)
                 line["c1"] = measure_c1(dev)
             except Exception as e:               # noqa: BLE001
                 line["c1"] = {"error": f"{type(e).__name__}: {e}"}
@@ -388,7 +389,7 @@ def run_render(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     system = make_system(dev, num_samples=args.num_samples)
     H, W = args.render_hw
     line = measure_render(system, dev, world, rank, local, H, W, args.render_chunk, args.steps, args.warmup)

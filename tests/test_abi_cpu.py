@@ -162,3 +162,18 @@ def test_bench_roofline_report_schema():
     assert abs(r["mlp_stage"]["kernel_ms_per_step"] - 4.5) < 1e-9 and abs(r["mlp_stage"]["achieved"] - 2.5e3 / 4.5) < 1e-6
     assert abs(r["whole_step"]["achieved"] - 500.0) < 1e-6 and abs(r["whole_step"]["frac"] - 500.0 / 1382.0) < 1e-9
     assert r["algorithmic_bytes_per_step"] == 3e8 and r["designed_bytes_per_step"] == 12e9
+
+
+def test_bench_rank_conditional_work_has_no_collectives():
+    """bench.py: work that only some ranks do must not contain a collective.  The C1 line (MipNeRF step with its own
+    FlatAdam, whose step all-reduces when a process group exists) once ran on rank 0 alone and dead-locked every N > 1
+    run against the other ranks' render barrier."""
+    import ast
+    import os
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py")).read()
+    tree = ast.parse(src)
+    run = next(n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name == "run_ours")
+    guards = [ast.unparse(node.test) for node in ast.walk(run)
+              if isinstance(node, ast.If) and any(isinstance(c, ast.Call) and getattr(c.func, "id", "") == "measure_c1"
+                                                  for b in node.body for c in ast.walk(b))]
+    assert "world == 1" in guards, guards
