@@ -110,14 +110,33 @@ int pnb_composite_bwd(int R, int N, const float* rgb, const float* density, cons
  * density = softplus(raw_den[:,0] + density_bias) live in registers only; albedo (nullable, [R*N,3], needs C >= 4)
  * receives sigmoid(raw_den[:,1:4]) 0.77 + 0.03.  Results are bit-identical to pnb_act_fwd + pnb_composite_fwd
  * (N <= 256) and pnb_composite_bwd + pnb_act_bwd.  d_raw_den is [R*N,C]: channel 0 = density, 1..3 = g_albedo through
- * the sigmoid (zero when g_albedo is null), the rest zero. */
+ * the sigmoid (zero when g_albedo is null), the rest zero.  d_t (nullable, [R,N+1]) receives the gradient w.r.t. the
+ * fence-posts (delta_i and t_mid_i of mip.py:456-462, the clamp of :476): `stop_resample_grad = False`. */
 int pnb_act_composite_fwd(int R, int N, int C, const float* raw_rgb, const float* raw_den, float density_bias,
                           float rgb_padding, const float* t, const float* dirs, int d_mod, int white_bkgd,
                           float* comp_rgb, float* distance, float* acc, float* weights, float* albedo, void* stream);
 int pnb_act_composite_bwd(int R, int N, int C, const float* raw_rgb, const float* raw_den, float density_bias,
                           float rgb_padding, const float* t, const float* dirs, int d_mod, int white_bkgd,
                           const float* g_comp, const float* g_dist, const float* g_acc, const float* g_weights,
-                          const float* g_albedo, float* d_raw_rgb, float* d_raw_den, void* stream);
+                          const float* g_albedo, float* d_raw_rgb, float* d_raw_den, float* d_t, void* stream);
+
+/* ---- `stop_resample_grad = False` (models/mip.py:336-350: the fine level's loss reaches the coarse weights) ----------
+ * pnb_ipe_cov_hess: d_covs = (d enc / d cov)^T d_enc (d_enc nullable); with h_enc (= d raw_sigma / d enc, the
+ *   Jacobian sweep's output, fp32) and d_v (= dL/d v, v = J_ipe^T h_enc) also the explicit second-order terms of the
+ *   density-gradient normals, d_v * d v / d mean into d_means and d_v * d v / d cov into d_covs (the ReLU network is
+ *   piece-wise linear in enc: what autograd through vmap(jacrev), pano_mip_nerf.py:295-302, adds for them).
+ *   accumulate != 0: += into d_means / d_covs (either may be null).
+ * pnb_cast_rays_bwd: d_t[R,N+1] (+)= (d means / d t)^T g_means + (d covs / d t)^T g_covs  (mip.py:67-89, cone).
+ * pnb_resample_bwd: d_weights[R,N] = (d new_t / d weights)^T g_new_t through the lerp, min(1, cumsum), the
+ *   normalisation (incl. the 1e-5 padding branch) and the blur-pool maxima, with torch's tie rules; same t / weights /
+ *   padding / blur_pool / u arguments as the forward call. */
+int pnb_ipe_cov_hess(int M, const float* means, const float* covs, int min_deg, int max_deg, const void* d_enc, int ld,
+                     int dtype, const float* h_enc, int ldh, const float* d_v, float* d_means, float* d_covs,
+                     int accumulate, void* stream);
+int pnb_cast_rays_bwd(int R, int N, const float* t, const float* directions, const float* radii, const float* g_means,
+                      const float* g_covs, float* d_t, int accumulate, void* stream);
+int pnb_resample_bwd(int R, int N, const float* t, const float* weights, float padding, int blur_pool, const float* u,
+                     int u_ld, const float* g_new_t, float* d_weights, void* stream);
 
 /* ---- K7  hierarchical resampling: models/mip.py:304-352 (blur-pool) + 240-301 (PDF/CDF/searchsorted/lerp) --
  * u: [N+1] when u_ld==0 (deterministic linspace(0,1-eps,N+1)) or [R,N+1] (u_ld=N+1, randomized).

@@ -234,9 +234,14 @@ def pdf_sample(bins, weights, num_samples: int, randomized: bool, u=None, return
     return (out, inds, cdf) if return_aux else out
 
 
-def resample_along_rays(origins, directions, radii, t, weights, randomized, padding, u=None):
-    """models/mip.py:304-352 with stop_grad=True (the only mode the configs use, *.yaml `stop_resample_grad`)."""
-    with torch.no_grad():
+def resample_along_rays(origins, directions, radii, t, weights, randomized, padding, u=None, stop_grad=True):
+    """models/mip.py:304-352.  stop_grad=True is what the configs use (*.yaml `stop_resample_grad`); with False the
+    new fence-posts stay on the tape (the else branch, mip.py:336-350): the fine level's loss reaches the coarse weights
+    through the CDF inversion."""
+    if stop_grad:
+        with torch.no_grad():
+            new_t = pdf_sample(t, blur_weights(weights, padding), t.shape[-1], randomized, u)
+    else:
         new_t = pdf_sample(t, blur_weights(weights, padding), t.shape[-1], randomized, u)
     return new_t, cast_cone(new_t, origins, directions, radii)
 
@@ -494,7 +499,8 @@ def mipnerf_forward(sd, rays: Rays, cfg, randomized=False, white_bkgd=False, use
                                                rand.get("t_rand"))
         else:
             t, (mean, cov) = resample_along_rays(rays.origins, rays.directions, rays.radii, t, w, randomized,
-                                                 cfg["resample_padding"], rand.get("u"))
+                                                 cfg["resample_padding"], rand.get("u"),
+                                                 cfg.get("stop_resample_grad", True))
         f = radiance_field(sd, mean, cov, rays.viewdirs, cfg)
         comp, dist, acc, w = composite(f["rgb"], f["density"], t, rays.directions, white_bkgd)
         if lvl == 1 and use_ort_loss:
@@ -519,7 +525,8 @@ def panonerf_forward(sd, rays: Rays, env: Rays, cfg, randomized=False, white_bkg
                                                rand.get("t_rand"))
         else:
             t, (mean, cov) = resample_along_rays(rays.origins, rays.directions, rays.radii, t, w, randomized,
-                                                 cfg["resample_padding"], rand.get("u"))
+                                                 cfg["resample_padding"], rand.get("u"),
+                                                 cfg.get("stop_resample_grad", True))
         f = radiance_field(sd, mean, cov, rays.viewdirs, cfg)
         comp, dist, acc, w = composite(f["rgb"], f["density"], t, rays.directions, white_bkgd)
         normal = surf = albedo = diffuse = ort = shading = None

@@ -363,6 +363,122 @@ __global__ void ipe_vjp_kernel(long long M, int min_deg, int L, const float* __r
   }
 }
 
+// ---- stop_resample_grad = False (models/mip.py:336-350): gradients w.r.t. the Gaussians' variances and fence-posts ----
+// sin(y), cos(y), sin(z), cos(z) for y = mean * 2^sh with phase `ph` and z = fl32(y + fl32(pi/2)) = y + pi/2 + eps
+__device__ __forceinline__ void sincos_pair_phase(float y, uint32_t ph, float* sy, float* cy, float* sz, float* cz) {
+  float sn, cs;
+  sincos_phase(ph, &sn, &cs);
+  const float z = y + kHalfPiF;
+  const float bb = z - y;
+  const float err = (y - (z - bb)) + (kHalfPiF - bb);
+  const float eps = 4.37113900018624283e-8f - err;
+  const float ce = fmaf(-0.5f * eps, eps, 1.0f);
+  const float se = eps * fmaf(-0.16666667f * eps, eps, 1.0f);
+  *sy = sn, *cy = cs;
+  *sz = cs * ce - sn * se;     // sin(y + pi/2 + eps) = cos(y + eps)
+  *cz = -(sn * ce + cs * se);  // cos(y + pi/2 + eps) = -sin(y + eps)
+}
+
+// One thread per (sample, component).  With e = exp(-0.5 cov 4^l), enc_s = e sin(y), enc_c = e sin(z):
+//   d enc / d cov = -0.5 4^l enc                                    -> d_covs  = sum_l -0.5 4^l e (g_s sin y + g_c sin z)
+// and, when `h` (= d raw_sigma / d enc from the Jacobian sweep) and `dv` (= dL/d v, v = J_ipe^T h the un-normalised
+// density gradient) are given, the explicit dependence of v on the Gaussian (the ReLU network is piece-wise linear in
+// enc, so h is locally constant and the only second derivatives are the encoding's own):
+//   d v_c / d mean_c = sum_l -4^l e (h_s sin y + h_c sin z),   d v_c / d cov_c = sum_l -0.5 4^l 2^l e (h_s cos y + h_c cos z)
+// d_means / d_covs: `accumulate` != 0 adds into the destination.
+template <typename T>
+__global__ void ipe_cov_hess_kernel(long long M, int min_deg, int L, const float* __restrict__ means,
+                                    const float* __restrict__ covs, const T* __restrict__ g, int ldg,
+                                    const float* __restrict__ h, int ldh, const float* __restrict__ dv,
+                                    float* __restrict__ d_means, float* __restrict__ d_covs, int accumulate) {
+  const int F = 3 * L;
+  const long long total = M * 3;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long m = idx / 3;
+    const int c = (int)(idx - m * 3);
+    const float mean = means[idx], cov = covs[idx];
+    uint32_t hi, lo;
+    phase_fixed(mean, &hi, &lo);
+    float acc_c = 0.f, acc_hm = 0.f, acc_hc = 0.f;
+    for (int l = 0; l < L; ++l) {
+      const float sc = exp2f((float)(min_deg + l)), sc2 = sc * sc;
+      const float e = expf(-0.5f * (cov * sc2));
+      if (e == 0.f) break;
+      float sy, cy, sz, cz;
+      sincos_pair_phase(mean * sc, __funnelshift_l(lo, hi, min_deg + l), &sy, &cy, &sz, &cz);
+      if (g != nullptr) {
+        const float gs = to_f32<T>(g[m * ldg + 3 * l + c]), gc = to_f32<T>(g[m * ldg + F + 3 * l + c]);
+        acc_c += (-0.5f * sc2) * (e * (gs * sy + gc * sz));
+      }
+      if (h != nullptr) {
+        const float hs = h[m * ldh + 3 * l + c], hc = h[m * ldh + F + 3 * l + c];
+        acc_hm += -sc2 * (e * (hs * sy + hc * sz));
+        acc_hc += (-0.5f * sc2 * sc) * (e * (hs * cy + hc * cz));
+      }
+    }
+    float dm = 0.f, dc = acc_c;
+    if (h != nullptr) {
+      const float w = dv[idx];
+      dm = w * acc_hm, dc += w * acc_hc;
+    }
+    if (d_means != nullptr) d_means[idx] = accumulate ? d_means[idx] + dm : dm;
+    if (d_covs != nullptr) d_covs[idx] = accumulate ? d_covs[idx] + dc : dc;
+  }
+}
+
+// Backward of cast_rays (models/mip.py:67-89, 36-58, 8-22) w.r.t. the fence-posts: one warp per ray.
+//   mean_k = o_k + d_k t_mean,  cov_k = t_var d_k^2 + r_var (1 - d_k^2 / |d|^2)   with mu = (t0+t1)/2, hw = (t1-t0)/2
+__global__ void __launch_bounds__(256)
+cast_rays_bwd_kernel(long long R, int N, const float* __restrict__ t, const float* __restrict__ dirs,
+                     const float* __restrict__ radii, const float* __restrict__ g_means,
+                     const float* __restrict__ g_covs, float* __restrict__ d_t, int accumulate) {
+  extern __shared__ float cb_smem[];
+  const int lane = threadIdx.x & 31;
+  float* s0 = cb_smem + (size_t)(threadIdx.x >> 5) * 2 * N;  // dL/dt0 of sample i
+  float* s1 = s0 + N;                                        // dL/dt1 of sample i
+  const long long warp0 = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  for (long long r = warp0; r < R; r += (long long)gridDim.x * (blockDim.x >> 5)) {
+    const float d[3] = {dirs[3 * r], dirs[3 * r + 1], dirs[3 * r + 2]};
+    const float rad = radii[r];
+    const RayGeom geom = ray_geom(d, d, rad);  // (origins do not enter the derivative)
+    const float* tr = t + r * (N + 1);
+    for (int i = lane; i < N; i += 32) {
+      const float t0 = tr[i], t1 = tr[i + 1];
+      const float mu = (t0 + t1) / 2.f, hw = (t1 - t0) / 2.f;
+      const float mu2 = mu * mu, hw2 = hw * hw, hw3 = hw2 * hw, hw4 = hw2 * hw2;
+      const float A = 3.f * mu2 + hw2, iA = 1.f / A, iA2 = iA * iA, iA3 = iA2 * iA;
+      const float B = hw4 * (12.f * mu2 - hw2);
+      const float tm_mu = 1.f + 2.f * hw2 * iA - 12.f * mu2 * hw2 * iA2;
+      const float tm_hw = 4.f * mu * hw * iA - 4.f * mu * hw3 * iA2;
+      const float k415 = (float)(4.0 / 15.0);
+      const float tv_mu = -k415 * (24.f * mu * hw4 * iA2 - 12.f * B * mu * iA3);
+      const float tv_hw = 2.f * hw * (float)(1.0 / 3.0) - k415 * ((48.f * mu2 * hw3 - 6.f * hw4 * hw) * iA2 - 4.f * B * hw * iA3);
+      const float rv_mu = geom.rad2 * (mu / 2.f + k415 * (6.f * mu * hw4 * iA2));
+      const float rv_hw = geom.rad2 * ((float)(5.0 / 6.0) * hw - k415 * (4.f * hw3 * iA - 2.f * hw4 * hw * iA2));
+      const float* gm = g_means + 3 * (r * N + i);
+      const float* gc = g_covs + 3 * (r * N + i);
+      float G_tm = 0.f, G_tv = 0.f, G_rv = 0.f;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        if (g_means != nullptr) G_tm += gm[k] * geom.d[k];
+        if (g_covs != nullptr) G_tv += gc[k] * geom.dd[k], G_rv += gc[k] * geom.perp[k];
+      }
+      const float g_mu = G_tm * tm_mu + G_tv * tv_mu + G_rv * rv_mu;
+      const float g_hw = G_tm * tm_hw + G_tv * tv_hw + G_rv * rv_hw;
+      s0[i] = 0.5f * (g_mu - g_hw);
+      s1[i] = 0.5f * (g_mu + g_hw);
+    }
+    __syncwarp();
+    float* dt = d_t + r * (N + 1);
+    for (int j = lane; j <= N; j += 32) {
+      const float g = (j < N ? s0[j] : 0.f) + (j > 0 ? s1[j - 1] : 0.f);
+      dt[j] = accumulate ? dt[j] + g : g;
+    }
+    __syncwarp();
+  }
+}
+
 template <typename T>
 __global__ void ipe_jvp_kernel(long long M, int min_deg, int L, const float* __restrict__ means,
                                const float* __restrict__ covs, const float* __restrict__ v, T* __restrict__ out,
@@ -624,6 +740,40 @@ extern "C" int pnb_ipe_vjp(int M, const float* means, const float* covs, int min
   else
     ipe_vjp_kernel<float><<<grid, 256, 0, st>>>(M, min_deg, L, means, covs, (const float*)d_enc, ld, d_means);
   return finish("ipe_vjp");
+}
+
+extern "C" int pnb_ipe_cov_hess(int M, const float* means, const float* covs, int min_deg, int max_deg,
+                                const void* d_enc, int ld, int dtype, const float* h_enc, int ldh, const float* d_v,
+                                float* d_means, float* d_covs, int accumulate, void* stream) {
+  int L = max_deg - min_deg;
+  PNB_REQUIRE(M >= 0 && L > 0 && min_deg >= 0 && max_deg <= 31, "ipe_cov_hess: degrees must lie in [0, 31]");
+  PNB_REQUIRE((d_enc == nullptr || ld >= 6 * L) && (h_enc == nullptr || (ldh >= 6 * L && d_v != nullptr)),
+              "ipe_cov_hess: bad row strides / missing d_v");
+  PNB_REQUIRE(d_enc != nullptr || h_enc != nullptr, "ipe_cov_hess: nothing to do");
+  if (M == 0) return 0;
+  int grid = grid_for((long long)M * 3, 256);
+  cudaStream_t st = as_stream(stream);
+  if (dtype == PNB_BF16)
+    ipe_cov_hess_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(M, min_deg, L, means, covs, (const __nv_bfloat16*)d_enc, ld,
+                                                             h_enc, ldh, d_v, d_means, d_covs, accumulate);
+  else
+    ipe_cov_hess_kernel<float><<<grid, 256, 0, st>>>(M, min_deg, L, means, covs, (const float*)d_enc, ld, h_enc, ldh,
+                                                     d_v, d_means, d_covs, accumulate);
+  return finish("ipe_cov_hess");
+}
+
+extern "C" int pnb_cast_rays_bwd(int R, int N, const float* t, const float* directions, const float* radii,
+                                 const float* g_means, const float* g_covs, float* d_t, int accumulate, void* stream) {
+  PNB_REQUIRE(R >= 0 && N > 0 && t && directions && radii && d_t && (g_means || g_covs), "cast_rays_bwd: bad arguments");
+  if (R == 0) return 0;
+  const size_t smem = (size_t)8 * 2 * N * sizeof(float);
+  PNB_REQUIRE(smem <= 200 * 1024, "cast_rays_bwd: N too large");
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(cast_rays_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int grid = grid_for((long long)R * 32, 256, 4);
+  cast_rays_bwd_kernel<<<grid, 256, smem, as_stream(stream)>>>(R, N, t, directions, radii, g_means, g_covs, d_t,
+                                                              accumulate);
+  return finish("cast_rays_bwd");
 }
 
 extern "C" int pnb_ipe_jvp(int M, const float* means, const float* covs, int min_deg, int max_deg, const float* v,

@@ -292,7 +292,8 @@ composite_bwd_kernel(long long R, int N, const float* __restrict__ rgb, const fl
                      const float* __restrict__ t, const float* __restrict__ dirs, int d_mod, int white_bkgd,
                      const float* __restrict__ g_comp, const float* __restrict__ g_dist,
                      const float* __restrict__ g_acc, const float* __restrict__ g_w, float* __restrict__ d_rgb,
-                     float* __restrict__ d_density, const ActArgs act, const float* __restrict__ g_alb) {
+                     float* __restrict__ d_density, const ActArgs act, const float* __restrict__ g_alb,
+                     float* __restrict__ d_t) {
   extern __shared__ float smem[];
   const bool atten = (white_bkgd & PNB_COMPOSITE_ATTENUATE) != 0;
   white_bkgd &= PNB_COMPOSITE_WHITE_BKGD;
@@ -371,6 +372,13 @@ composite_bwd_kernel(long long R, int N, const float* __restrict__ rgb, const fl
       float incl = warp_scan_incl(q, lane);
       float excl = tail + incl - q;
       tail += __shfl_sync(0xffffffffu, incl, 31);
+      if (ok && d_t != nullptr) {
+        // dL/d t (stop_resample_grad = False): sd_i = sigma_i (t_{i+1} - t_i) |d| and the distance's t_mid_i
+        const float sig = ACT ? softplus_f(density[(r * N + i) * act.C] + act.bias) : density[r * N + i];
+        const float ds = (sT[i] - excl) * (sig * dnorm), dm = 0.5f * (gd * sW[i]);
+        sQ[i] = dm - ds;  // share of t_i      (this lane has consumed sQ[i] above; sW[i] is not read again)
+        sW[i] = dm + ds;  // share of t_{i+1}
+      }
       if (ok) {
         const float dd = (sT[i] - excl) * ((tr[i + 1] - tr[i]) * dnorm);
         if (ACT) {
@@ -391,6 +399,19 @@ composite_bwd_kernel(long long R, int N, const float* __restrict__ rgb, const fl
       }
     }
     __syncwarp();
+    if (d_t != nullptr) {
+      float* dt = d_t + r * (N + 1);
+      for (int j = lane; j <= N; j += 32) {
+        float g = (j < N ? sQ[j] : 0.f) + (j > 0 ? sW[j - 1] : 0.f);
+        // torch.clamp(dist, t_0, t_N) hands the gradient to the bound that clips
+        if (g_dist != nullptr && !pass && (j == 0 || j == N)) {
+          if (j == 0 && dnum < tr[0]) g += g_dist[r];
+          if (j == N && dnum > tr[N]) g += g_dist[r];
+        }
+        dt[j] = g;
+      }
+      __syncwarp();
+    }
   }
 }
 
@@ -404,19 +425,29 @@ composite_bwd_kernel(long long R, int N, const float* __restrict__ rgb, const fl
 //     strided layout i = L + 32 k reproduces that order exactly (checked against torch.sum on the host for every N
 //     the tests use; N < 8 takes ATen's scalar path: 4 interleaved scalar accumulators);
 //   * torch.cumsum on the CPU accumulates in double and rounds every prefix to fp32: the scan runs in fp64.
-template <int KMAX>
+//
+// BWD = true is the backward pass of the same function for `stop_resample_grad = False` (the else branch of
+// models/mip.py:336-350): the forward quantities (blur, sum, pdf, cdf, indices) are recomputed exactly as above, then
+// `g_t` = dL/d new_t [R,N+1] (arriving through `new_t`) is pulled back through the lerp onto the two gathered cdf
+// entries (shared-memory atomics), through min(1, cumsum) (suffix sums; torch's tie rule of `minimum`: half at
+// equality), the normalisation (with the 1e-5 padding branch) and the blur-pool's maxima (torch.maximum: the larger
+// operand takes the gradient, ties split) into dL/d weights [R,N] (written to `d_weights`).  Bins and u carry no gradient.
+template <int KMAX, bool BWD>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 resample_kernel(long long R, int N, const float* __restrict__ t, const float* __restrict__ weights, float padding,
                 int blur_pool, const float* __restrict__ u, int u_ld, float* __restrict__ new_t,
                 long long* __restrict__ inds_out, const float* __restrict__ origins, const float* __restrict__ dirs,
-                const float* __restrict__ radii, float* __restrict__ means, float* __restrict__ covs, int stage_cast) {
+                const float* __restrict__ radii, float* __restrict__ means, float* __restrict__ covs, int stage_cast,
+                float* __restrict__ d_weights) {
   extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int stride = 3 * N + 4 + (stage_cast ? 6 * N : 0);
+  const int stride = 3 * N + 4 + (stage_cast ? 6 * N : 0) + (BWD ? 2 * N + 4 : 0);
   float* sa = smem + (size_t)wib * stride;  // raw weights, later the cdf (N+1 entries)
   float* sp = sa + N + 1;                   // blurred weights, then the pdf, then the new fence-posts (N+1)
   float* sb = sp + N + 1;                   // bins (t), N+1 entries
   float* sg = sb + N + 2;                   // staged Gaussians [3N | 3N] (16-byte aligned: the stride is a multiple of 4)
+  float* sdc = sb + N + 2;                  // BWD: dL/d cdf (N+1), later dL/d (blurred weight) (N)
+  float* smk = sdc + N + 2;                 // BWD: pass factor of min(1, cumsum) per cdf entry (N+1)
   const int K = (N + 31) >> 5;              // samples per lane
   const int vec = N >> 3, ilp = vec >> 2;   // ATen: 8-float vectors, 4 interleaved accumulators
   const bool ragged = (N & 31) != 0;
@@ -501,9 +532,16 @@ resample_kernel(long long R, int N, const float* __restrict__ t, const float* __
 #pragma unroll
       for (int j = 0; j < KMAX; ++j) {
         const int i = lane * K + j;
-        if (j < K && i < N) sa[i] = i == 0 ? 0.f : fminf(1.f, (float)(base + e[j]));
+        if (j < K && i < N) {
+          const float pre = (float)(base + e[j]);
+          sa[i] = i == 0 ? 0.f : fminf(1.f, pre);
+          if (BWD) smk[i] = i == 0 ? 0.f : (pre < 1.f ? 1.f : (pre == 1.f ? 0.5f : 0.f)), sdc[i] = 0.f;
+        }
       }
-      if (lane == 0) sa[N] = 1.f;
+      if (lane == 0) {
+        sa[N] = 1.f;
+        if (BWD) smk[N] = 0.f, sdc[N] = 0.f;
+      }
     }
     __syncwarp();
     // searchsorted(cdf, u, right=True): lane owns Q consecutive outputs; u is sorted along a ray (linspace, or the
@@ -536,6 +574,17 @@ resample_kernel(long long R, int N, const float* __restrict__ t, const float* __
         if (den < 1e-5f) den = 1.f;
         const float frac = (uj - c0) / den;
         const float b0 = sb[below], b1 = sb[above];
+        if (BWD) {
+          const float g = new_t[r * (N + 1) + j] * (b1 - b0);  // (`new_t` carries dL/d new_t in this mode)
+          if (c1 - c0 < 1e-5f) {
+            atomicAdd(&sdc[below], -g);
+          } else {
+            const float inv2 = 1.f / (den * den);
+            atomicAdd(&sdc[below], g * (uj - c1) * inv2);
+            atomicAdd(&sdc[above], -(g * (uj - c0)) * inv2);
+          }
+          continue;
+        }
         const float nt = b0 + frac * (b1 - b0);
         new_t[r * (N + 1) + j] = nt;
         sp[j] = nt;
@@ -543,6 +592,70 @@ resample_kernel(long long R, int N, const float* __restrict__ t, const float* __
       }
     }
     __syncwarp();
+    if (BWD) {
+      // dL/d pdf_k = sum_{i = k+1}^{N-1} gcdf_i (cdf_i = sum_{k < i} pdf_k, i = 1..N-1), gcdf = dL/d cdf * pass factor
+      double sfx[KMAX];
+      double run = 0.0;
+#pragma unroll
+      for (int j = KMAX - 1; j >= 0; --j) {
+        const int i = lane * K + j;  // entry i contributes to pdf_k, k < i
+        sfx[j] = run;                // sum of the lane's entries above i
+        if (j < K && i < N) run += (double)(sdc[i] * smk[i]);
+      }
+      // exclusive suffix over the lanes: lanes above this one
+      double incl = run;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double n = __shfl_down_sync(0xffffffffu, incl, o);
+        if (lane + o < 32) incl += n;
+      }
+      const double above_lanes = incl - run;
+      float dpdf[KMAX];
+      float dot = 0.f, tot = 0.f;
+#pragma unroll
+      for (int j = 0; j < KMAX; ++j) {
+        const int k = lane * K + j;
+        dpdf[j] = 0.f;
+        if (j < K && k < N) {
+          dpdf[j] = (float)(above_lanes + sfx[j]);  // entries i > k (entry k itself belongs to pdf_{k-1} and below)
+          dot += dpdf[j] * sp[k];
+          tot += dpdf[j];
+        }
+      }
+      dot = warp_sum(dot), tot = warp_sum(tot);
+      __syncwarp();  // every lane has read its dL/d cdf entries: the array is re-used for dL/d (blurred weight)
+      const float sub = pad > 0.f ? tot / (float)N : dot;  // (pad > 0: weights' = w + (eps - S) / N, sum' = eps)
+#pragma unroll
+      for (int j = 0; j < KMAX; ++j) {
+        const int k = lane * K + j;
+        if (j < K && k < N) sdc[k] = (dpdf[j] - sub) / wsum;
+      }
+      __syncwarp();
+      float* dw = d_weights + r * N;
+      for (int i = lane; i < N; i += 32) {
+        if (!blur_pool) {
+          dw[i] = sdc[i];
+          continue;
+        }
+        // blur[i] = .5 (wm[i] + wm[i+1]), wm[k] = max(w[max(k-1,0)], w[min(k,N-1)]), k = 0..N
+        auto dwm = [&](int k) { return 0.5f * ((k >= 1 ? sdc[k - 1] : 0.f) + (k <= N - 1 ? sdc[k] : 0.f)); };
+        const float wi = wr[i];
+        float g = 0.f;
+        if (i == 0) g += dwm(0);
+        else {
+          const float wl = wr[i - 1];
+          g += (wi > wl ? 1.f : (wi == wl ? 0.5f : 0.f)) * dwm(i);
+        }
+        if (i == N - 1) g += dwm(N);
+        else {
+          const float wn = wr[i + 1];
+          g += (wi > wn ? 1.f : (wi == wn ? 0.5f : 0.f)) * dwm(i + 1);
+        }
+        dw[i] = g;
+      }
+      __syncwarp();
+      continue;
+    }
     if (means != nullptr) {  // cast_rays on the new fence-posts (models/mip.py:351, 67-89)
       const float o[3] = {origins[3 * r], origins[3 * r + 1], origins[3 * r + 2]};
       const float d[3] = {dirs[3 * r], dirs[3 * r + 1], dirs[3 * r + 2]};
@@ -655,7 +768,7 @@ extern "C" int pnb_composite_bwd(int R, int N, const float* rgb, const float* de
   int grid = grid_for((long long)R * 32, kWarpsPerBlock * 32, 4);
   composite_bwd_kernel<false><<<grid, kWarpsPerBlock * 32, smem, as_stream(stream)>>>(
       R, N, rgb, density, t, dirs, d_mod, white_bkgd, g_comp, g_dist, g_acc, g_weights, d_rgb, d_density,
-      ActArgs{1, 0.f, 0.f, nullptr}, nullptr);
+      ActArgs{1, 0.f, 0.f, nullptr}, nullptr, nullptr);
   return finish("composite_bwd");
 }
 
@@ -663,9 +776,11 @@ extern "C" int pnb_act_composite_bwd(int R, int N, int C, const float* raw_rgb, 
                                      float density_bias, float rgb_padding, const float* t, const float* dirs,
                                      int d_mod, int white_bkgd, const float* g_comp, const float* g_dist,
                                      const float* g_acc, const float* g_weights, const float* g_albedo,
-                                     float* d_raw_rgb, float* d_raw_den, void* stream) {
+                                     float* d_raw_rgb, float* d_raw_den, float* d_t, void* stream) {
   PNB_REQUIRE(R >= 0 && N > 0 && d_mod >= 0 && C >= 1 && (g_albedo == nullptr || C >= 4),
               "act_composite_bwd: bad sizes (albedo needs C >= 4)");
+  PNB_REQUIRE(d_t == nullptr || (white_bkgd & PNB_COMPOSITE_ATTENUATE) == 0,
+              "act_composite_bwd: no fence-post gradient with the attenuation flag");
   if (R == 0) return 0;
   size_t smem = (size_t)kWarpsPerBlock * 3 * N * sizeof(float);
   PNB_REQUIRE(smem <= 200 * 1024, "act_composite_bwd: N too large for the per-warp shared-memory staging");
@@ -674,7 +789,7 @@ extern "C" int pnb_act_composite_bwd(int R, int N, int C, const float* raw_rgb, 
   int grid = grid_for((long long)R * 32, kWarpsPerBlock * 32, 4);
   composite_bwd_kernel<true><<<grid, kWarpsPerBlock * 32, smem, as_stream(stream)>>>(
       R, N, raw_rgb, raw_den, t, dirs, d_mod, white_bkgd, g_comp, g_dist, g_acc, g_weights, d_raw_rgb, d_raw_den,
-      ActArgs{C, density_bias, rgb_padding, nullptr}, g_albedo);
+      ActArgs{C, density_bias, rgb_padding, nullptr}, g_albedo, d_t);
   return finish("act_composite_bwd");
 }
 
@@ -685,11 +800,37 @@ static int launch_resample(int R, int N, const float* t, const float* weights, f
   const int stage = means != nullptr && N % 4 == 0 && ((uintptr_t)means % 16 == 0) && ((uintptr_t)covs % 16 == 0);
   const size_t smem = (size_t)kWarpsPerBlock * (3 * N + 4 + (stage ? 6 * N : 0)) * sizeof(float);
   if (smem > 48 * 1024)
-    cudaFuncSetAttribute(resample_kernel<KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(resample_kernel<KMAX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int grid = grid_for((long long)R * 32, kWarpsPerBlock * 32, 4);
-  resample_kernel<KMAX><<<grid, kWarpsPerBlock * 32, smem, st>>>(R, N, t, weights, padding, blur_pool, u, u_ld, new_t,
-                                                                inds, origins, dirs, radii, means, covs, stage);
+  resample_kernel<KMAX, false><<<grid, kWarpsPerBlock * 32, smem, st>>>(
+      R, N, t, weights, padding, blur_pool, u, u_ld, new_t, inds, origins, dirs, radii, means, covs, stage, nullptr);
   return finish("resample");
+}
+
+template <int KMAX>
+static int launch_resample_bwd(int R, int N, const float* t, const float* weights, float padding, int blur_pool,
+                               const float* u, int u_ld, const float* g_new_t, float* d_weights, cudaStream_t st) {
+  const size_t smem = (size_t)kWarpsPerBlock * (3 * N + 4 + 2 * N + 4) * sizeof(float);
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(resample_kernel<KMAX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int grid = grid_for((long long)R * 32, kWarpsPerBlock * 32, 4);
+  resample_kernel<KMAX, true><<<grid, kWarpsPerBlock * 32, smem, st>>>(
+      R, N, t, weights, padding, blur_pool, u, u_ld, const_cast<float*>(g_new_t), nullptr, nullptr, nullptr, nullptr,
+      nullptr, nullptr, 0, d_weights);
+  return finish("resample_bwd");
+}
+
+extern "C" int pnb_resample_bwd(int R, int N, const float* t, const float* weights, float padding, int blur_pool,
+                                const float* u, int u_ld, const float* g_new_t, float* d_weights, void* stream) {
+  PNB_REQUIRE(R >= 0 && N > 0 && N <= 256 && (u_ld == 0 || u_ld >= N + 1), "resample_bwd: need 0 < N <= 256");
+  PNB_REQUIRE(t && weights && u && g_new_t && d_weights, "resample_bwd: null argument");
+  if (R == 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  const int k = (N + 31) / 32;
+  if (k <= 1) return launch_resample_bwd<1>(R, N, t, weights, padding, blur_pool, u, u_ld, g_new_t, d_weights, st);
+  if (k <= 2) return launch_resample_bwd<2>(R, N, t, weights, padding, blur_pool, u, u_ld, g_new_t, d_weights, st);
+  if (k <= 4) return launch_resample_bwd<4>(R, N, t, weights, padding, blur_pool, u, u_ld, g_new_t, d_weights, st);
+  return launch_resample_bwd<8>(R, N, t, weights, padding, blur_pool, u, u_ld, g_new_t, d_weights, st);
 }
 
 extern "C" int pnb_resample_cast(int R, int N, const float* t, const float* weights, float padding, int blur_pool,

@@ -517,6 +517,27 @@ def _use_fused(cfg, P) -> bool:
             and not (cfg["with_normals"] and cfg.get("jac_precision") == "fp32"))
 
 
+def _gaussian_grads(ctx, means, covs, cfg, d_enc, d_v):
+    """Gradients w.r.t. the Gaussians from dL/d enc (`d_enc`, [M,6L]): the means' (env branch: surface point ->
+    distance; stop_resample_grad=False: the resampled fence-posts) and, only with stop_resample_grad=False, the
+    variances'.  When the normals feed the loss (`d_v` = dL/d v given) their explicit dependence on the Gaussian
+    through the encoding's Jacobian is added (pnb_ipe_cov_hess; `ctx.g_keep` = d sigma / d enc of the forward)."""
+    if d_enc is None:
+        return None, None
+    d_means = ops.ipe_vjp(means, covs, cfg["min_deg"], cfg["max_deg"], d_enc)
+    d_covs = None
+    if ctx.need_covs:
+        d_covs = torch.empty_like(d_means)
+        ops.ipe_cov_hess(means, covs, cfg["min_deg"], cfg["max_deg"], d_enc=d_enc, d_covs=d_covs)
+    if ctx.g_keep is not None and d_v is not None:
+        h = ctx.g_keep if ctx.g_keep.dtype == torch.float32 else ctx.g_keep.float()
+        ops.ipe_cov_hess(means, covs, cfg["min_deg"], cfg["max_deg"], h_enc=h, d_v=d_v, d_means=d_means,
+                         d_covs=d_covs, accumulate=True)
+    ctx.g_keep = None
+    return (d_means.view(ctx.means_shape) if ctx.need_means else None,
+            d_covs.view(ctx.means_shape) if d_covs is not None else None)
+
+
 class _Field(torch.autograd.Function):
     """(means, covs, venc, *params) -> (raw_rgb [M,3], raw_den [M,C], n_raw [M,3] | None)."""
 
@@ -569,8 +590,12 @@ class _Field(torch.autograd.Function):
                 masks = fused_masks(M, dev, True) if need_bwd else None
                 raw_den, raw_rgb = fused_forward(enc, vb, S, C, pack, acts, g_enc, masks, need_bwd, vb_mod=vmod)
             n_raw, jac = None, None
+            g_keep = None
             if cfg["with_normals"]:
                 v = ops.ipe_vjp(means2, covs2, cfg["min_deg"], cfg["max_deg"], g_enc)
+                # stop_resample_grad=False: the Gaussians are on the tape and the normals depend on them explicitly
+                # through the encoding's Jacobian; d sigma / d enc is then needed again in the backward
+                g_keep = g_enc if (need_bwd and (means.requires_grad or covs.requires_grad)) else None
                 del g_enc
                 n_raw = torch.empty(M, 3, device=dev, dtype=f32)
                 with torch.cuda.device(dev):
@@ -581,6 +606,8 @@ class _Field(torch.autograd.Function):
             ctx.cfg = cfg
             ctx.n_params = len(params)
             ctx.need_means = means.requires_grad
+            ctx.need_covs = covs.requires_grad
+            ctx.g_keep = g_keep
             ctx.means_shape = means.shape
             if need_bwd:
                 if vmod:                         # the backward's view-direction weight gradient is per ray
@@ -653,6 +680,7 @@ class _Field(torch.autograd.Function):
             jb.dgrad(a[0], jb.w("layers.0.0.weight"), g_enc, accum=not first)
             del hs_j
             v = ops.ipe_vjp(means2, covs2, cfg["min_deg"], cfg["max_deg"], g_enc)
+            g_keep = g_enc if (means.requires_grad or covs.requires_grad) else None
             del g_enc
             n_raw = torch.empty(M, 3, device=dev, dtype=f32)
             with torch.cuda.device(dev):
@@ -663,6 +691,8 @@ class _Field(torch.autograd.Function):
         ctx.cfg = cfg
         ctx.n_params = len(params)
         ctx.need_means = means.requires_grad
+        ctx.need_covs = covs.requires_grad
+        ctx.g_keep = g_keep if cfg["with_normals"] else None
         ctx.means_shape = means.shape
         # raw buffers are kept on ctx (not save_for_backward): they are private to this Function and never
         # modified in place afterwards
@@ -713,6 +743,7 @@ class _Field(torch.autograd.Function):
         d_raw_rgb = torch.zeros(M, 3, device=dev, dtype=f32) if d_raw_rgb is None else d_raw_rgb.contiguous()
 
         # ---- adjoint of the Jacobian sweep (second-order terms of the normals) -------------------------------
+        d_v = None
         if B["jac"] is not None and d_n_raw is not None:
             a, v = B["jac"]
             d_n_raw = d_n_raw.contiguous()
@@ -738,7 +769,7 @@ class _Field(torch.autograd.Function):
             wb.add(q, depth - 1, 256, u, 0, 16, scratch, G["density_layer.weight"][0])
 
         # ---- dgrad chain ------------------------------------------------------------------------------------
-        need_enc = ctx.need_means
+        need_enc = ctx.need_means or ctx.need_covs
         d_enc = torch.empty(M, xyz, device=dev, dtype=f32) if need_enc else None
         dz = fused_backward(M, C, pack, d_raw_rgb, d_raw_den, masks, d_enc)
         dzv = dz[0][:, :hv.shape[1]]
@@ -764,17 +795,15 @@ class _Field(torch.autograd.Function):
         G["density_layer.weight"].add_(tmp_d[:, :C].t())
         dvb = _group_sum(dzv, S)
         f32be.wgrad(dvb, venc, G["view_layers.0.0.weight"][:, width:])
-        d_means = None
-        if need_enc:
-            d_means = ops.ipe_vjp(means, covs, cfg["min_deg"], cfg["max_deg"], d_enc).view(ctx.means_shape)
+        d_means, d_covs = _gaussian_grads(ctx, means, covs, cfg, d_enc if need_enc else None, d_v)
         ctx.bufs = None
         if direct:
-            return (d_means, None, None, None, None) + (None,) * ctx.n_tape_params
+            return (d_means, d_covs, None, None, None) + (None,) * ctx.n_tape_params
         if ctx.n_tape_params == 0:                   # off-tape parameters lost their flat views mid-step: fold
             for nme, p_ in zip(names, ctx.params):
                 p_.grad = G[nme] if p_.grad is None else p_.grad + G[nme]
-            return (d_means, None, None, None, None)
-        return (d_means, None, None, None, None) + tuple(G[n] for n in names)
+            return (d_means, d_covs, None, None, None)
+        return (d_means, d_covs, None, None, None) + tuple(G[n] for n in names)
 
     @staticmethod
     @_amp_bwd
@@ -807,6 +836,7 @@ class _Field(torch.autograd.Function):
         d_raw_rgb = torch.zeros(M, 3, device=dev, dtype=f32) if d_raw_rgb is None else d_raw_rgb.contiguous()
 
         # ---- adjoint of the Jacobian sweep (second-order terms of the normals) -------------------------------
+        d_v = None
         if B["jac"] is not None and d_n_raw is not None:
             a, v = B["jac"]
             d_n_raw = d_n_raw.contiguous()
@@ -879,7 +909,7 @@ class _Field(torch.autograd.Function):
         del pad, d_bott
 
         # ---- trunk -------------------------------------------------------------------------------------------
-        need_enc = ctx.need_means
+        need_enc = ctx.need_means or ctx.need_covs
         d_enc = torch.zeros(M, xyz, device=dev, dtype=f32) if need_enc else None
         for i in range(depth - 1, -1, -1):
             wname = f"layers.{i}.0.weight"
@@ -902,11 +932,9 @@ class _Field(torch.autograd.Function):
                 nxt = torch.empty(M, width, device=dev, dtype=dt)
                 be.dgrad(dz, be.w(wname), nxt, mask=x_prev, colsum_out=prev_bias)
             dz = nxt
-        d_means = None
-        if need_enc:
-            d_means = ops.ipe_vjp(means, covs, cfg["min_deg"], cfg["max_deg"], d_enc).view(ctx.means_shape)
+        d_means, d_covs = _gaussian_grads(ctx, means, covs, cfg, d_enc if need_enc else None, d_v)
         ctx.bufs = None
-        return (d_means, None, None, None, None) + tuple(G[n] for n in names)
+        return (d_means, d_covs, None, None, None) + tuple(G[n] for n in names)
 
 
 def radiance_field(means, covs, venc, params: Dict[str, torch.Tensor], *, precision: str, samples_per_ray: int,

@@ -58,12 +58,20 @@ def sorted_piecewise_constant_pdf(bins, weights, num_samples, randomized, u=None
 
 def resample_along_rays(origins, directions, radii, t_samples, weights, randomized, ray_shape, stop_grad,
                         resample_padding, u=None, return_inds=False):
-    """models/mip.py:304-352.  Only `stop_grad=True` (configs/*.yaml `stop_resample_grad: True`) is implemented."""
+    """models/mip.py:304-352.  `stop_grad=True` (configs/*.yaml `stop_resample_grad: True`) runs off the tape; with
+    False the new fence-posts and Gaussians carry the gradient back to `weights` (ops.resample_cast_grad)."""
     _check_shape(ray_shape)
-    if not stop_grad:
-        raise NotImplementedError("gradient through the resampling step (stop_resample_grad=False) is not implemented")
     f = ops._f32c
-    t_samples, weights = f(t_samples), f(weights)
+    if not stop_grad and weights.requires_grad and torch.is_grad_enabled():
+        if return_inds:
+            raise NotImplementedError("return_inds is a test hook of the stop_grad=True path")
+        t_samples, weights = f(t_samples.detach()), f(weights)
+        if randomized and u is None:
+            u = stratified_u(weights.shape[0], t_samples.shape[-1], weights.device)
+        new_t, means, covs = ops.resample_cast_grad(t_samples, weights, resample_padding, u if randomized else None,
+                                                    f(origins), f(directions), f(radii))
+        return new_t, (means, covs)
+    t_samples, weights = f(t_samples.detach()), f(weights.detach())
     if randomized and u is None:
         u = stratified_u(weights.shape[0], t_samples.shape[-1], weights.device)
     res = ops.resample(t_samples, weights, resample_padding, u=u if randomized else None, return_inds=return_inds,

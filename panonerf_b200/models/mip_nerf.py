@@ -120,7 +120,8 @@ class _NerfBase(torch.nn.Module):
         if lvl == 0:
             return mip.sample_along_rays(rays.origins, rays.directions, rays.radii, self.num_samples, rays.near,
                                          rays.far, randomized, self.disparity, self.ray_shape)
-        return mip.resample_along_rays(rays.origins, rays.directions, rays.radii, t, weights.detach(), randomized,
+        return mip.resample_along_rays(rays.origins, rays.directions, rays.radii, t,
+                                       weights.detach() if self.stop_resample_grad else weights, randomized,
                                        self.ray_shape, self.stop_resample_grad,
                                        resample_padding=self.resample_padding)
 

@@ -184,6 +184,64 @@ def resample(t, weights, padding: float, u=None, return_inds=False, blur_pool=Tr
     return out if len(out) > 1 else new_t
 
 
+class _ResampleCast(torch.autograd.Function):
+    """resample_along_rays with stop_grad=False (the else branch of models/mip.py:336-350): blur-pool + PDF sampling +
+    cast_rays in one launch; the backward pulls the gradients of the new fence-posts (direct, and through the
+    Gaussians: pnb_cast_rays_bwd) back to the coarse weights (pnb_resample_bwd).  Bins, origins, directions, radii and
+    the uniform draws receive no gradient (upstream's bins are the coarse fence-posts, which are off the tape)."""
+
+    @staticmethod
+    @_amp_fwd
+    def forward(ctx, weights, t, padding, u, origins, directions, radii):
+        new_t, means, covs = resample(t, weights, padding, u=u, cast=(origins, directions, radii))
+        ctx.save_for_backward(weights, t, u if u is not None else torch.empty(0, device=t.device), new_t, directions,
+                              radii)
+        ctx.cfg = (float(padding), u is not None)
+        return new_t, means, covs
+
+    @staticmethod
+    @_amp_bwd
+    def backward(ctx, g_t, g_means, g_covs):
+        weights, t, u, new_t, directions, radii = ctx.saved_tensors
+        padding, has_u = ctx.cfg
+        r, n = weights.shape
+        dev = weights.device
+        cg = lambda g: None if g is None else g.contiguous()
+        g_t, g_means, g_covs = cg(g_t), cg(g_means), cg(g_covs)
+        if g_t is None and g_means is None and g_covs is None:
+            return (None,) * 7
+        g_total = g_t.clone() if g_t is not None else torch.zeros(r, n + 1, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            if g_means is not None or g_covs is not None:
+                check(_lib.lib().pnb_cast_rays_bwd(r, n, _p(new_t), _p(directions), _p(radii), _p(g_means), _p(g_covs),
+                                                   _p(g_total), 1, _stream()), "cast_rays_bwd")
+            d_w = torch.empty_like(weights)
+            uu, u_ld = (u, n + 1) if has_u else (linspace_u(n + 1, dev), 0)
+            check(_lib.lib().pnb_resample_bwd(r, n, _p(t), _p(weights), padding, 1, _p(uu), u_ld, _p(g_total), _p(d_w),
+                                              _stream()), "resample_bwd")
+        return d_w, None, None, None, None, None, None
+
+
+def resample_cast_grad(t, weights, padding, u, origins, directions, radii):
+    """Differentiable (w.r.t. `weights`) resample_along_rays: -> new_t, means, covs."""
+    return _ResampleCast.apply(_req(weights, "weights"), _req(t, "t"), padding, u, _req(origins, "origins"),
+                               _req(directions, "directions"), _req(radii, "radii"))
+
+
+def ipe_cov_hess(means, covs, min_deg, max_deg, d_enc=None, h_enc=None, d_v=None, d_means=None, d_covs=None,
+                 accumulate=False):
+    """pnb_ipe_cov_hess: the variance gradient of the encoding and the explicit second-order terms of the
+    density-gradient normals (include/panonerf_b200.h)."""
+    m = means.numel() // 3
+    any_rows = d_enc if d_enc is not None else h_enc
+    with torch.cuda.device(means.device):
+        check(_lib.lib().pnb_ipe_cov_hess(m, _p(means), _p(covs), min_deg, max_deg, _p(d_enc),
+                                          d_enc.stride(0) if d_enc is not None else 0,
+                                          dt_code(d_enc.dtype) if d_enc is not None else dt_code(any_rows.dtype),
+                                          _p(h_enc), h_enc.stride(0) if h_enc is not None else 0, _p(d_v), _p(d_means),
+                                          _p(d_covs), int(accumulate), _stream()), "ipe_cov_hess")
+
+
 def hdr_to_ldr(x, quantize=False):
     x = _req(x, "x")
     out = torch.empty_like(x)
@@ -332,21 +390,25 @@ class _ActComposite(torch.autograd.Function):
         r, n, d_mod, white, bias, pad = ctx.cfg
         d_raw_rgb = torch.empty_like(raw_rgb)
         d_raw_den = torch.empty_like(raw_den)
+        # fence-post gradient: only with stop_resample_grad=False (the resampled t is then on the tape)
+        d_t = torch.empty_like(t) if ctx.needs_input_grad[2] else None
         cg = lambda g: None if g is None else g.contiguous()
         g_comp, g_dist, g_acc, g_w, g_alb = cg(g_comp), cg(g_dist), cg(g_acc), cg(g_w), cg(g_alb)
         with torch.cuda.device(raw_den.device):
             check(_lib.lib().pnb_act_composite_bwd(r, n, raw_den.shape[1], _p(raw_rgb), _p(raw_den), bias, pad, _p(t),
                                                    _p(dirs), d_mod, white, _p(g_comp), _p(g_dist), _p(g_acc), _p(g_w),
-                                                   _p(g_alb), _p(d_raw_rgb), _p(d_raw_den), _stream()),
+                                                   _p(g_alb), _p(d_raw_rgb), _p(d_raw_den), _p(d_t), _stream()),
                   "act_composite_bwd")
-        return (d_raw_rgb, d_raw_den) + (None,) * 9
+        return (d_raw_rgb, d_raw_den, d_t) + (None,) * 8
 
 
 def act_composite(raw_rgb, raw_den, t, dirs, white_bkgd, density_bias, rgb_padding, want_albedo, d_mod=0):
     """raw_rgb [R*N,3], raw_den [R*N,C], t [R,N+1], dirs [R,3] (or [D,3] with d_mod=D) -> comp, distance, acc, weights,
     albedos ([R*N,3] or None).  One launch when N <= 256 (the fused kernel), otherwise activations() + composite()."""
     r, n = t.shape[0], t.shape[1] - 1
-    if n > 256 or os.environ.get("PNB_UNFUSED_ACT") == "1":
+    if t.requires_grad and n > 256:
+        raise NotImplementedError("stop_resample_grad=False needs the fused activation + compositing kernels (N <= 256)")
+    if (n > 256 or os.environ.get("PNB_UNFUSED_ACT") == "1") and not t.requires_grad:
         rgb, den, alb = activations(raw_rgb, raw_den, density_bias, rgb_padding, want_albedo)
         comp, dist, acc, w = composite(rgb.view(r, n, 3), den.view(r, n), t, dirs, white_bkgd, d_mod=d_mod)
         return comp, dist, acc, w, alb

@@ -119,7 +119,8 @@ def ops_fixture(ns):
     print("ops.npz", len(out), "arrays")
 
 
-def model_fixture(ns, name, pano, width, b, n, h, w, sd_from_seed=None, store_grads=True, gslice=64):
+def model_fixture(ns, name, pano, width, b, n, h, w, sd_from_seed=None, store_grads=True, gslice=64,
+                  stop_resample_grad=True):
     out = {}
     c2w = camera(rot_seed=1)
     ds, rays = ref_rays(ns, h, w, c2w)
@@ -131,7 +132,8 @@ def model_fixture(ns, name, pano, width, b, n, h, w, sd_from_seed=None, store_gr
     torch.manual_seed(4)
     cls = ns.pano_mip_nerf.PanoMipNeRF if pano else ns.mip_nerf.MipNeRF
     model = cls(num_samples=n, rgb_activation="softplus", rgb_padding=0.0, mlp_net_width=width,
-                mlp_num_density_channels=5 if pano else 1, num_env_samples=10)
+                mlp_num_density_channels=5 if pano else 1, num_env_samples=10,
+                stop_resample_grad=stop_resample_grad)
     if sd_from_seed is not None:
         sd = O.synth_state_dict(seed=sd_from_seed, width=width, c_density=5 if pano else 1)
         model.mlp.load_state_dict(sd)
@@ -142,7 +144,7 @@ def model_fixture(ns, name, pano, width, b, n, h, w, sd_from_seed=None, store_gr
         for k, v in model.mlp.state_dict().items():
             out["sd/" + k] = npy(v)
     out.update(c2w=c2w, hw=np.array([h, w]), perm=npy(perm), gt=npy(gt), n=np.array(n), width=np.array(width),
-               env_radius=np.array(float(ds.radii)))
+               env_radius=np.array(float(ds.radii)), stop_resample_grad=np.array(int(stop_resample_grad)))
     if pano:
         res = model(rays=r, env_rays=env32, randomized=False, white_bkgd=False, enable_surf=True, use_ort_loss=True)
         loss = O.panonerf_loss(res, r, gt)
@@ -297,7 +299,11 @@ def main():
     assert rh.available(), "reference tree not found"
     torch.set_num_threads(8)
     ns = rh.load()
-    which = set(sys.argv[1:]) or {"ops", "small", "resample", "c1", "c2s", "variants"}
+    which = set(sys.argv[1:]) or {"ops", "small", "resample", "c1", "c2s", "variants", "rg"}
+    if "rg" in which:
+        # stop_resample_grad=False (models/mip.py:336-350): the fine level's loss reaches the coarse weights
+        model_fixture(ns, "mipnerf_w64_rg.npz", False, 64, 24, 16, 8, 16, stop_resample_grad=False)
+        model_fixture(ns, "panonerf_w64_rg.npz", True, 64, 24, 16, 8, 16, stop_resample_grad=False)
     if "variants" in which:
         variants_fixture(ns)
     if "ops" in which:

@@ -116,15 +116,36 @@ def test_guard_bands_fused_activation_compositing(R, N, C, d_mod):
         if alb:
             outs.append(alb.check("albedo"))
         g = [torch.rand(x.shape, generator=torch.Generator().manual_seed(3 + i)).to(DEV) for i, x in enumerate(outs)]
-        d_rgb, d_den = Guarded((R * N, 3)), Guarded((R * N, C))
+        d_rgb, d_den, d_t = Guarded((R * N, 3)), Guarded((R * N, C)), Guarded((R, N + 1))
         _call(lib.pnb_act_composite_bwd, R, N, C, _p(raw_rgb), _p(raw_den), -1.0, 0.001, _p(t), _p(d), d_mod, 0,
-              _p(g[0]), _p(g[1]), _p(g[2]), _p(g[3]), _p(g[4]) if alb else None, _p(d_rgb.t), _p(d_den.t), st)
+              _p(g[0]), _p(g[1]), _p(g[2]), _p(g[3]), _p(g[4]) if alb else None, _p(d_rgb.t), _p(d_den.t),
+              _p(d_t.t) if rep != 1 else None, st)          # (the fence-post gradient is optional)
         outs += [d_rgb.check("d_raw_rgb"), d_den.check("d_raw_den")]
         if C == 5:
             assert float(outs[-1][:, 4].abs().max()) == 0.0      # the roughness channel never reaches a loss
+        if rep != 1:
+            outs.append(d_t.check("d_t"))
         runs.append(outs)
     for other in runs[1:]:
-        for a, b in zip(runs[0], other):
+        for a, b in zip(runs[0], other):           # (run 1 has no d_t: zip stops at the shorter list)
+            assert torch.equal(a, b)
+    # resample backward + cast_rays backward of the same shapes
+    if d_mod == 0:
+        from panonerf_b200 import ops
+        w = runs[0][3]
+        o = torch.zeros(R, 3, device=DEV)
+        rad = torch.full((R, 1), 0.003, device=DEV)
+        gm, gc = torch.rand(R, N, 3, device=DEV), torch.rand(R, N, 3, device=DEV)
+        res = []
+        for rep in range(2):
+            dt2, dw = Guarded((R, N + 1)), Guarded((R, N))
+            dt2.t.zero_()
+            _call(lib.pnb_cast_rays_bwd, R, N, _p(t), _p(d), _p(rad), _p(gm), _p(gc), _p(dt2.t), 1, st)
+            gt2 = dt2.check("cast_rays_bwd d_t")
+            _call(lib.pnb_resample_bwd, R, N, _p(t), _p(w), 0.01, 1, _p(ops.linspace_u(N + 1, torch.device(DEV, 0))), 0,
+                  _p(gt2), _p(dw.t), st)
+            res.append([gt2, dw.check("resample_bwd d_weights")])
+        for a, b in zip(res[0], res[1]):
             assert torch.equal(a, b)
 
 

@@ -223,9 +223,13 @@ def test_resample_bit_exact_indices(golden_ops):
     wb = O.blur_weights(T(g["rs_w"]), 0.01).to(DEV)
     out = mip.sorted_piecewise_constant_pdf(T(g["rs_t"]).to(DEV), wb, 17, True, u=T(g["rs_u_r"]).to(DEV))
     assert_close(out.cpu(), T(g["rs_new_t_r"]), 1e-5, "new_t_r")
-    with pytest.raises(NotImplementedError):
-        mip.resample_along_rays(r.origins, r.directions, r.radii, T(g["rs_t"]).to(DEV), T(g["rs_w"]).to(DEV), False,
-                                "cone", False, 0.01)
+    # stop_grad=False: same values, and the weights receive a gradient (tests/test_resample_grad_gpu.py checks it)
+    wg = T(g["rs_w"]).to(DEV).requires_grad_()
+    nt2, (m2, c2) = mip.resample_along_rays(r.origins, r.directions, r.radii, T(g["rs_t"]).to(DEV), wg, False, "cone",
+                                            False, 0.01)
+    assert torch.equal(nt2.detach(), new_t) and nt2.requires_grad and m2.requires_grad and c2.requires_grad
+    (nt2.sum() + m2.sum()).backward()
+    assert wg.grad is not None and bool(torch.isfinite(wg.grad).all()) and float(wg.grad.abs().max()) > 0
 
 
 @pytest.mark.parametrize("n", [64, 128, 256])

@@ -27,6 +27,8 @@ def build(g, pano, precision):
     hp = default_hparams("panonerf" if pano else "mipnerf", precision=precision)
     hp.update({"nerf.num_samples": int(g["n"]), "nerf.mlp.net_width": width, "train.randomized": False,
                "loss.ort_loss": 0.1})
+    if "stop_resample_grad" in g:
+        hp["nerf.stop_resample_grad"] = bool(int(g["stop_resample_grad"]))
     system = (PanoNeRFSystem if pano else MipNeRFSystem)(hp).to(DEV)
     system.mip_nerf.mlp.load_state_dict(golden_state_dict(g))
     rays, env = golden_rays(g, DEV)
@@ -44,7 +46,8 @@ def run(system, rays, gt, pano):
 
 
 @pytest.mark.parametrize("name,pano", [("mipnerf_w64.npz", False), ("panonerf_w64.npz", True),
-                                       ("mipnerf_w256.npz", False), ("panonerf_w256.npz", True)])
+                                       ("mipnerf_w256.npz", False), ("panonerf_w256.npz", True),
+                                       ("mipnerf_w64_rg.npz", False), ("panonerf_w64_rg.npz", True)])
 def test_fp32_parity_with_reference(name, pano):
     g = load_golden(name)
     system, rays, gt = build(g, pano, "fp32")
@@ -67,7 +70,7 @@ def test_fp32_parity_with_reference(name, pano):
     rays_c, env_c = golden_rays(g)
     r64 = O.Rays(*[x.double() for x in rays_c])
     e64 = O.Rays(*[x.double() for x in env_c])
-    cfg = dict(num_samples=int(g["n"]))
+    cfg = dict(num_samples=int(g["n"]))          # (the forward values do not depend on stop_resample_grad)
     truth = (O.panonerf_forward(sd64, r64, e64, cfg) if pano else O.mipnerf_forward(sd64, r64, cfg, use_ort_loss=True))[0]
     for nm in ("normal", "shading", "surface_rgb", "ort_loss"):
         key = f"out/1/{nm}"
@@ -93,6 +96,34 @@ def test_fp32_parity_with_reference(name, pano):
             ref = T(g["gslice/" + k])
             got = p.grad.cpu().reshape(-1)[:: max(1, p.numel() // 64)][:64]
             assert float((got - ref).norm()) <= 2e-3 * max(float(ref.norm()), 1e-9), k
+
+
+def test_stop_resample_grad_false_on_the_tensor_core_path():
+    """stop_resample_grad=False through the fused bf16 kernels (MipNeRF, first-order loss): the gradient agrees with
+    the fp32 parity path of the same configuration (cosine >= 0.99 per tensor), differs from the stop_grad=True
+    gradient (the feature is live), and a PanoMipNeRF step with normals + surface runs and stays finite."""
+    g = load_golden("mipnerf_w256.npz")
+    grads = {}
+    for prec, sg in (("fp32", False), ("bf16", False), ("bf16", True)):
+        system, rays, gt = build(g, False, prec)
+        system.hparams["loss.ort_loss"] = 0.0
+        system.mip_nerf.stop_resample_grad = sg
+        loss = system.training_step((rays, gt))
+        loss.backward()
+        grads[(prec, sg)] = {k: p.grad.detach().float().clone() for k, p in system.mip_nerf.mlp.named_parameters()}
+    flat = lambda d: torch.cat([v.flatten() for v in d.values()])
+    for k in grads[("fp32", False)]:
+        a, b = grads[("fp32", False)][k].flatten(), grads[("bf16", False)][k].flatten()
+        cos = float(torch.dot(a, b) / (a.norm() * b.norm() + 1e-30))
+        assert cos >= 0.99, (k, cos)
+    live = float((flat(grads[("bf16", False)]) - flat(grads[("bf16", True)])).norm() / flat(grads[("bf16", True)]).norm())
+    assert live > 1e-4, live
+    gp = load_golden("panonerf_w256.npz")
+    system, rays, gt = build(gp, True, "bf16")
+    system.mip_nerf.stop_resample_grad = False
+    loss = system.training_step((rays, gt))
+    loss.backward()
+    assert all(bool(torch.isfinite(p.grad).all()) for p in system.mip_nerf.mlp.parameters())
 
 
 @pytest.mark.parametrize("name,pano", [("mipnerf_w256.npz", False), ("panonerf_w256.npz", True)])

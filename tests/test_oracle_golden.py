@@ -73,13 +73,15 @@ def test_surface_and_tonemap(golden_ops):
 
 
 @pytest.mark.parametrize("name,pano", [("mipnerf_w64.npz", False), ("panonerf_w64.npz", True),
-                                       ("mipnerf_w256.npz", False), ("panonerf_w256.npz", True)])
+                                       ("mipnerf_w256.npz", False), ("panonerf_w256.npz", True),
+                                       ("mipnerf_w64_rg.npz", False), ("panonerf_w64_rg.npz", True)])
 def test_models_forward_loss_grads(name, pano):
     g = load_golden(name)
     sd = {k: v.clone().requires_grad_() for k, v in golden_state_dict(g).items()}
     rays, env = golden_rays(g)
     env = O.Rays(*[x.float() for x in env])
-    cfg = dict(num_samples=int(g["n"]))
+    # (`*_rg`: the reference ran with stop_resample_grad=False, models/mip.py:336-350)
+    cfg = dict(num_samples=int(g["n"]), stop_resample_grad=bool(int(g["stop_resample_grad"])) if "stop_resample_grad" in g else True)
     if pano:
         out, _ = O.panonerf_forward(sd, rays, env, cfg, train=True)
         names = ["comp_rgb", "distance", "ort_loss", "normal", "albedo", "roughness", "surface_rgb", "diffuse", "shading"]
