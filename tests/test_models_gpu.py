@@ -264,10 +264,12 @@ def test_optimizer_step_decreases_loss():
     assert not torch.equal(system.mip_nerf.mlp.state_dict()["layers.0.0.weight"].cpu(), sd0["layers.0.0.weight"])
 
 
-def test_cuda_graph_step_equals_eager_step():
+@pytest.mark.parametrize("stop_resample_grad", [True, False])
+def test_cuda_graph_step_equals_eager_step(stop_resample_grad):
     """GraphedTrainStep replays the eager step: same losses and same parameters after 2 steps
     (deterministic sampling, so both runs see identical inputs; the learning-rate schedule advances through the
-    device-side hyper-parameter tensor)."""
+    device-side hyper-parameter tensor).  Also with the gradient through the resampling (its backward kernels must be
+    capturable: no host synchronisation)."""
     from panonerf_b200 import _lib
     if not _lib.lib().pnb_tc_available():
         pytest.skip("not an sm_100 device")
@@ -282,7 +284,7 @@ def test_cuda_graph_step_equals_eager_step():
     results = []
     for use_graph in (False, True):
         hp = default_hparams("panonerf", precision="bf16")
-        hp.update({"nerf.num_samples": 32, "train.randomized": False})
+        hp.update({"nerf.num_samples": 32, "train.randomized": False, "nerf.stop_resample_grad": stop_resample_grad})
         system = PanoNeRFSystem(hp).to(DEV)
         system.mip_nerf.mlp.load_state_dict(sd)
         rays = generate_rays(h, w, c2w, 0.0, 10.0, torch.device(DEV, 0))
@@ -309,8 +311,10 @@ def test_cuda_graph_step_equals_eager_step():
     # same kernels in the same order; the only freedom left is the order of the float atomics in the head-bias sums,
     # so two steps agree to rounding noise (the network's second-order terms amplify it over longer runs)
     assert l0[0] == l1[0], (l0, l1)
-    assert abs(l0[1] - l1[1]) <= 2e-5 * abs(l0[1]), (l0, l1)
-    assert float((p0 - p1).norm() / p0.norm()) < 1e-5
+    # (with the gradient through the resampling the shared-memory float atomics of its backward add one more
+    # order-dependent sum, and the second-order terms of the normals amplify it)
+    assert abs(l0[1] - l1[1]) <= (2e-5 if stop_resample_grad else 2e-4) * abs(l0[1]), (l0, l1)
+    assert float((p0 - p1).norm() / p0.norm()) < (1e-5 if stop_resample_grad else 1e-4)
 
 
 def test_graphed_steps_then_render_sees_current_weights():

@@ -1,0 +1,2 @@
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_models_gpu.py -x -q -m gpu -k "cuda_graph" > gpurun_out/tests_one.log 2>&1; echo "pytest exit $?"; grep -E "^E  |FAILED|passed|failed|Error" gpurun_out/tests_one.log | head -20
