@@ -153,8 +153,8 @@ static int launch_gemm(int mode, long long M, int N, long long K, const void* A,
 static int check_gemm_args(int mode, long long M, int N, long long K, const float* bias, const float* row_bias,
                            int row_group, const void* mask_src, int flags) {
   PNB_REQUIRE(mode >= 0 && mode <= 2 && M >= 0 && N > 0 && K >= 0, "gemm: bad arguments");
-  PNB_REQUIRE(!(flags & PNB_EPI_BIAS) || bias != nullptr, "gemm: bias flag without bias");
-  PNB_REQUIRE(!(flags & PNB_EPI_MASK) || mask_src != nullptr, "gemm: mask flag without mask source");
+  PNB_REQUIRE(M == 0 || !(flags & PNB_EPI_BIAS) || bias != nullptr, "gemm: bias flag without bias");
+  PNB_REQUIRE(M == 0 || !(flags & PNB_EPI_MASK) || mask_src != nullptr, "gemm: mask flag without mask source");
   PNB_REQUIRE(row_bias == nullptr || row_group > 0, "gemm: row_bias needs row_group");
   PNB_REQUIRE((M + BM - 1) / BM < (1ll << 31), "gemm: M too large");
   return 0;

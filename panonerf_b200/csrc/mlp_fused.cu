@@ -1551,7 +1551,7 @@ extern "C" int pnb_mlp_fused_fwd(long long M, int S, int C, const void* enc, int
                                  const float* bblob, const float* row_bias, int vb_mod, float* raw_den, float* raw_rgb,
                                  void* acts, float* g_enc, void* masks, int masks_per_tile, void* stream) {
   PNB_REQUIRE(M >= 0 && S >= 1 && C >= 1 && C <= 16 && vb_mod >= 0, "mlp_fused_fwd: bad sizes");
-  PNB_REQUIRE(enc && wblob && bblob && row_bias && raw_den && raw_rgb, "mlp_fused_fwd: null argument");
+  PNB_REQUIRE(M == 0 || (enc && wblob && bblob && row_bias && raw_den && raw_rgb), "mlp_fused_fwd: null argument");
   PNB_REQUIRE(ld_enc % 8 == 0 && ld_enc >= kEncDim && ((uintptr_t)enc % 16 == 0) && ((uintptr_t)wblob % 16 == 0) &&
                   ((uintptr_t)bblob % 16 == 0) && ((uintptr_t)row_bias % 16 == 0),
               "mlp_fused_fwd: enc / blobs / row_bias must be 16-byte aligned, ld_enc % 8 == 0");
@@ -1590,7 +1590,7 @@ extern "C" int pnb_mlp_fused_fwd_ipe(long long M, int S, int C, const float* mea
                                      float* raw_den, float* raw_rgb, float* g_enc, void* masks, void* scratch,
                                      void* stream) {
   PNB_REQUIRE(M >= 0 && S >= 1 && C >= 1 && C <= 16 && vb_mod >= 0, "mlp_fused_fwd_ipe: bad sizes");
-  PNB_REQUIRE(means && covs && wblob && bblob && row_bias && raw_den && raw_rgb && scratch,
+  PNB_REQUIRE(M == 0 || (means && covs && wblob && bblob && row_bias && raw_den && raw_rgb && scratch),
               "mlp_fused_fwd_ipe: null argument");
   PNB_REQUIRE(min_deg >= 0 && min_deg + 16 <= 31, "mlp_fused_fwd_ipe: IPE degrees must lie in [0, 31)");
   PNB_REQUIRE(((uintptr_t)wblob % 16 == 0) && ((uintptr_t)bblob % 16 == 0) && ((uintptr_t)row_bias % 16 == 0) &&
@@ -1618,7 +1618,7 @@ extern "C" int pnb_mlp_fused_fwd_ipe(long long M, int S, int C, const float* mea
 extern "C" int pnb_mlp_fused_bwd(long long M, int C, const void* wblob, const float* bblob, const float* d_rgb,
                                  const float* d_den, const void* masks, void* dz_planes, float* d_enc, void* stream) {
   PNB_REQUIRE(M >= 0 && C >= 1 && C <= 16, "mlp_fused_bwd: bad sizes");
-  PNB_REQUIRE(wblob && bblob && d_rgb && d_den && masks && dz_planes, "mlp_fused_bwd: null argument");
+  PNB_REQUIRE(M == 0 || (wblob && bblob && d_rgb && d_den && masks && dz_planes), "mlp_fused_bwd: null argument");
   PNB_REQUIRE(((uintptr_t)wblob % 16 == 0) && ((uintptr_t)bblob % 16 == 0) && ((uintptr_t)dz_planes % 128 == 0) &&
                   (d_enc == nullptr || (uintptr_t)d_enc % 16 == 0),
               "mlp_fused_bwd: misaligned argument");
@@ -1639,7 +1639,7 @@ extern "C" int pnb_mlp_fused_bwd(long long M, int C, const void* wblob, const fl
 extern "C" int pnb_mlp_fused_jadj(long long M, const void* u, int ld_u, const void* wblob, const void* masks,
                                   void* q_planes, void* stream) {
   PNB_REQUIRE(M >= 0, "mlp_fused_jadj: bad sizes");
-  PNB_REQUIRE(u && wblob && masks && q_planes, "mlp_fused_jadj: null argument");
+  PNB_REQUIRE(M == 0 || (u && wblob && masks && q_planes), "mlp_fused_jadj: null argument");
   PNB_REQUIRE(ld_u % 8 == 0 && ld_u >= kEncDim && ((uintptr_t)u % 16 == 0) && ((uintptr_t)wblob % 16 == 0) &&
                   ((uintptr_t)q_planes % 128 == 0),
               "mlp_fused_jadj: misaligned argument");

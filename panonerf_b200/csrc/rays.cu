@@ -764,7 +764,8 @@ extern "C" int pnb_ipe_cov_hess(int M, const float* means, const float* covs, in
 
 extern "C" int pnb_cast_rays_bwd(int R, int N, const float* t, const float* directions, const float* radii,
                                  const float* g_means, const float* g_covs, float* d_t, int accumulate, void* stream) {
-  PNB_REQUIRE(R >= 0 && N > 0 && t && directions && radii && d_t && (g_means || g_covs), "cast_rays_bwd: bad arguments");
+  PNB_REQUIRE(R >= 0 && N > 0 && (R == 0 || (t && directions && radii && d_t && (g_means || g_covs))),
+              "cast_rays_bwd: bad arguments");
   if (R == 0) return 0;
   const size_t smem = (size_t)8 * 2 * N * sizeof(float);
   PNB_REQUIRE(smem <= 200 * 1024, "cast_rays_bwd: N too large");

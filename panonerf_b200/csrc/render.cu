@@ -823,7 +823,7 @@ static int launch_resample_bwd(int R, int N, const float* t, const float* weight
 extern "C" int pnb_resample_bwd(int R, int N, const float* t, const float* weights, float padding, int blur_pool,
                                 const float* u, int u_ld, const float* g_new_t, float* d_weights, void* stream) {
   PNB_REQUIRE(R >= 0 && N > 0 && N <= 256 && (u_ld == 0 || u_ld >= N + 1), "resample_bwd: need 0 < N <= 256");
-  PNB_REQUIRE(t && weights && u && g_new_t && d_weights, "resample_bwd: null argument");
+  PNB_REQUIRE(R == 0 || (t && weights && u && g_new_t && d_weights), "resample_bwd: null argument");
   if (R == 0) return 0;
   cudaStream_t st = as_stream(stream);
   const int k = (N + 31) / 32;
@@ -838,9 +838,9 @@ extern "C" int pnb_resample_cast(int R, int N, const float* t, const float* weig
                                  const float* directions, const float* radii, float* means, float* covs,
                                  void* stream) {
   PNB_REQUIRE(R >= 0 && N > 0 && N <= 256 && (u_ld == 0 || u_ld >= N + 1), "resample: need 0 < N <= 256");
-  PNB_REQUIRE(t && weights && u && new_t, "resample: null argument");
+  PNB_REQUIRE(R == 0 || (t && weights && u && new_t), "resample: null argument");
   PNB_REQUIRE((means == nullptr) == (covs == nullptr), "resample: means and covs go together");
-  PNB_REQUIRE(means == nullptr || (origins && directions && radii), "resample: the fused cast needs the rays");
+  PNB_REQUIRE(R == 0 || means == nullptr || (origins && directions && radii), "resample: the fused cast needs the rays");
   if (R == 0) return 0;
   cudaStream_t st = as_stream(stream);
   if (N <= 64)

@@ -805,7 +805,8 @@ extern "C" int pnb_group_sum(long long M, int N, int group, const void* x, int l
 }
 
 extern "C" int pnb_pad_head_grad(long long M, int C, const float* src, void* dst_bf16, float* colsum, void* stream) {
-  PNB_REQUIRE(M >= 0 && C >= 1 && C <= 16 && src != nullptr && dst_bf16 != nullptr, "pad_head_grad: bad arguments");
+  PNB_REQUIRE(M >= 0 && C >= 1 && C <= 16 && (M == 0 || (src != nullptr && dst_bf16 != nullptr)),
+              "pad_head_grad: bad arguments");
   PNB_REQUIRE(((uintptr_t)dst_bf16 % 16) == 0, "pad_head_grad: dst must be 16-byte aligned");
   if (M == 0) return 0;
   pnb::pad_head_grad_kernel<<<grid_for(M * 8, 256, 8), 256, 0, as_stream(stream)>>>(M, C, src, (__nv_bfloat16*)dst_bf16, colsum);

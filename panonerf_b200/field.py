@@ -955,6 +955,11 @@ def radiance_field(means, covs, venc, params: Dict[str, torch.Tensor], *, precis
     if w0.shape[1] != 6 * (max_deg - min_deg):
         raise RuntimeError("IPE width does not match the first layer")
     R = means.shape[0]
+    if means.numel() == 0:                       # an empty batch: empty outputs of the right widths, nothing to launch
+        C = params["density_layer.weight"].shape[0]
+        tie = sum(p.sum() for p in params.values()) * 0.0      # keeps the outputs on the tape (zero gradients)
+        e = lambda ch: torch.zeros(R, samples_per_ray, ch, device=means.device, dtype=torch.float32) + tie
+        return e(params["color_layer.weight"].shape[0]), e(C), (e(3) if with_normals else None)
     plist = [params[n] for n in names]
     anchor = None
     if (cfg["grad_enabled"] and _use_fused(cfg, params)
@@ -970,8 +975,8 @@ def radiance_field(means, covs, venc, params: Dict[str, torch.Tensor], *, precis
         anchor = torch.empty(0, device=means.device, dtype=torch.float32, requires_grad=True)
         plist = []
     raw_rgb, raw_den, n_raw = _Field.apply(means, covs, venc, cfg, anchor, *plist)
-    raw_rgb = raw_rgb.view(R, samples_per_ray, -1)
-    raw_den = raw_den.view(R, samples_per_ray, -1)
+    raw_rgb = raw_rgb.view(R, samples_per_ray, raw_rgb.shape[-1])   # (explicit widths: R may be 0)
+    raw_den = raw_den.view(R, samples_per_ray, raw_den.shape[-1])
     if n_raw is not None:
         n_raw = n_raw.view(R, samples_per_ray, 3)
     return raw_rgb, raw_den, n_raw

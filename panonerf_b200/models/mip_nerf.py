@@ -154,7 +154,7 @@ class MipNeRF(_NerfBase):
             raw_rgb, raw_den, n_raw = self._field(means, covs, venc, means.shape[1], want_normals)
             R, S = means.shape[0], means.shape[1]
             comp_rgb, distance, acc, weights, _ = ops.act_composite(
-                raw_rgb.view(R * S, -1), raw_den.view(R * S, -1), t, rays.directions, white_bkgd, self.density_bias,
+                raw_rgb.view(R * S, raw_rgb.shape[-1]), raw_den.view(R * S, raw_den.shape[-1]), t, rays.directions, white_bkgd, self.density_bias,
                 self.rgb_padding, False)
             if want_normals:
                 normal, ort, _ = ops.normals_aggregate(n_raw, weights, rays.directions, None)

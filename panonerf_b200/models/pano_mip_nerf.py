@@ -35,7 +35,7 @@ class PanoMipNeRF(_NerfBase):
             raw_rgb, raw_den, n_raw = self._field(means, covs, venc, S, fine)
             C = raw_den.shape[-1]
             comp_rgb, distance, acc, weights, albedos = ops.act_composite(
-                raw_rgb.view(R * S, -1), raw_den.view(R * S, C), t, rays.directions, white_bkgd, self.density_bias,
+                raw_rgb.view(R * S, raw_rgb.shape[-1]), raw_den.view(R * S, C), t, rays.directions, white_bkgd, self.density_bias,
                 self.rgb_padding, C >= 5 and fine and enable_surf)
             normal = surface_rgb = albedo = diffuse = ort_loss = shading = None
             if fine:
@@ -53,7 +53,7 @@ class PanoMipNeRF(_NerfBase):
                                                              env.radii, env.near, env.far, Ne, t_rand)
                     lit_venc = ops.pos_enc(env.directions, self.deg_view)            # [D,27], one per env direction
                     e_rgb, e_den, _ = self._field(lit_means, lit_covs, lit_venc, Ne, False, venc_mod=D)
-                    env_rgb = ops.act_composite(e_rgb.view(R * D * Ne, -1), e_den.view(R * D * Ne, C), lit_t,
+                    env_rgb = ops.act_composite(e_rgb.view(R * D * Ne, e_rgb.shape[-1]), e_den.view(R * D * Ne, C), lit_t,
                                                 env.directions, False, self.density_bias, self.rgb_padding, False,
                                                 d_mod=D)[0].view(R, D, 3)
                     surface_rgb, shading = ops.shade(env_rgb, albedo, normal, env.directions,

@@ -514,3 +514,28 @@ def test_device_ray_feed_gathers_the_rays_of_its_pixels():
     full_gt = torch.cat([i.reshape(-1, 3) for i in imgs], 0).to(DEV)
     assert torch.equal(gt, full_gt[ids])
     assert int(ids.min()) >= 0 and int(ids.max()) < len(feed) and len(torch.unique(ids)) > 200
+
+
+def test_empty_batches():
+    """Zero rays: every stage returns empty tensors of the reference's shapes (PyTorch ops on empty tensors do), forward
+    and backward, including the MLP (both precisions) and a whole model forward."""
+    from panonerf_b200 import ops
+    from panonerf_b200.models import mip
+    from panonerf_b200.models.mip_nerf import MipNeRF
+    from panonerf_b200.datasets.base_datasets import Rays
+    z = lambda *s: torch.zeros(*s, device=DEV)
+    t, (m, c) = mip.sample_along_rays(z(0, 3), z(0, 3), z(0, 1), 16, z(0, 1), z(0, 1), False, False, "cone")
+    assert t.shape == (0, 17) and m.shape == (0, 16, 3) and c.shape == (0, 16, 3)
+    enc = mip.integrated_pos_enc((m, c), 0, 16)
+    assert enc.shape == (0, 16, 96)
+    comp, dist, acc, w = ops.composite(z(0, 16, 3), z(0, 16), t, z(0, 3), False)
+    assert comp.shape == (0, 3) and w.shape == (0, 16)
+    nt, (m2, c2) = mip.resample_along_rays(z(0, 3), z(0, 3), z(0, 1), t, w, False, "cone", True, 0.01)
+    assert nt.shape == (0, 17) and m2.shape == (0, 16, 3)
+    for prec in ("fp32", "bf16"):
+        model = MipNeRF(num_samples=16, rgb_activation="softplus", precision=prec).to(DEV)
+        rays = Rays(z(0, 3), z(0, 3), z(0, 3), z(0, 1), z(0, 1), z(0, 1), z(0, 1), z(0, 1))
+        out = model(rays=rays, randomized=False, white_bkgd=False, use_ort_loss=False)
+        assert out[1][0].shape == (0, 3)
+        (out[0][0].sum() + out[1][0].sum()).backward()
+        assert all(p.grad is None or float(p.grad.abs().max()) == 0.0 for p in model.mlp.parameters())
