@@ -206,11 +206,12 @@ def pdf_sample(bins, weights, num_samples: int, randomized: bool, u=None, return
     """models/mip.py:240-301.  `u` (if given) replaces the internal draw (deterministic: linspace(0,1-eps))."""
     eps = 1e-5
     wsum = torch.sum(weights, -1, keepdim=True)
-    padding = torch.clamp_min(eps - wsum, 0.0)
+    padding = torch.maximum(torch.zeros_like(wsum), eps - wsum)
     weights = weights + padding / weights.shape[-1]
     wsum = wsum + padding
     pdf = weights / wsum
-    cdf = torch.clamp_max(torch.cumsum(pdf[..., :-1], -1), 1.0)
+    cdf = torch.cumsum(pdf[..., :-1], -1)
+    cdf = torch.minimum(torch.ones_like(cdf), cdf)      # (minimum, not clamp: its tie rule is what autograd sees)
     z = torch.zeros(list(cdf.shape[:-1]) + [1])
     cdf = torch.cat([z, cdf, z + 1.0], -1)
     if u is None:

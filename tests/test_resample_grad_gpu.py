@@ -114,6 +114,8 @@ def test_resample_backward(R, N, randomized, padding):
     w = torch.rand(R, N, generator=g) ** 4
     w[1] = 0.0                                   # empty ray: weight sum below eps when padding is tiny
     w[2, 5:9] = w[2, 5]                          # ties in the blur-pool
+    w[3] = 0.0
+    w[3, 0] = 1.0                                # all mass in front: the cdf reaches 1 early (ties of min(1, cumsum))
     t = torch.sort(torch.rand(R, N + 1, generator=g) * 6, dim=1).values.contiguous()
     u = None
     if randomized:
