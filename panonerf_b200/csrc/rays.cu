@@ -78,7 +78,9 @@ __device__ __forceinline__ float strat_t(int i, int N, float nr, float fr, const
 // index division per sample (the flat-index version spent most of its instructions there).
 // STAGE: the Gaussians of a ray are staged in shared memory and leave as 16-byte rows (3 N floats per array, N % 4 == 0)
 // instead of 4-byte stores at a 12-byte lane stride, which hit every 32-byte sector from three instructions.
-template <bool STAGE>
+// MODE: 0 = every run-time option; 1 / 2 = the main rays' calls (one origin / direction / radius row per ray, linear
+// spacing), deterministic / randomized: the 64-bit index divisions and the option branches fold away at compile time.
+template <bool STAGE, int MODE>
 __global__ void __launch_bounds__(256)
 sample_cast_kernel(long long R, int N, const float* __restrict__ origins, int o_div,
                    const float* __restrict__ dirs, const float* __restrict__ radii,
@@ -95,9 +97,11 @@ sample_cast_kernel(long long R, int N, const float* __restrict__ origins, int o_
   // The nine per-ray scalars of the NEXT ray are requested before the current ray is worked on: a warp otherwise starts
   // every ray with a dependent ~700 ns load (ncu: long-scoreboard stalls dominated, 50 % occupancy could not hide them).
   float nxt[9];
+  if (MODE != 0) disparity = 0;
+  if (MODE == 1) t_rand = nullptr;
   auto fetch = [&](long long r) {
-    const long long rd = d_mod ? r % d_mod : r, ro = r / o_div;
-    const long long rdir = dir_mod ? r % dir_mod : r;  // (sample_each_points_hemisp: one direction per ray)
+    const long long rd = (MODE == 0 && d_mod) ? r % d_mod : r, ro = (MODE == 0 && o_div != 1) ? r / o_div : r;
+    const long long rdir = (MODE == 0 && dir_mod) ? r % dir_mod : r;  // (sample_each_points_hemisp: one direction per ray)
     nxt[0] = near_v[rd], nxt[1] = far_v[rd], nxt[2] = radii[rd];
 #pragma unroll
     for (int k = 0; k < 3; ++k) nxt[3 + k] = origins[3 * ro + k], nxt[6 + k] = dirs[3 * rdir + k];
@@ -641,14 +645,19 @@ static int launch_sample_cast(int R, int N, const float* origins, int o_div, con
   const size_t smem = (size_t)8 * 6 * N * sizeof(float);
   const bool stage = N % 4 == 0 && smem <= 48 * 1024 && ((uintptr_t)means % 16 == 0) && ((uintptr_t)covs % 16 == 0);
   const int grid = grid_for((long long)R * 32, 256, 8);
-  if (stage)
-    sample_cast_kernel<true><<<grid, 256, smem, as_stream(stream)>>>(R, N, origins, o_div, directions, radii, near_v,
-                                                                     far_v, d_mod, dir_mod, s_lin, t_rand, rand_ld,
-                                                                     disparity, t_out, means, covs);
-  else
-    sample_cast_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(R, N, origins, o_div, directions, radii, near_v,
-                                                                   far_v, d_mod, dir_mod, s_lin, t_rand, rand_ld,
-                                                                   disparity, t_out, means, covs);
+  const bool plain = o_div == 1 && d_mod == 0 && dir_mod == 0 && !disparity;
+#define PNB_LAUNCH_SC(STAGE_, MODE_)                                                                                 \
+  sample_cast_kernel<STAGE_, MODE_><<<grid, 256, (STAGE_) ? smem : 0, as_stream(stream)>>>(                           \
+      R, N, origins, o_div, directions, radii, near_v, far_v, d_mod, dir_mod, s_lin, t_rand, rand_ld, disparity, t_out, \
+      means, covs)
+  if (stage) {
+    if (plain && t_rand == nullptr) PNB_LAUNCH_SC(true, 1);
+    else if (plain) PNB_LAUNCH_SC(true, 2);
+    else PNB_LAUNCH_SC(true, 0);
+  } else {
+    PNB_LAUNCH_SC(false, 0);
+  }
+#undef PNB_LAUNCH_SC
   return finish("sample_cast");
 }
 
