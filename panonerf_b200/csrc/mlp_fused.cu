@@ -1240,7 +1240,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmEnc, const __grid_constan
           } else if (kFwd && epi == E_EXTRA) {
             rewrite_abuf<M_BIAS>(c, p, op, nullptr, op.bias_off);
           } else if (kFwd && epi == E_VIEW) {
-            rewrite_abuf<M_ROWBIAS_RELU>(c, p, op, p.row_bias + (p.vb_mod ? (m_safe / p.S) % p.vb_mod : m_safe / p.S) * kCondW, 0);
+            // (M < 2^31 is checked at launch: 32-bit divisions, not the ~100-instruction 64-bit subroutine, on the epilogue warps)
+            const unsigned ray = (unsigned)m_safe / (unsigned)p.S;
+            rewrite_abuf<M_ROWBIAS_RELU>(c, p, op, p.row_bias + (size_t)(p.vb_mod ? ray % (unsigned)p.vb_mod : ray) * kCondW, 0);
           } else if (P != P_FWD && epi == E_MASK) {
             rewrite_abuf<M_MASK>(c, p, op, nullptr, 0);
           } else if (P == P_BWD && epi == E_LIN) {

@@ -303,7 +303,7 @@ composite_bwd_kernel(long long R, int N, const float* __restrict__ rgb, const fl
   float* sQ = sW + N;                      // G_i * w_i
   const long long warp0 = blockIdx.x * (long long)kWarpsPerBlock + wib;
   for (long long r = warp0; r < R; r += (long long)gridDim.x * kWarpsPerBlock) {
-    long long rd = d_mod ? r % d_mod : r;
+    const long long rd = d_mod ? (long long)((unsigned)r % (unsigned)d_mod) : r;  // (R is an int: 32-bit modulo)
     float d0 = dirs[3 * rd], d1 = dirs[3 * rd + 1], d2 = dirs[3 * rd + 2];
     float dnorm = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
     const float* tr = t + r * (N + 1);
