@@ -100,8 +100,10 @@ sample_cast_kernel(long long R, int N, const float* __restrict__ origins, int o_
   if (MODE != 0) disparity = 0;
   if (MODE == 1) t_rand = nullptr;
   auto fetch = [&](long long r) {
-    const long long rd = (MODE == 0 && d_mod) ? r % d_mod : r, ro = (MODE == 0 && o_div != 1) ? r / o_div : r;
-    const long long rdir = (MODE == 0 && dir_mod) ? r % dir_mod : r;  // (sample_each_points_hemisp: one direction per ray)
+    // (R is an int at the C boundary: 32-bit divisions instead of the 64-bit subroutines)
+    const unsigned ru = (unsigned)r;
+    const long long rd = (MODE == 0 && d_mod) ? ru % (unsigned)d_mod : r, ro = (MODE == 0 && o_div != 1) ? ru / (unsigned)o_div : r;
+    const long long rdir = (MODE == 0 && dir_mod) ? ru % (unsigned)dir_mod : r;  // (sample_each_points_hemisp: one direction per ray)
     nxt[0] = near_v[rd], nxt[1] = far_v[rd], nxt[2] = radii[rd];
 #pragma unroll
     for (int k = 0; k < 3; ++k) nxt[3 + k] = origins[3 * ro + k], nxt[6 + k] = dirs[3 * rdir + k];

@@ -714,7 +714,7 @@ __global__ void group_sum_bf16x2_kernel(long long G, int N, int group, const __n
   const long long total = G * slabs;
   for (long long w = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5); w < total;
        w += (long long)gridDim.x * (blockDim.x >> 5)) {
-    const long long g = w / slabs;
+    const long long g = (long long)((unsigned)w / (unsigned)slabs);  // (total < 2^31, checked by the launcher)
     const int col = (int)(w - g * slabs) * 64 + 8 * c8;
     const __nv_bfloat16* base = x + g * group * (long long)ldx + col;
     float s[8];
@@ -793,7 +793,8 @@ extern "C" int pnb_group_sum(long long M, int N, int group, const void* x, int l
   PNB_REQUIRE(M >= 0 && N > 0 && group > 0 && M % group == 0, "group_sum: M must be a multiple of group");
   if (M == 0) return 0;
   long long G = M / group;
-  if (dtype == PNB_BF16 && N % 64 == 0 && ldx % 8 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)out % 16) == 0) {
+  if (dtype == PNB_BF16 && N % 64 == 0 && ldx % 8 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)out % 16) == 0 &&
+      G * (N / 64) < (1ll << 31)) {
     const long long warps = G * (N / 64);
     const int grid = grid_for(warps * 32, 256, 8);
     pnb::group_sum_bf16x2_kernel<<<grid, 256, 0, as_stream(stream)>>>(G, N, group, (const __nv_bfloat16*)x, ldx, out);
