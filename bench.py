@@ -150,7 +150,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=300))
     torch.manual_seed(4 + rank)
     system = make_system(dev)
     opt = system.configure_optimizers()
@@ -389,7 +389,7 @@ def run_render(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=300))
     system = make_system(dev, num_samples=args.num_samples)
     H, W = args.render_hw
     line = measure_render(system, dev, world, rank, local, H, W, args.render_chunk, args.steps, args.warmup)
