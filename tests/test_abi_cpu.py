@@ -177,3 +177,32 @@ def test_bench_rank_conditional_work_has_no_collectives():
               if isinstance(node, ast.If) and any(isinstance(c, ast.Call) and getattr(c.func, "id", "") == "measure_c1"
                                                   for b in node.body for c in ast.walk(b))]
     assert "world == 1" in guards, guards
+
+
+def test_mip_lr_decay_scheduler_class_matches_the_reference_class():
+    """utils.lr_schedule.MipLRDecay: same constructor, same rates as the upstream class on a stock Adam, step by step."""
+    import warnings
+    from oracle import ref_harness
+    from panonerf_b200.utils.lr_schedule import MipLRDecay
+    if not ref_harness.available():
+        pytest.skip("reference tree not present (GPU box)")
+    ns = ref_harness.load()
+    ref_cls = ns.lr_schedule.MipLRDecay if hasattr(ns, "lr_schedule") else None
+    if ref_cls is None:
+        import importlib
+        ref_cls = importlib.import_module("utils.lr_schedule").MipLRDecay
+    rates = []
+    for cls in (MipLRDecay, ref_cls):
+        p = torch.nn.Parameter(torch.zeros(3))
+        opt = torch.optim.Adam([p], lr=5e-4)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            sch = cls(opt, 5e-4, 5e-6, 2000, 250, 0.01)
+            seq = []
+            for _ in range(400):
+                seq.append(opt.param_groups[0]["lr"])
+                opt.step()
+                sch.step()
+        rates.append(seq)
+    for a, b in zip(*rates):
+        assert abs(a - b) <= 1e-12 * max(abs(b), 1e-12), (a, b)
