@@ -432,7 +432,9 @@ composite_bwd_kernel(long long R, int N, const float* __restrict__ rgb, const fl
 // entries (shared-memory atomics), through min(1, cumsum) (suffix sums; torch's tie rule of `minimum`: half at
 // equality), the normalisation (with the 1e-5 padding branch) and the blur-pool's maxima (torch.maximum: the larger
 // operand takes the gradient, ties split) into dL/d weights [R,N] (written to `d_weights`).  Bins and u carry no gradient.
-template <int KMAX, bool BWD>
+// FULL: N == 32 * KMAX exactly (64, 128, 256: the configurations of the YAMLs), blur-pool on, no index output: the
+// ragged-row / short-row paths and the bounds tests of the lane loops fold away at compile time (same arithmetic).
+template <int KMAX, bool BWD, bool FULL = false>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 resample_kernel(long long R, int N, const float* __restrict__ t, const float* __restrict__ weights, float padding,
                 int blur_pool, const float* __restrict__ u, int u_ld, float* __restrict__ new_t,
@@ -448,9 +450,10 @@ resample_kernel(long long R, int N, const float* __restrict__ t, const float* __
   float* sg = sb + N + 2;                   // staged Gaussians [3N | 3N] (16-byte aligned: the stride is a multiple of 4)
   float* sdc = sb + N + 2;                  // BWD: dL/d cdf (N+1), later dL/d (blurred weight) (N)
   float* smk = sdc + N + 2;                 // BWD: pass factor of min(1, cumsum) per cdf entry (N+1)
-  const int K = (N + 31) >> 5;              // samples per lane
-  const int vec = N >> 3, ilp = vec >> 2;   // ATen: 8-float vectors, 4 interleaved accumulators
-  const bool ragged = (N & 31) != 0;
+  if (FULL) N = 32 * KMAX, blur_pool = 1, inds_out = nullptr;
+  const int K = FULL ? KMAX : (N + 31) >> 5;  // samples per lane
+  const int vec = N >> 3, ilp = vec >> 2;     // ATen: 8-float vectors, 4 interleaved accumulators
+  const bool ragged = FULL ? false : (N & 31) != 0;
   const long long warp0 = blockIdx.x * (long long)kWarpsPerBlock + wib;
   for (long long r = warp0; r < R; r += (long long)gridDim.x * kWarpsPerBlock) {
     const float* wr = weights + r * N;
@@ -483,7 +486,7 @@ resample_kernel(long long R, int N, const float* __restrict__ t, const float* __
       if (k < ilp) local += blur[k];  // accumulator lane/8, vector lane%8: elements i4*32 + lane, i4 ascending
     }
     float wsum;
-    if (N < 8) {  // ATen scalar path: 4 interleaved scalar accumulators, leftovers into accumulator 0
+    if (!FULL && N < 8) {  // ATen scalar path: 4 interleaved scalar accumulators, leftovers into accumulator 0
       __syncwarp();
       float p4[4] = {0.f, 0.f, 0.f, 0.f};
       const int q4 = N >> 2;
@@ -802,6 +805,13 @@ static int launch_resample(int R, int N, const float* t, const float* weights, f
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(resample_kernel<KMAX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int grid = grid_for((long long)R * 32, kWarpsPerBlock * 32, 4);
+  if (N == 32 * KMAX && blur_pool && inds == nullptr) {
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(resample_kernel<KMAX, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    resample_kernel<KMAX, false, true><<<grid, kWarpsPerBlock * 32, smem, st>>>(
+        R, N, t, weights, padding, blur_pool, u, u_ld, new_t, inds, origins, dirs, radii, means, covs, stage, nullptr);
+    return finish("resample");
+  }
   resample_kernel<KMAX, false><<<grid, kWarpsPerBlock * 32, smem, st>>>(
       R, N, t, weights, padding, blur_pool, u, u_ld, new_t, inds, origins, dirs, radii, means, covs, stage, nullptr);
   return finish("resample");
