@@ -150,6 +150,40 @@ sample_cast_kernel(long long R, int N, const float* __restrict__ origins, int o_
   }
 }
 
+// Short rays (the env rays' N = 10: a warp-per-ray walk would idle 22 of 32 lanes): one thread per sample, the per-ray
+// scalars come through L1 (a ray's samples sit in neighbouring lanes), same device functions - same bits.
+__global__ void __launch_bounds__(256)
+sample_cast_short_kernel(unsigned total, int N, const float* __restrict__ origins, int o_div,
+                         const float* __restrict__ dirs, const float* __restrict__ radii,
+                         const float* __restrict__ near_v, const float* __restrict__ far_v, int d_mod, int dir_mod,
+                         const float* __restrict__ s_lin, const float* __restrict__ t_rand, int rand_ld,
+                         int disparity, float* __restrict__ t_out, float* __restrict__ means,
+                         float* __restrict__ covs) {
+  for (unsigned s = blockIdx.x * blockDim.x + threadIdx.x; s < total; s += gridDim.x * blockDim.x) {
+    const unsigned r = s / (unsigned)N;
+    const int i = (int)(s - r * (unsigned)N);
+    const unsigned rd = d_mod ? r % (unsigned)d_mod : r, ro = o_div != 1 ? r / (unsigned)o_div : r;
+    const unsigned rdir = dir_mod ? r % (unsigned)dir_mod : r;
+    const float nr = near_v[rd], fr = far_v[rd];
+    const float o[3] = {origins[3 * ro], origins[3 * ro + 1], origins[3 * ro + 2]};
+    const float d[3] = {dirs[3 * rdir], dirs[3 * rdir + 1], dirs[3 * rdir + 2]};
+    const float* rnd = t_rand ? t_rand + (size_t)rand_ld * r : nullptr;
+    const RayGeom geom = ray_geom(o, d, radii[rd]);
+    const float t0 = strat_t(i, N, nr, fr, s_lin, rnd, disparity);
+    const float t1 = strat_t(i + 1, N, nr, fr, s_lin, rnd, disparity);
+    float* trow = t_out + (size_t)r * (N + 1);
+    trow[i] = t0;
+    if (i == N - 1) trow[N] = t1;
+    float m[3], c[3];
+    frustum_gaussian(t0, t1, geom, m, c);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      means[3 * (size_t)s + k] = m[k];
+      covs[3 * (size_t)s + k] = c[k];
+    }
+  }
+}
+
 __global__ void cast_rays_kernel(long long R, int N, const float* __restrict__ t, const float* __restrict__ origins,
                                  int o_div, const float* __restrict__ dirs, const float* __restrict__ radii, int d_mod,
                                  float* __restrict__ means, float* __restrict__ covs) {
@@ -652,6 +686,13 @@ static int launch_sample_cast(int R, int N, const float* origins, int o_div, con
   sample_cast_kernel<STAGE_, MODE_><<<grid, 256, (STAGE_) ? smem : 0, as_stream(stream)>>>(                           \
       R, N, origins, o_div, directions, radii, near_v, far_v, d_mod, dir_mod, s_lin, t_rand, rand_ld, disparity, t_out, \
       means, covs)
+  if (N <= 16 && (long long)R * N < (1ll << 31)) {
+    const unsigned total = (unsigned)R * (unsigned)N;
+    sample_cast_short_kernel<<<grid_for((long long)total, 256, 8), 256, 0, as_stream(stream)>>>(
+        total, N, origins, o_div, directions, radii, near_v, far_v, d_mod, dir_mod, s_lin, t_rand, rand_ld, disparity,
+        t_out, means, covs);
+    return finish("sample_cast");
+  }
   if (stage) {
     if (plain && t_rand == nullptr) PNB_LAUNCH_SC(true, 1);
     else if (plain) PNB_LAUNCH_SC(true, 2);
