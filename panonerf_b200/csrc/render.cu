@@ -700,6 +700,8 @@ resample_kernel(long long R, int N, const float* __restrict__ t, const float* __
 }  // namespace pnb
 
 using namespace pnb;
+// CTAs queued per SM by the warp-per-ray kernels (resampling, compositing backward): 4 -> 16 measured -7 % on the resampler
+static int pnb_rays_ctas() { return 16; }
 
 template <bool ACT>
 static int launch_composite_fwd(int R, int N, const float* rgb, const float* density, const float* t,
@@ -768,7 +770,7 @@ extern "C" int pnb_composite_bwd(int R, int N, const float* rgb, const float* de
   PNB_REQUIRE(smem <= 200 * 1024, "composite_bwd: N too large for the per-warp shared-memory staging");
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(composite_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  int grid = grid_for((long long)R * 32, kWarpsPerBlock * 32, 4);
+  int grid = grid_for((long long)R * 32, kWarpsPerBlock * 32, pnb_rays_ctas());
   composite_bwd_kernel<false><<<grid, kWarpsPerBlock * 32, smem, as_stream(stream)>>>(
       R, N, rgb, density, t, dirs, d_mod, white_bkgd, g_comp, g_dist, g_acc, g_weights, d_rgb, d_density,
       ActArgs{1, 0.f, 0.f, nullptr}, nullptr, nullptr);
@@ -789,7 +791,7 @@ extern "C" int pnb_act_composite_bwd(int R, int N, int C, const float* raw_rgb, 
   PNB_REQUIRE(smem <= 200 * 1024, "act_composite_bwd: N too large for the per-warp shared-memory staging");
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(composite_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  int grid = grid_for((long long)R * 32, kWarpsPerBlock * 32, 4);
+  int grid = grid_for((long long)R * 32, kWarpsPerBlock * 32, pnb_rays_ctas());
   composite_bwd_kernel<true><<<grid, kWarpsPerBlock * 32, smem, as_stream(stream)>>>(
       R, N, raw_rgb, raw_den, t, dirs, d_mod, white_bkgd, g_comp, g_dist, g_acc, g_weights, d_raw_rgb, d_raw_den,
       ActArgs{C, density_bias, rgb_padding, nullptr}, g_albedo, d_t);
@@ -804,7 +806,7 @@ static int launch_resample(int R, int N, const float* t, const float* weights, f
   const size_t smem = (size_t)kWarpsPerBlock * (3 * N + 4 + (stage ? 6 * N : 0)) * sizeof(float);
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(resample_kernel<KMAX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  const int grid = grid_for((long long)R * 32, kWarpsPerBlock * 32, 4);
+  const int grid = grid_for((long long)R * 32, kWarpsPerBlock * 32, pnb_rays_ctas());
   if (N == 32 * KMAX && blur_pool && inds == nullptr) {
     if (smem > 48 * 1024)
       cudaFuncSetAttribute(resample_kernel<KMAX, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -823,7 +825,7 @@ static int launch_resample_bwd(int R, int N, const float* t, const float* weight
   const size_t smem = (size_t)kWarpsPerBlock * (3 * N + 4 + 2 * N + 4) * sizeof(float);
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(resample_kernel<KMAX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  const int grid = grid_for((long long)R * 32, kWarpsPerBlock * 32, 4);
+  const int grid = grid_for((long long)R * 32, kWarpsPerBlock * 32, pnb_rays_ctas());
   resample_kernel<KMAX, true><<<grid, kWarpsPerBlock * 32, smem, st>>>(
       R, N, t, weights, padding, blur_pool, u, u_ld, const_cast<float*>(g_new_t), nullptr, nullptr, nullptr, nullptr,
       nullptr, nullptr, 0, d_weights);
