@@ -15,6 +15,7 @@ One JSON line is printed by rank 0.  `--impl reference` times the reference algo
 import argparse
 import datetime
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -99,15 +100,28 @@ class ClockSampler(threading.Thread):
 # synthetic inputs
 # ----------------------------------------------------------------------------------------------------------------
 def host_batch(rank, n_rays):
-    """Host-side (pinned) ray batch + HDR ground truth, built from the oracle's equirect generator once."""
-    from oracle import panonerf_oracle as O            # input synthesis only; never on the measured path
+    """Host-side (pinned) ray batch + HDR ground truth: rays of the 256 x 512 grid from the package's own equirect
+    generator (the GPU arm does not touch oracle/), a seeded random subset, copied back to pinned host memory once."""
+    from panonerf_b200.datasets.pano_datasets import generate_rays
     h, w = GRID_HW
-    rays = O.equirect_rays(h, w, camera(), 0.0, 10.0)
+    rays = generate_rays(h, w, camera(), 0.0, 10.0, torch.device("cuda", torch.cuda.current_device()))
     g = torch.Generator().manual_seed(rank)
-    perm = torch.randperm(h * w, generator=g)[:n_rays]
-    packed = torch.cat([getattr(rays, k)[perm] for k in O.Rays._fields], dim=1).contiguous()   # [n, 14]
+    perm = torch.randperm(h * w, generator=g)[:n_rays].to(rays.origins.device)
+    packed = torch.cat([x[perm] for x in rays], dim=1).contiguous().cpu()                     # [n, 14]
     gt = torch.rand(n_rays, 3, generator=g) * 2
     return packed.pin_memory(), gt.pin_memory()
+
+
+def synth_weights(mlp, seed=4):
+    """Deterministic Xavier-uniform-like weights for random-init benchmarks, drawn from a CPU generator in state-dict
+    order (the same numbers oracle.synth_state_dict hands the CPU arm: same order, shapes, bounds and generator)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for k, v in mlp.state_dict().items():
+        s = tuple(v.shape)
+        bound = math.sqrt(6.0 / (s[0] + s[1])) if k.endswith("weight") else 0.05
+        sd[k] = (torch.rand(s, generator=g) * 2 - 1) * bound
+    return sd
 
 
 def unpack_rays(packed):
@@ -121,7 +135,6 @@ def unpack_rays(packed):
 
 
 def make_system(device, precision="bf16", seed=4, num_samples=None):
-    from oracle import panonerf_oracle as O            # deterministic weight factory (checksummed in the tests)
     from panonerf_b200.systems.base_system import default_hparams
     from panonerf_b200.systems.panonerf_system import PanoNeRFSystem
     from panonerf_b200.datasets.pano_datasets import generate_lit_rays, pixel_radius
@@ -130,7 +143,7 @@ def make_system(device, precision="bf16", seed=4, num_samples=None):
     if num_samples:
         hp["nerf.num_samples"] = int(num_samples)
     system = PanoNeRFSystem(hp).to(device)
-    system.mip_nerf.mlp.load_state_dict(O.synth_state_dict(seed=seed, width=256, c_density=5))
+    system.mip_nerf.mlp.load_state_dict(synth_weights(system.mip_nerf.mlp, seed))
     radius = pixel_radius(GRID_HW[0], GRID_HW[1], camera(), device)
     system.env_rays = generate_lit_rays(radius, num=10, device=device)
     return system
@@ -437,19 +450,19 @@ def measure_c1(dev, steps=10):
     """BASELINE.json configs[0] on the GPU: configs/mipnerf.yaml training step (MipNeRF, C = 1 density channel, no ort
     loss), 4096 rays of a 64 x 128 equirect grid, 128 coarse + 128 fine samples, forward + backward + Adam, eager (no
     CUDA graph).  The reference runs this configuration in fp32 on the CPU (~27 s per step on 8 cores)."""
-    from oracle import panonerf_oracle as O            # input / weight synthesis only
+    from panonerf_b200.datasets.pano_datasets import generate_rays
     from panonerf_b200.systems.base_system import default_hparams
     from panonerf_b200.systems.mipnerf_system import MipNeRFSystem
     n, ns = 4096, 128
     hp = default_hparams("mipnerf", precision="bf16")
     hp.update({"nerf.num_samples": ns, "train.randomized": True})
     system = MipNeRFSystem(hp).to(dev)
-    system.mip_nerf.mlp.load_state_dict(O.synth_state_dict(seed=4, width=256, c_density=1))
+    system.mip_nerf.mlp.load_state_dict(synth_weights(system.mip_nerf.mlp, 4))
     opt = system.configure_optimizers()
-    rays = O.equirect_rays(64, 128, camera(), 0.0, 10.0)
+    rays = generate_rays(64, 128, camera(), 0.0, 10.0, dev)
     g = torch.Generator().manual_seed(0)
     from panonerf_b200.datasets.base_datasets import Rays
-    rays_d = Rays(*[getattr(rays, k)[:n].contiguous().to(dev) for k in O.Rays._fields])
+    rays_d = Rays(*[x[:n].contiguous() for x in rays])
     gt_d = (torch.rand(n, 3, generator=g) * 2).to(dev)
 
     def step():
